@@ -1,0 +1,203 @@
+/* libtokamak_b200 -- C-ABI of the B200-native proving core for Tokamak zk-EVM.
+ *
+ * Drop-in boundary for the data-parallel hot path of packages/backend (reference paths below are
+ * relative to /root/reference/packages/backend/): the BLS12-381 G1 MSM behind every commitment
+ * and the bivariate polynomial engine of libs (DensePolynomialExt).  Each entry point names the
+ * reference interface it replaces.  A thin Rust `-sys` crate binds these symbols 1:1
+ * (see INTEGRATION.md); tests bind them with ctypes.
+ *
+ * Conventions
+ *  - every function returns int32_t status: 0 = OK, negative = tkm_status; tkm_last_error()
+ *    returns a thread-local message.  No C++ exception or abort crosses this boundary
+ *    (the reference panics/unwraps eIcicleError; the Rust shim turns a non-zero status into panic!).
+ *  - byte formats at the boundary are the reference's: Fr = 32-byte little-endian canonical,
+ *    G1 affine = x||y, 2 x 48-byte little-endian canonical, all-zero = identity
+ *    (libs/src/iotools/mod.rs:1786-1815,1969-1980; group_structures/mod.rs:889-893).
+ *  - "host" pointers are ordinary host memory; "dev" pointers are CUDA device pointers owned by
+ *    the caller (or by an opaque handle).  Device-resident field data is in Montgomery form.
+ *  - a context is bound to one device and one stream and is not thread-safe (the reference has
+ *    the same rule: .cargo/config.toml:5 RUST_TEST_THREADS=1).
+ *  - the CUDA kernels are the only implementation: there is no CPU fallback.
+ */
+#ifndef TOKAMAK_B200_H
+#define TOKAMAK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TKM_OK = 0,
+  TKM_ERR_INVALID_ARGUMENT = -1, /* eIcicleError::InvalidArgument */
+  TKM_ERR_ALLOCATION = -2,       /* eIcicleError::AllocationFailed / OutOfMemory */
+  TKM_ERR_DOMAIN = -3,           /* NTT domain missing or too small (bivariate_polynomial/mod.rs:1437-1445) */
+  TKM_ERR_CUDA = -4,             /* any CUDA runtime failure */
+  TKM_ERR_NO_DEVICE = -5,        /* no usable CUDA device: there is deliberately no CPU fallback */
+  TKM_ERR_INTERNAL = -6
+} tkm_status;
+
+typedef struct tkm_ctx tkm_ctx;   /* device + stream + NTT domain + scratch */
+typedef struct tkm_poly tkm_poly; /* device-resident bivariate polynomial (DensePolynomialExt) */
+typedef struct tkm_crs tkm_crs;   /* device-resident G1 base table (sigma_1.xy_powers or a sparse table) */
+
+enum { TKM_FORWARD = 0, TKM_INVERSE = 1 };                  /* NTTDir::kForward / kInverse */
+enum { TKM_OP_ADD = 0, TKM_OP_SUB = 1, TKM_OP_MUL = 2, TKM_OP_DIV = 3 }; /* VecOps::add/sub/mul/div */
+
+const char *tkm_last_error(void);
+const char *tkm_version(void);
+
+/* ---- context: replaces utils::check_device (libs/src/utils/mod.rs:88-110) ------------------ */
+int32_t tkm_ctx_create(int32_t device_ordinal, tkm_ctx **out);
+int32_t tkm_ctx_destroy(tkm_ctx *ctx);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own. */
+int32_t tkm_ctx_set_stream(tkm_ctx *ctx, void *cuda_stream);
+int32_t tkm_ctx_sync(tkm_ctx *ctx);
+
+/* ---- raw device memory (DeviceVec::device_malloc / copy_from_host / copy_to_host) ----------- */
+int32_t tkm_dev_alloc(tkm_ctx *ctx, size_t bytes, void **out_dev);
+int32_t tkm_dev_free(tkm_ctx *ctx, void *dev);
+int32_t tkm_memcpy_h2d(tkm_ctx *ctx, void *dev, const void *host, size_t bytes);
+int32_t tkm_memcpy_d2h(tkm_ctx *ctx, void *host, const void *dev, size_t bytes);
+
+/* ---- NTT domain: init_ntt_domain_for_size / ntt::initialize_domain / release_domain /
+ *      get_root_of_unity (libs/src/bivariate_polynomial/mod.rs:33-55, :505) --------------------- */
+int32_t tkm_ntt_domain_init(tkm_ctx *ctx, uint32_t log2_size);
+int32_t tkm_ntt_domain_release(tkm_ctx *ctx);
+int32_t tkm_ntt_domain_log2(tkm_ctx *ctx, int32_t *out_log2); /* -1 when not initialised */
+int32_t tkm_root_of_unity(uint32_t log2_n, uint8_t out32[32]);
+
+/* ---- Fr vectors on the device (Montgomery form) ------------------------------------------------ */
+/* canonical <-> Montgomery, in place allowed.  (ICICLE hides this inside ScalarField.) */
+int32_t tkm_fr_to_mont(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
+int32_t tkm_fr_from_mont(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
+/* VecOps::{add,sub,mul,div} (libs/src/vector_operations/mod.rs:19-141); div uses inv(0)=0. */
+int32_t tkm_fr_vec_op(tkm_ctx *ctx, int32_t op, const void *dev_a, const void *dev_b, void *dev_out, size_t n);
+/* VecOps::scalar_mul: out = s * a, s = 32-byte canonical host scalar. */
+int32_t tkm_fr_vec_scale(tkm_ctx *ctx, const uint8_t s32[32], const void *dev_a, void *dev_out, size_t n);
+/* VecOps::inv, batched (Montgomery trick in-kernel), inv(0)=0 (bivariate_polynomial/mod.rs:2180). */
+int32_t tkm_fr_vec_inv(tkm_ctx *ctx, const void *dev_a, void *dev_out, size_t n);
+/* Host-buffer forms of the same ops (HostSlice in, HostSlice out; canonical bytes). */
+int32_t tkm_fr_vec_op_host(tkm_ctx *ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+
+/* ---- bivariate NTT: DensePolynomialExt::_biNTT (libs/src/bivariate_polynomial/mod.rs:1422-1478)
+ * Row-major, X = row, Y = contiguous column; natural order in and out; inverse includes 1/(x*y);
+ * coset_x / coset_y: NULL (= 1) or a 32-byte canonical host scalar per axis; forward scales
+ * coefficient (i,j) by gx^i gy^j first, inverse scales by gx^-i gy^-j last (libs/src/tests.rs:134-180).
+ * dev_in may equal dev_out. */
+int32_t tkm_bintt(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t x_size, size_t y_size, int32_t dir,
+                  const uint8_t *coset_x32, const uint8_t *coset_y32);
+/* Same with host buffers in canonical form (the HostSlice path of ntt::ntt): H2D, transform, D2H. */
+int32_t tkm_bintt_host(tkm_ctx *ctx, const uint8_t *in, uint8_t *out, size_t x_size, size_t y_size, int32_t dir,
+                       const uint8_t *coset_x32, const uint8_t *coset_y32);
+/* ntt::ntt with NTTConfig{batch_size, columns_batch} (used by tests.rs:519-588): `batch` vectors of
+ * length n, row batch (element j of vector b at b*n+j) or column batch (at j*batch+b). */
+int32_t tkm_ntt_batch(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n, size_t batch, int32_t columns_batch,
+                      int32_t dir, const uint8_t *coset32);
+
+/* ---- G1 MSM: msm::msm with MSMConfig::default() (libs/src/iotools/mod.rs:2093-2099;
+ *      group_structures/mod.rs:108-114,135-141) ---------------------------------------------------- */
+/* Host scalars (n x 32 B canonical), host affine bases (n x 96 B canonical) -> one affine point (96 B). */
+int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint8_t out96[96]);
+/* Device-resident: scalars n x 8 u32 (Montgomery if scalars_mont != 0, else canonical),
+ * bases = device table in Montgomery form (from tkm_g1_bases_to_mont or a tkm_crs). */
+int32_t tkm_msm_g1(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, const void *dev_bases_mont, size_t n,
+                   uint8_t out96[96]);
+/* Canonical affine bytes on the device -> Montgomery-form base table (in place allowed). */
+int32_t tkm_g1_bases_to_mont(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
+/* Strided rectangle (the trimmed (deg_x+1) x (deg_y+1) rectangle encode_poly commits,
+ * iotools/mod.rs:2061-2088): scalar (i,j) at dev_scalars[i*scalar_row_stride + j],
+ * base (i,j) at bases[i*base_row_stride + j], i < rows, j < cols. */
+int32_t tkm_msm_g1_rect(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, size_t scalar_row_stride,
+                        const void *dev_bases_mont, size_t base_row_stride, size_t rows, size_t cols,
+                        uint8_t out96[96]);
+/* Sparse-gather MSM (msm_g1_bases over gathered CRS rows, group_structures/mod.rs:127-300):
+ * result = sum_k scalars[k] * table[idx[k]].  dev_idx: n x u32. */
+int32_t tkm_msm_g1_indexed(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, const void *dev_bases_mont,
+                           const void *dev_idx, size_t n, uint8_t out96[96]);
+/* N independent scalar multiples of one base: msm::msm with batch_size = N over a generator vector
+ * (from_coef_vec_to_g1serde_vec, iotools/mod.rs:1113-1135).  out: n x 96 B canonical on the device. */
+int32_t tkm_g1_fixed_base_mul(tkm_ctx *ctx, const uint8_t base96[96], const void *dev_scalars, int32_t scalars_mont,
+                              size_t n, void *dev_out_affine);
+/* G1serde ops (group_structures/mod.rs:895-947): out = a + b ; out = k * a.  Host bytes. */
+int32_t tkm_g1_add(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t b96[96], uint8_t out96[96]);
+int32_t tkm_g1_mul(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t k32[32], uint8_t out96[96]);
+
+/* ---- CRS tables: Sigma1.xy_powers and friends (libs/src/group_structures/mod.rs:361-394;
+ *      archived form iotools/mod.rs:1701-1783) ------------------------------------------------------- */
+/* Upload rows*cols canonical affine points (row-major, index cols*h + i <-> x^h y^i) once. */
+int32_t tkm_crs_upload(tkm_ctx *ctx, const uint8_t *points96, size_t rows, size_t cols, tkm_crs **out);
+/* Wrap points already on the device in canonical form (converted in place to Montgomery). */
+int32_t tkm_crs_from_device(tkm_ctx *ctx, void *dev_points, size_t rows, size_t cols, int32_t take_ownership,
+                            tkm_crs **out);
+int32_t tkm_crs_free(tkm_ctx *ctx, tkm_crs *crs);
+int32_t tkm_crs_device_ptr(tkm_crs *crs, void **out_dev, size_t *rows, size_t *cols);
+
+/* ---- device-resident bivariate polynomial: DensePolynomialExt
+ *      (libs/src/bivariate_polynomial/mod.rs:112-118 and the BivariatePolynomial trait :1283-1416) -- */
+/* from_coeffs (:1527-1551): sizes must be powers of two; coeffs canonical host bytes. */
+int32_t tkm_poly_from_coeffs_host(tkm_ctx *ctx, const uint8_t *coeffs, size_t x_size, size_t y_size, tkm_poly **out);
+/* from_rou_evals (:1615-1644). */
+int32_t tkm_poly_from_evals_host(tkm_ctx *ctx, const uint8_t *evals, size_t x_size, size_t y_size,
+                                 const uint8_t *coset_x32, const uint8_t *coset_y32, tkm_poly **out);
+int32_t tkm_poly_zero(tkm_ctx *ctx, size_t x_size, size_t y_size, tkm_poly **out);
+int32_t tkm_poly_clone(tkm_ctx *ctx, const tkm_poly *p, tkm_poly **out); /* Clone (:520-530) */
+int32_t tkm_poly_free(tkm_ctx *ctx, tkm_poly *p);
+int32_t tkm_poly_shape(const tkm_poly *p, size_t *x_size, size_t *y_size);
+int32_t tkm_poly_device_ptr(tkm_poly *p, void **out_dev); /* Montgomery form, row-major */
+/* copy_coeffs (:1676-1682) / to_rou_evals (:1646-1674) into canonical host bytes. */
+int32_t tkm_poly_copy_coeffs_host(tkm_ctx *ctx, const tkm_poly *p, uint8_t *out);
+int32_t tkm_poly_to_evals_host(tkm_ctx *ctx, const tkm_poly *p, const uint8_t *coset_x32, const uint8_t *coset_y32,
+                               uint8_t *out);
+/* In-place transforms between coefficient and evaluation form on the device buffer. */
+int32_t tkm_poly_ntt_inplace(tkm_ctx *ctx, tkm_poly *p, int32_t dir, const uint8_t *coset_x32,
+                             const uint8_t *coset_y32);
+/* find_degree (:1480-1515): (-1,-1) for the zero polynomial. */
+int32_t tkm_poly_find_degree(tkm_ctx *ctx, const tkm_poly *p, int64_t *x_degree, int64_t *y_degree);
+/* resize (:1784-1806): crop / zero-pad to the next powers of two of (target_x, target_y). */
+int32_t tkm_poly_resize(tkm_ctx *ctx, tkm_poly *p, size_t target_x, size_t target_y);
+/* optimize_size (:1808-1818). */
+int32_t tkm_poly_optimize_size(tkm_ctx *ctx, tkm_poly *p);
+/* mul_monomial (:1820-1844): multiply by X^ex Y^ey (new polynomial). */
+int32_t tkm_poly_mul_monomial(tkm_ctx *ctx, const tkm_poly *p, size_t ex, size_t ey, tkm_poly **out);
+/* out = a*ca + b*cb on the max power-of-two shape (operator impls :532-1281 and poly_comb!,
+ * prove/src/lib.rs:30-38, fused: no host resize/clone).  ca/cb: 32-byte canonical or NULL (= 1). */
+int32_t tkm_poly_axpby(tkm_ctx *ctx, const tkm_poly *a, const uint8_t *ca32, const tkm_poly *b, const uint8_t *cb32,
+                       tkm_poly **out);
+/* p(0,0) += s  (poly +/- scalar, :975-1020). */
+int32_t tkm_poly_add_scalar(tkm_ctx *ctx, tkm_poly *p, const uint8_t s32[32]);
+/* _mul (:1846-1996): product via pad -> 2 x NTT -> pointwise -> INTT; scalar fast paths included. */
+int32_t tkm_poly_mul(tkm_ctx *ctx, const tkm_poly *a, const tkm_poly *b, tkm_poly **out);
+/* scale_coeffs_x / scale_coeffs_y (:1553-1613): c_ij * sx^i * sy^j; NULL = 1. */
+int32_t tkm_poly_scale_coeffs(tkm_ctx *ctx, const tkm_poly *p, const uint8_t *sx32, const uint8_t *sy32,
+                              tkm_poly **out);
+/* eval (:1742-1750): P(x, y). */
+int32_t tkm_poly_eval(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], const uint8_t y32[32], uint8_t out32[32]);
+/* eval_x / eval_y (:1719-1740): partial evaluation, result shape 1 x y_size / x_size x 1. */
+int32_t tkm_poly_eval_x(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], tkm_poly **out);
+int32_t tkm_poly_eval_y(tkm_ctx *ctx, const tkm_poly *p, const uint8_t y32[32], tkm_poly **out);
+/* div_by_vanishing_opt (:2284-2410): P = Qx (X^c - 1) + Qy (Y^d - 1); p is optimize_size'd first
+ * (it takes &mut self in the reference).  Qx shape = p shape, Qy shape = c x y_size. */
+int32_t tkm_poly_div_by_vanishing(tkm_ctx *ctx, tkm_poly *p, size_t c, size_t d, tkm_poly **out_qx, tkm_poly **out_qy);
+/* div_by_ruffini (:2412-2477): P = Qx (X - x) + Qy (Y - y) + r.  Qx shape = p shape, Qy = 1 x y_size. */
+int32_t tkm_poly_div_by_ruffini(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], const uint8_t y32[32],
+                                tkm_poly **out_qx, tkm_poly **out_qy, uint8_t out_r32[32]);
+/* encode_poly (iotools/mod.rs:2041-2113; group_structures/mod.rs:59-119): optimize_size, bounds
+ * check against the CRS grid, commit the trimmed rectangle.  Zero polynomial -> identity. */
+int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t out96[96]);
+
+/* ---- instrumentation used by bench.py (not part of the reference API) ---------------------- */
+/* Times one device-resident launch sequence with CUDA events on the context stream; ms out. */
+int32_t tkm_event_time_begin(tkm_ctx *ctx);
+int32_t tkm_event_time_end(tkm_ctx *ctx, float *out_ms);
+/* Kernel launches issued by this library on this context since creation. */
+int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out);
+/* Micro-benchmarks: integer pipe peak (dependent-free IMAD / IMAD.WIDE streams) and field-mul rate.
+ * kind: 0 = IMAD.U32, 1 = IMAD.WIDE.U32, 2 = Fr mul, 3 = Fq mul, 4 = XYZZ mixed add.  out = ops/s. */
+int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKAMAK_B200_H */

@@ -1,0 +1,467 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libtokamak_b200) against the CPU oracle on the
+same seeded inputs, against the committed golden vectors, and -- at full sizes -- through
+size-independent identities.  Bit-exact everywhere (integer arithmetic).
+Modeled on packages/backend/libs/src/tests.rs (test names cited per test)."""
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import pyref as P
+from util import frs, fr1, g1_tuple, g1s, golden, ints, pt_from_golden, to_ints
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import tokamak_b200 as T
+
+    return T
+
+
+@pytest.fixture(scope="module")
+def ctx(T):
+    O.build()
+    c = T.Context(0)
+    c.init_ntt_domain_for_size(1 << 23)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------ fields
+def test_fr_vec_ops_edge_and_random(ctx, T):
+    edge = [0, 1, 2, P.R_MOD - 1, P.R_MOD - 2, (1 << 256) % P.R_MOD, (1 << 32) - 1, 1 << 32, P.R_MOD >> 1]
+    a = np.concatenate([frs(edge * len(edge)), O.random_fr(11, 4096)])
+    b = np.concatenate([frs([e for e in edge for _ in edge]), O.random_fr(12, 4096)])
+    for op, name in ((T.OP_ADD, "add"), (T.OP_SUB, "sub"), (T.OP_MUL, "mul")):
+        got = ctx.vec_op_host(op, a, b)
+        assert np.array_equal(got, O.fr_vec_op(name, a, b)), name
+    got = ctx.vec_op_host(T.OP_DIV, a[:512], b[:512])
+    exp = O.fr_vec_op("mul", a[:512], O.fr_vec_inv(b[:512]))
+    assert np.array_equal(got, exp)
+
+
+def test_fr_vec_inv_batched(ctx):
+    a = np.concatenate([frs([0, 1, P.R_MOD - 1, 0, 0, 7]), O.random_fr(13, 1001)])
+    d = ctx.upload_fr(a)
+    ctx.lib.tkm_fr_vec_inv(ctx.h, d, d, a.shape[0])
+    got = ctx.download_fr(d, a.shape[0])
+    ctx.dev_free(d)
+    assert np.array_equal(got, O.fr_vec_inv(a))
+
+
+def test_mont_roundtrip_and_root_of_unity(ctx):
+    a = O.random_fr(14, 777)
+    d = ctx.upload_fr(a)
+    assert np.array_equal(ctx.download_fr(d, 777), a)
+    ctx.dev_free(d)
+    for k in (1, 2, 8, 12, 23, 32):
+        assert ctx.get_root_of_unity(1 << k) == P.root_of_unity(1 << k)
+
+
+# ------------------------------------------------------------------------------------------ NTT
+def test_golden_bintt(ctx, T):
+    g = golden()["bintt"]
+    x, y, a = g["x"], g["y"], frs(ints(g["in"]))
+    gx, gy = int(g["coset_x"], 16), int(g["coset_y"], 16)
+    assert to_ints(ctx.bintt_host(a, x, y, T.FORWARD)) == ints(g["fwd"])
+    assert to_ints(ctx.bintt_host(a, x, y, T.FORWARD, gx, gy)) == ints(g["fwd_coset"])
+    assert to_ints(ctx.bintt_host(a, x, y, T.INVERSE)) == ints(g["inv"])
+    assert to_ints(ctx.bintt_host(a, x, y, T.INVERSE, gx, gy)) == ints(g["inv_coset"])
+    g1 = golden()["ntt_1d"]
+    b = frs(ints(g1["in"]))
+    assert to_ints(ctx.bintt_host(b, 16, 1, T.FORWARD)) == ints(g1["fwd_x16"])
+    assert to_ints(ctx.bintt_host(b, 1, 16, T.INVERSE)) == ints(g1["inv_y16"])
+
+
+SHAPES = [(1, 2), (2, 1), (2, 2), (4, 8), (64, 4), (16, 512), (1, 1024), (2048, 1), (4096, 1), (128, 1), (1, 256),
+          (2048, 2), (4096, 16), (1024, 1024), (8192, 8), (16384, 4)]
+
+
+@pytest.mark.parametrize("x,y", SHAPES)
+def test_bintt_vs_oracle_all_modes(ctx, T, x, y):
+    """_biNTT on every code path: single-pass / two-pass axes, degenerate axes, batch over rows or columns."""
+    a = O.random_fr(100 + x + y, x * y)
+    cx, cy = O.random_fr(5, 1)[0], O.random_fr(6, 1)[0]
+    for inv in (False, True):
+        for gx, gy in ((None, None), (cx, cy), (cx, None), (None, cy)):
+            got = ctx.bintt_host(a, x, y, T.INVERSE if inv else T.FORWARD, gx, gy)
+            exp = O.bintt(a, x, y, inv, gx, gy)
+            assert np.array_equal(got, exp), (x, y, inv, gx is not None, gy is not None)
+
+
+@pytest.mark.parametrize("x,y", [(4096, 256), (8192, 256), (8192, 512)])
+def test_bintt_prover_shapes_vs_oracle(ctx, T, x, y):
+    """The prover's transform shapes, full compare against the C oracle."""
+    a = O.random_fr(200 + x, x * y)
+    assert np.array_equal(ctx.bintt_host(a, x, y, T.FORWARD), O.bintt(a, x, y, False))
+    assert np.array_equal(ctx.bintt_host(a, x, y, T.INVERSE), O.bintt(a, x, y, True))
+
+
+def test_bintt_largest_shape_properties(ctx, T):
+    """16384 x 512 = 2^23 (BASELINE.json config): round trip (tests.rs:107-131), coset == manual scaling
+    (tests.rs:134-180), linearity, and sampled evaluations against Horner on the oracle."""
+    x, y = 16384, 512
+    n = x * y
+    a = O.random_fr(31, n)
+    d = ctx.upload_fr(a)
+    e = ctx.dev_alloc(n * 32)
+    ctx.bintt_dev(d, e, x, y, T.FORWARD)
+    ev = ctx.download_fr(e, n)
+    wx, wy = P.root_of_unity(x), P.root_of_unity(y)
+    for (k, l) in ((0, 0), (1, 0), (0, 1), (12345, 77), (16383, 511), (8192, 256)):
+        exp = O.eval_xy(a, x, y, fr1(pow(wx, k, P.R_MOD)), fr1(pow(wy, l, P.R_MOD)))
+        assert np.array_equal(ev[k * y + l], exp), (k, l)
+    ctx.bintt_dev(e, e, x, y, T.INVERSE)
+    assert np.array_equal(ctx.download_fr(e, n), a)
+    # coset forward == scale coefficients then plain forward
+    gx, gy = 0x1234567 + (1 << 200), 0x7654321 + (1 << 199)
+    ctx.bintt_dev(d, e, x, y, T.FORWARD, gx, gy)
+    got = ctx.download_fr(e, n)
+    scaled = O.scale_coeffs(a, x, y, fr1(gx), fr1(gy))
+    ds = ctx.upload_fr(scaled)
+    ctx.bintt_dev(ds, ds, x, y, T.FORWARD)
+    assert np.array_equal(got, ctx.download_fr(ds, n))
+    # inverse coset undoes it
+    ctx.bintt_dev(e, e, x, y, T.INVERSE, gx, gy)
+    assert np.array_equal(ctx.download_fr(e, n), a)
+    for p in (d, e, ds):
+        ctx.dev_free(p)
+
+
+def test_ntt_batch_rows_vs_columns(ctx, T):
+    """Row batch == column batch on the transpose (tests.rs:519-588,617-646)."""
+    n, batch = 512, 64
+    a = O.random_fr(41, n * batch)
+    d = ctx.upload_fr(a)
+    o = ctx.dev_alloc(n * batch * 32)
+    ctx.ntt_batch_dev(d, o, n, batch, columns_batch=False)
+    assert np.array_equal(ctx.download_fr(o, n * batch), O.ntt(a, n, batch, False))
+    ctx.ntt_batch_dev(d, o, n, batch, columns_batch=True)
+    assert np.array_equal(ctx.download_fr(o, n * batch), O.ntt(a, n, batch, True))
+    ctx.dev_free(d)
+    ctx.dev_free(o)
+
+
+def test_ntt_domain_errors(T):
+    c = T.Context(0)
+    a = O.random_fr(1, 16)
+    with pytest.raises(T.TkmError) as e:  # bivariate_polynomial/mod.rs:1437-1439
+        c.bintt_host(a, 4, 4)
+    assert e.value.status == -3
+    c.init_ntt_domain_for_size(8)
+    with pytest.raises(T.TkmError) as e:  # bivariate_polynomial/mod.rs:1440-1445
+        c.bintt_host(a, 4, 4)
+    assert e.value.status == -3 and "too small" in str(e.value)
+    c.init_ntt_domain_for_size(16)
+    assert np.array_equal(c.bintt_host(a, 4, 4), O.bintt(a, 4, 4))
+    with pytest.raises(T.TkmError):
+        c.bintt_host(O.random_fr(1, 12), 3, 4)
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------ G1 / MSM
+def test_golden_msm(ctx):
+    g = golden()["msm"]
+    ss = frs(ints(g["scalars"]))
+    pts = g1s([pt_from_golden(p) for p in g["points"]])
+    assert g1_tuple(ctx.msm_g1_host(ss, pts)) == pt_from_golden(g["result"])
+
+
+def test_g1_single_ops(ctx):
+    a = g1s([P.G1_GEN])[0]
+    k = 0x123456789ABCDEF123456789ABCDEF
+    b = ctx.g1_mul(a, k)
+    assert g1_tuple(b) == P.g1_mul(P.G1_GEN, k)
+    assert g1_tuple(ctx.g1_add(a, b)) == P.g1_mul(P.G1_GEN, k + 1)
+    assert g1_tuple(ctx.g1_add(a, a)) == P.g1_mul(P.G1_GEN, 2)
+    assert g1_tuple(ctx.g1_add(a, g1s([P.g1_neg(P.G1_GEN)])[0])) is None
+    assert g1_tuple(ctx.g1_add(a, g1s([None])[0])) == P.G1_GEN
+    assert g1_tuple(ctx.g1_mul(a, 0)) is None
+    assert g1_tuple(ctx.g1_mul(a, P.R_MOD - 1)) == P.g1_neg(P.G1_GEN)
+
+
+def test_fixed_base_mul_vs_oracle(ctx):
+    """N one-point MSMs == per-point scalar mul (cpu_and_gpu_versions_produce_same, tests.rs:19-45)."""
+    G = g1s([P.G1_GEN_FIXED_TAU])[0]
+    ks = np.concatenate([frs([0, 1, 2, P.R_MOD - 1]), O.random_fr(51, 252)])
+    got = ctx.g1_fixed_base_mul(G, ks)
+    assert np.array_equal(got, O.g1_fixed_base_mul_batch(G, ks))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 127, 510, 1000, 4096])
+def test_msm_random_affine_vs_oracle(ctx, n):
+    """Random affine bases (not multiples of a known generator order): compare with the C oracle Pippenger."""
+    G = g1s([P.G1_GEN])[0]
+    pts = O.g1_fixed_base_mul_batch(G, O.random_fr(60 + n, n))
+    ss = O.random_fr(61 + n, n)
+    assert np.array_equal(ctx.msm_g1_host(ss, pts), O.msm_g1(ss, pts))
+
+
+def test_msm_empty_and_degenerate(ctx):
+    G = g1s([P.G1_GEN])[0]
+    assert g1_tuple(ctx.msm_g1_host(np.zeros((0, 4), np.uint64), np.zeros((0, 12), np.uint64))) is None
+    pts = O.g1_fixed_base_mul_batch(G, O.random_fr(71, 600))
+    zeros = np.zeros((600, 4), dtype=np.uint64)
+    assert g1_tuple(ctx.msm_g1_host(zeros, pts)) is None  # all-zero scalars
+    ones = frs([1] * 600)
+    exp = None
+    for p in pts:
+        exp = P.g1_add(exp, g1_tuple(p))
+    assert g1_tuple(ctx.msm_g1_host(ones, pts)) == exp  # hot bucket: every digit identical
+    same = np.tile(pts[0], (600, 1))  # all bases equal: every bucket add is a doubling candidate
+    ss = O.random_fr(72, 600)
+    assert np.array_equal(ctx.msm_g1_host(ss, same), O.msm_g1(ss, same))
+    ident = np.zeros((600, 12), dtype=np.uint64)  # all bases identity
+    assert g1_tuple(ctx.msm_g1_host(ss, ident)) is None
+    # P and -P with the same scalar cancel
+    pm = np.stack([pts[0], g1s([P.g1_neg(g1_tuple(pts[0]))])[0]])
+    assert g1_tuple(ctx.msm_g1_host(frs([12345, 12345]), pm)) is None
+    # scalar mix the witness polynomials have: zeros, ones, r-1, small values
+    mix = frs(([0] * 7 + [1] * 5 + [P.R_MOD - 1] * 3 + [2, 3, 255, 65535, 65536]) * 30)
+    assert np.array_equal(ctx.msm_g1_host(mix, pts), O.msm_g1(mix, pts))
+
+
+@pytest.mark.parametrize("logn", [16, 18, 20])
+def test_msm_large_known_discrete_logs(ctx, logn):
+    """Bases k_i*G generated on the device; answer (sum s_i k_i)*G from O(N) field work on the oracle
+    (SURVEY.md §8d config 2)."""
+    n = 1 << logn
+    G = g1s([P.G1_GEN])[0]
+    ks = O.random_fr(80 + logn, n)
+    ss = O.random_fr(81 + logn, n)
+    dk = ctx.upload_fr(ks, to_mont=False)
+    dpts = ctx.dev_alloc(n * 96)
+    ctx.lib.tkm_g1_fixed_base_mul(ctx.h, G.ctypes.data, dk, 0, n, dpts)
+    # spot-check the generated bases against the oracle
+    pts_head = np.empty((8, 12), dtype=np.uint64)
+    ctx.d2h(pts_head, dpts)
+    assert np.array_equal(pts_head, O.g1_fixed_base_mul_batch(G, ks[:8]))
+    ctx.lib.tkm_g1_bases_to_mont(ctx.h, dpts, dpts, n)
+    ds = ctx.upload_fr(ss, to_mont=False)
+    got = ctx.msm_g1_dev(ds, False, dpts, n)
+    exp = O.g1_mul(G, O.fr_inner_product(ss, ks))
+    assert np.array_equal(got, exp)
+    # Montgomery-form scalars give the same point
+    ctx.lib.tkm_fr_to_mont(ctx.h, ds, ds, n)
+    assert np.array_equal(ctx.msm_g1_dev(ds, True, dpts, n), exp)
+    for p in (dk, dpts, ds):
+        ctx.dev_free(p)
+
+
+def test_msm_rect_and_indexed(ctx):
+    """Strided rectangle of a CRS grid (encode_poly, iotools/mod.rs:2061-2088) and sparse gather
+    (msm_g1_bases over gathered rows, group_structures/mod.rs:266-300)."""
+    G = g1s([P.G1_GEN])[0]
+    rs_x, rs_y = 32, 16
+    grid = O.g1_fixed_base_mul_batch(G, O.random_fr(91, rs_x * rs_y))
+    sx, sy = 16, 16  # scalar matrix shape
+    sc = O.random_fr(92, sx * sy)
+    dg = ctx.upload_bases(grid)
+    ds = ctx.upload_fr(sc)
+    for rows, cols in ((16, 16), (13, 9), (1, 16), (16, 1), (5, 7)):
+        got = ctx.msm_g1_rect_dev(ds, True, sy, dg, rs_y, rows, cols)
+        assert np.array_equal(got, O.msm_g1_rect(sc, sy, grid, rs_y, rows, cols)), (rows, cols)
+    idx = np.array([(7 * k * k + 3) % (rs_x * rs_y) for k in range(200)], dtype=np.uint32)
+    sc2 = O.random_fr(93, 200)
+    ds2 = ctx.upload_fr(sc2, to_mont=False)
+    di = ctx.dev_alloc(idx.nbytes)
+    ctx.h2d(di, idx)
+    got = ctx.msm_g1_indexed_dev(ds2, False, dg, di, 200)
+    assert np.array_equal(got, O.msm_g1(sc2, grid[idx]))
+    for p in (dg, ds, ds2, di):
+        ctx.dev_free(p)
+
+
+# ------------------------------------------------------------------------------------------ polynomial engine
+def poly_from(T, ctx, a, x, y):
+    return T.DensePolynomialExt.from_coeffs(ctx, a, x, y)
+
+
+def test_golden_poly_ops(ctx, T):
+    g = golden()
+    x, y = g["bintt"]["x"], g["bintt"]["y"]
+    a = frs(ints(g["bintt"]["in"]))
+    p = poly_from(T, ctx, a, x, y)
+    px, py = ints(g["poly"]["point"])
+    assert p.eval(px, py) == int(g["poly"]["eval"], 16)
+    assert p._scale(px, py).coeffs_ints() == ints(g["poly"]["scale"])
+    qx, qy, r = p.div_by_ruffini(px, py)
+    assert qx.coeffs_ints() == ints(g["poly"]["ruffini_qx"]) and qy.coeffs_ints() == ints(g["poly"]["ruffini_qy"])
+    assert r == int(g["poly"]["ruffini_r"], 16)
+    v = g["vanishing"]
+    vqx, vqy = p.clone().div_by_vanishing_opt(v["c"], v["d"])
+    assert vqx.coeffs_ints() == ints(v["qx"]) and vqy.coeffs_ints() == ints(v["qy"])
+    m = p * p
+    assert m.shape == (g["mul_self"]["nx"], g["mul_self"]["ny"]) and m.coeffs_ints() == ints(g["mul_self"]["out"])
+    grid = g1s([pt_from_golden(q) for q in g["commit"]["grid"]])
+    sigma = T.Sigma1(ctx, grid, 8, 4)
+    assert g1_tuple(sigma.encode_poly(p)) == pt_from_golden(g["commit"]["result"])
+
+
+def test_from_evals_and_to_evals(ctx, T):
+    """test_from_evals / test_coset_ntt_matches_manual_scaling (tests.rs:107-180)."""
+    x, y = 64, 32
+    ev = O.random_fr(301, x * y)
+    p = T.DensePolynomialExt.from_rou_evals(ctx, ev, x, y)
+    assert np.array_equal(p.copy_coeffs(), O.bintt(ev, x, y, True))
+    assert np.array_equal(p.to_rou_evals(), ev)
+    gx, gy = 11111, 22222
+    assert np.array_equal(p.to_rou_evals(gx, gy), O.bintt(p.copy_coeffs(), x, y, False, fr1(gx), fr1(gy)))
+    q = T.DensePolynomialExt.from_rou_evals(ctx, ev, x, y, gx, gy)
+    assert np.array_equal(q.copy_coeffs(), O.bintt(ev, x, y, True, fr1(gx), fr1(gy)))
+
+
+def test_add_sub_neg_scalar_mismatched_shapes(ctx, T):
+    """test_add / test_sub / mismatched sizes / scalar ops / neg (tests.rs:183-403,711-797)."""
+    a = O.random_fr(311, 8 * 4)
+    b = O.random_fr(312, 4 * 16)
+    pa, pb = poly_from(T, ctx, a, 8, 4), poly_from(T, ctx, b, 4, 16)
+    ai, bi = to_ints(a), to_ints(b)
+
+    def ref(op):
+        out = [0] * (8 * 16)
+        for i in range(8):
+            for j in range(16):
+                u = ai[i * 4 + j] if j < 4 else 0
+                v = bi[i * 16 + j] if i < 4 else 0
+                out[i * 16 + j] = op(u, v) % P.R_MOD
+        return out
+
+    s = pa + pb
+    assert s.shape == (8, 16) and s.coeffs_ints() == ref(lambda u, v: u + v)
+    assert (pa - pb).coeffs_ints() == ref(lambda u, v: u - v)
+    assert (pb - pa).coeffs_ints() == ref(lambda u, v: v - u)
+    assert (-pa).coeffs_ints() == [(-u) % P.R_MOD for u in ai]
+    k = 0xDEADBEEF12345
+    assert (pa * k).coeffs_ints() == [u * k % P.R_MOD for u in ai]
+    assert (pa + k).coeffs_ints() == [(ai[0] + k) % P.R_MOD] + ai[1:]
+    assert (pa - k).coeffs_ints() == [(ai[0] - k) % P.R_MOD] + ai[1:]
+
+
+def test_resize_optimize_find_degree_mul_monomial(ctx, T):
+    """test_resize / test_optimize_size / update_degree_general_case / test_mul_monomial (tests.rs:886-932,1011-1039,1312-1360)."""
+    x, y = 16, 8
+    ai = [0] * (x * y)
+    for (i, j, v) in ((0, 0, 5), (3, 2, 7), (5, 1, 9)):
+        ai[i * y + j] = v
+    p = poly_from(T, ctx, frs(ai), x, y)
+    assert p.find_degree() == (5, 2)
+    q = p.clone()
+    q.optimize_size()
+    assert q.shape == (8, 4) and q.coeffs_ints() == P.resize(ai, x, y, 6, 3)[0]
+    q.resize(3, 17)
+    exp, nx, ny = P.resize(P.resize(ai, x, y, 6, 3)[0], 8, 4, 3, 17)
+    assert q.shape == (nx, ny) == (4, 32) and q.coeffs_ints() == exp
+    z = T.DensePolynomialExt.zero(ctx, 4, 4)
+    assert z.find_degree() == (-1, -1) and z.is_zero()
+    z.optimize_size()
+    assert z.shape == (4, 4)
+    m = p.mul_monomial(3, 5)
+    exp, nx, ny = P.mul_monomial(ai, x, y, 3, 5)
+    assert m.shape == (nx, ny) and m.coeffs_ints() == exp
+    with pytest.raises(T.TkmError):
+        T.DensePolynomialExt.from_coeffs(ctx, frs([1] * 12), 3, 4)
+
+
+def test_eval_and_partial_evals(ctx, T):
+    """test_eval / test_eval_x / test_eval_y (tests.rs:838-883)."""
+    x, y = 256, 64
+    a = O.random_fr(321, x * y)
+    p = poly_from(T, ctx, a, x, y)
+    px, py = 0xABCDEF0123456789, (1 << 250) + 12345
+    assert p.eval(px, py) == O.fr_to_int(O.eval_xy(a, x, y, fr1(px), fr1(py)))
+    ex = p.eval_x(px)
+    assert ex.shape == (1, y)
+    ai = to_ints(a)
+    assert ex.coeffs_ints() == P.eval_x(ai, x, y, px)
+    ey = p.eval_y(py)
+    assert ey.shape == (x, 1) and ey.coeffs_ints() == P.eval_y(ai, x, y, py)
+
+
+def test_scale_coeffs(ctx, T):
+    x, y = 128, 32
+    a = O.random_fr(331, x * y)
+    p = poly_from(T, ctx, a, x, y)
+    s = 0x1234567890ABCDEF
+    assert np.array_equal(p.scale_coeffs_x(s).copy_coeffs(), O.scale_coeffs(a, x, y, fr1(s), None))
+    assert np.array_equal(p.scale_coeffs_y(s).copy_coeffs(), O.scale_coeffs(a, x, y, None, fr1(s)))
+
+
+def test_mul_polynomial(ctx, T):
+    """test_mul_polynomial (tests.rs:1042-1088) + scalar fast paths (bivariate_polynomial/mod.rs:1867-1877)."""
+    a = O.random_fr(341, 32 * 16)
+    b = O.random_fr(342, 8 * 64)
+    pa, pb = poly_from(T, ctx, a, 32, 16), poly_from(T, ctx, b, 8, 64)
+    m = pa * pb
+    exp, nx, ny = P.poly_mul(to_ints(a), 32, 16, to_ints(b), 8, 64)
+    assert m.shape == (nx, ny) and m.coeffs_ints() == exp
+    c = poly_from(T, ctx, frs([7] + [0] * 15), 4, 4)
+    assert (pa * c).coeffs_ints() == [u * 7 % P.R_MOD for u in to_ints(a)]
+    assert (c * c).shape == (1, 1) and (c * c).coeffs_ints() == [49]
+    z = T.DensePolynomialExt.zero(ctx, 2, 2)
+    assert (pa * z).is_zero()
+
+
+@pytest.mark.parametrize("x,y,c,d", [(16, 16, 4, 4), (64, 32, 16, 8), (8192, 512, 4096, 256), (256, 64, 64, 64 // 2)])
+def test_div_by_vanishing_opt(ctx, T, x, y, c, d):
+    """test_div_by_vanishing_opt_basic (tests.rs:1224-1237): build P = Qx t_x + Qy t_y, divide, compare with the oracle
+    restatement of the reference recurrences."""
+    a = O.random_fr(351 + x, x * y)  # top row/column non-zero with overwhelming probability: optimize_size keeps the shape
+    p = poly_from(T, ctx, a, x, y)
+    qx, qy = p.div_by_vanishing_opt(c, d)
+    eqx, eqy = O.div_by_vanishing_opt(a, x, y, c, d)
+    assert qx.shape == (x, y) and qy.shape == (c, y)
+    assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy)
+
+
+def test_div_by_vanishing_reconstructs(ctx, T):
+    x, y, c, d = 32, 16, 8, 4
+    rng = P.SplitMix64(77)
+    qx0 = [rng.fr() if i < x - c else 0 for i in range(x) for j in range(y)]
+    qy0 = [rng.fr() if j < y - d else 0 for i in range(c) for j in range(y)]
+    tX = T.DensePolynomialExt.from_coeffs(ctx, frs([P.R_MOD - 1] + [0] * (c - 1) + [1] + [0] * (c - 1)), 2 * c, 1)
+    tY = T.DensePolynomialExt.from_coeffs(ctx, frs([P.R_MOD - 1] + [0] * (d - 1) + [1] + [0] * (d - 1)), 1, 2 * d)
+    pq = poly_from(T, ctx, frs(qx0), x, y) * tX + poly_from(T, ctx, frs(qy0), c, y) * tY
+    pq.optimize_size()
+    assert pq.shape == (x, y)
+    qx, qy = pq.div_by_vanishing_opt(c, d)
+    assert qx.coeffs_ints() == qx0 and qy.coeffs_ints() == qy0
+
+
+@pytest.mark.parametrize("x,y", [(2, 2), (1, 8), (8, 1), (64, 32), (4096, 256)])
+def test_div_by_ruffini(ctx, T, x, y):
+    """test_div_by_ruffini (tests.rs:935-952)."""
+    a = O.random_fr(361 + x, x * y)
+    p = poly_from(T, ctx, a, x, y)
+    px, py = 987654321987654321, 123456789123456789
+    qx, qy, r = p.div_by_ruffini(px, py)
+    eqx, eqy, er = O.div_by_ruffini(a, x, y, fr1(px), fr1(py))
+    assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy) and r == O.fr_to_int(er)
+    assert r == p.eval(px, py)
+
+
+def test_encode_poly_fixed_tau(ctx, T):
+    """encode_poly(P) == P(tau_x, tau_y) * G (setup/trusted-setup/src/main.rs:222-246) on a 64 x 32 grid built
+    on the device with the fixed-tau generator; trimmed-rectangle, zero-polynomial and too-small-CRS paths."""
+    rs_x, rs_y = 64, 32
+    tx, ty = P.TAU_FIXED["x"], P.TAU_FIXED["y"]
+    G = g1s([P.G1_GEN_FIXED_TAU])[0]
+    mon = [pow(tx, h, P.R_MOD) * pow(ty, i, P.R_MOD) % P.R_MOD for h in range(rs_x) for i in range(rs_y)]
+    grid = ctx.g1_fixed_base_mul(G, frs(mon))
+    sigma = T.Sigma1(ctx, grid, rs_x, rs_y)
+    a = O.random_fr(371, 32 * 16)
+    p = poly_from(T, ctx, a, 32, 16)
+    exp = O.g1_mul(G, O.eval_xy(a, 32, 16, fr1(tx), fr1(ty)))
+    assert np.array_equal(sigma.encode_poly(p), exp)
+    # sparse polynomial in a larger buffer: only the (deg+1) rectangle is committed
+    ai = [0] * (64 * 32)
+    ai[0], ai[5 * 32 + 3], ai[17 * 32 + 9] = 3, 1, P.R_MOD - 1
+    ps = poly_from(T, ctx, frs(ai), 64, 32)
+    exp = O.g1_mul(G, O.eval_xy(frs(ai), 64, 32, fr1(tx), fr1(ty)))
+    assert np.array_equal(sigma.encode_poly(ps), exp)
+    assert g1_tuple(sigma.encode_poly(T.DensePolynomialExt.zero(ctx, 8, 8))) is None
+    big = poly_from(T, ctx, O.random_fr(372, 128 * 2), 128, 2)
+    with pytest.raises(T.TkmError) as e:
+        sigma.encode_poly(big)
+    assert "Insufficient length" in str(e.value)

@@ -1,0 +1,504 @@
+// C-ABI entry points of libtokamak_b200 (see include/tokamak_b200.h for the reference interface each
+// one replaces).  Validation + plumbing only; the kernels live in vec_ops.cu, ntt.cu, msm.cu, poly.cu.
+#include "common.cuh"
+
+namespace tkm {
+Fr root_of_unity_host(uint32_t log_n);
+int32_t domain_init(tkm_ctx *ctx, uint32_t log2_size);
+int32_t domain_release(tkm_ctx *ctx);
+
+// ---- single-point helpers (G1serde ops, group_structures/mod.rs:895-947) and fixed-base batch mul
+__global__ void k_g1_add_single(const G1Affine *a, const G1Affine *b, uint32_t *out_canonical) {
+  if (threadIdx.x || blockIdx.x) return;
+  G1Affine pa = *a, pb = *b;
+  pa.x = pa.x.to_mont(); pa.y = pa.y.to_mont();
+  pb.x = pb.x.to_mont(); pb.y = pb.y.to_mont();
+  G1Xyzz acc = G1Xyzz::identity();
+  g1_madd(acc, pa);
+  g1_madd(acc, pb);
+  G1Affine r = g1_to_affine(acc);
+  Fq x = r.x.from_mont(), y = r.y.from_mont();
+  for (int i = 0; i < 12; i++) { out_canonical[i] = x.v[i]; out_canonical[12 + i] = y.v[i]; }
+}
+
+// out[i] = k_i * base for n scalars: 4-bit fixed windows over a 64 x 15 table of affine multiples held in
+// global memory (built by one small kernel), one thread per scalar, then a batched conversion to affine.
+constexpr int FB_WINDOWS = 64;
+__global__ void k_fixed_base_table(G1Affine base_canonical, G1Affine *table /* [64][16] */) {
+  // one warp; lane w handles windows w and w+32: entry [w][d] = d * 16^w * base
+  const int lane = threadIdx.x;
+  G1Affine b = base_canonical;
+  b.x = b.x.to_mont(); b.y = b.y.to_mont();
+  for (int w = lane; w < FB_WINDOWS; w += 32) {
+    G1Xyzz cur = G1Xyzz::from_affine(b);
+    for (int k = 0; k < 4 * w; k++) cur = g1_dbl(cur);
+    G1Affine step = g1_to_affine(cur);
+    G1Xyzz acc = G1Xyzz::identity();
+    table[w * 16] = G1Affine::identity();
+    for (int d = 1; d < 16; d++) {
+      g1_madd(acc, step);
+      table[w * 16 + d] = g1_to_affine(acc);
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_fixed_base_mul(const G1Affine *__restrict__ table, const Fr *__restrict__ scalars, int scalars_mont,
+                                                       size_t n, G1Affine *__restrict__ out_canonical) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr s = scalars[i];
+    if (scalars_mont) s = s.from_mont();
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int w = 0; w < FB_WINDOWS; w++) {
+      uint32_t d = (s.v[w >> 3] >> ((w & 7) * 4)) & 15u;
+      if (d) {
+        G1Affine t = table[w * 16 + d];
+        g1_madd(acc, t);
+      }
+    }
+    G1Affine r = g1_to_affine(acc);
+    r.x = r.x.from_mont();
+    r.y = r.y.from_mont();
+    out_canonical[i] = r;
+  }
+}
+
+// ---- micro-benchmarks: dependent-free integer streams and field-op rates (ops/s over the whole GPU)
+template <int KIND>
+__global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (KIND == 0) {  // 8 independent IMAD chains
+    uint32_t a[8];
+    for (int i = 0; i < 8; i++) a[i] = t + i;
+    uint32_t m = t | 1u;
+    for (int it = 0; it < iters; it++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = a[i] * m + a[(i + 1) & 7];
+    uint32_t r = 0;
+    for (int i = 0; i < 8; i++) r ^= a[i];
+    if (r == 0x12345678u) sink[0] = r;
+  } else if (KIND == 1) {  // 8 independent IMAD.WIDE chains
+    uint64_t a[8];
+    for (int i = 0; i < 8; i++) a[i] = t + i;
+    uint32_t m = t | 1u;
+    for (int it = 0; it < iters; it++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = (uint64_t)(uint32_t)a[i] * m + a[i];
+    uint64_t r = 0;
+    for (int i = 0; i < 8; i++) r ^= a[i];
+    if (r == 0x12345678u) sink[0] = (uint32_t)r;
+  } else if (KIND == 2) {
+    Fr x = Fr::one(), y = Fr::r2();
+    x.v[0] ^= t;
+    for (int it = 0; it < iters; it++) { x = x * y; y = y * x; }
+    if (x.v[0] == 0x12345678u && y.v[1] == 1) sink[0] = x.v[1];
+  } else if (KIND == 3) {
+    Fq x = Fq::one(), y = Fq::r2();
+    x.v[0] ^= t;
+    for (int it = 0; it < iters; it++) { x = x * y; y = y * x; }
+    if (x.v[0] == 0x12345678u && y.v[1] == 1) sink[0] = x.v[1];
+  } else {
+    G1Xyzz acc = G1Xyzz::identity();
+    G1Affine p;
+    p.x = Fq::one(); p.y = Fq::r2();
+    p.x.v[0] ^= t;
+    acc.X = Fq::r2(); acc.Y = Fq::one(); acc.ZZ = Fq::one(); acc.ZZZ = Fq::one();
+    for (int it = 0; it < iters; it++) { g1_madd(acc, p); p.x.v[1] ^= acc.X.v[0]; }
+    if (acc.X.v[0] == 0x12345678u && acc.Y.v[1] == 1) sink[0] = acc.ZZ.v[1];
+  }
+}
+}  // namespace tkm
+
+using namespace tkm;
+
+#define API_BEGIN                                                  \
+  if (!ctx) return fail(TKM_ERR_INVALID_ARGUMENT, "null context"); \
+  cudaSetDevice(ctx->device);
+
+extern "C" {
+
+const char *tkm_last_error(void) { return last_error().c_str(); }
+const char *tkm_version(void) { return "tokamak_b200 0.1.0 (sm_100a)"; }
+
+int32_t tkm_ctx_create(int32_t device_ordinal, tkm_ctx **out) {
+  if (!out) return fail(TKM_ERR_INVALID_ARGUMENT, "null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(TKM_ERR_NO_DEVICE, "no CUDA device available (%s); libtokamak_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device_ordinal < 0 || device_ordinal >= count) return fail(TKM_ERR_INVALID_ARGUMENT, "device ordinal %d out of range [0,%d)", device_ordinal, count);
+  TKM_CUDA(cudaSetDevice(device_ordinal));
+  tkm_ctx *ctx = new (std::nothrow) tkm_ctx();
+  if (!ctx) return fail(TKM_ERR_ALLOCATION, "out of host memory");
+  ctx->device = device_ordinal;
+  cudaDeviceProp prop;
+  TKM_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  ctx->sm_count = prop.multiProcessorCount;
+  TKM_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  TKM_CUDA(cudaEventCreate(&ctx->ev0));
+  TKM_CUDA(cudaEventCreate(&ctx->ev1));
+  // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  Fr two = Fr::one() + Fr::one();
+  Fr inv2 = two.inv();
+  ctx->inv_pow2[0] = Fr::one();
+  for (int k = 1; k <= 32; k++) ctx->inv_pow2[k] = ctx->inv_pow2[k - 1] * inv2;
+  *out = ctx;
+  return TKM_OK;
+}
+
+int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
+  if (!ctx) return TKM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->twiddles) cudaFree(ctx->twiddles);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return TKM_OK;
+}
+
+int32_t tkm_ctx_set_stream(tkm_ctx *ctx, void *cuda_stream) {
+  API_BEGIN
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return TKM_OK;
+}
+
+int32_t tkm_ctx_sync(tkm_ctx *ctx) {
+  API_BEGIN
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_dev_alloc(tkm_ctx *ctx, size_t bytes, void **out_dev) {
+  API_BEGIN
+  TKM_REQUIRE(out_dev, "null out pointer");
+  cudaError_t e = cudaMalloc(out_dev, bytes ? bytes : 1);
+  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return TKM_OK;
+}
+int32_t tkm_dev_free(tkm_ctx *ctx, void *dev) {
+  API_BEGIN
+  if (!dev) return TKM_OK;
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  TKM_CUDA(cudaFree(dev));
+  return TKM_OK;
+}
+int32_t tkm_memcpy_h2d(tkm_ctx *ctx, void *dev, const void *host, size_t bytes) {
+  API_BEGIN
+  TKM_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+int32_t tkm_memcpy_d2h(tkm_ctx *ctx, void *host, const void *dev, size_t bytes) {
+  API_BEGIN
+  TKM_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_ntt_domain_init(tkm_ctx *ctx, uint32_t log2_size) {
+  API_BEGIN
+  return domain_init(ctx, log2_size);
+}
+int32_t tkm_ntt_domain_release(tkm_ctx *ctx) {
+  API_BEGIN
+  return domain_release(ctx);
+}
+int32_t tkm_ntt_domain_log2(tkm_ctx *ctx, int32_t *out_log2) {
+  API_BEGIN
+  TKM_REQUIRE(out_log2, "null out pointer");
+  *out_log2 = ctx->domain_log2;
+  return TKM_OK;
+}
+int32_t tkm_root_of_unity(uint32_t log2_n, uint8_t out32[32]) {
+  if (log2_n > 32) return fail(TKM_ERR_INVALID_ARGUMENT, "no 2^%u-th root of unity in Fr (2-adicity 32)", log2_n);
+  fr_to_bytes_host(root_of_unity_host(log2_n), out32);
+  return TKM_OK;
+}
+
+int32_t tkm_fr_to_mont(tkm_ctx *ctx, const void *in, void *out, size_t n) {
+  API_BEGIN
+  return vec_to_mont(ctx, (const Fr *)in, (Fr *)out, n);
+}
+int32_t tkm_fr_from_mont(tkm_ctx *ctx, const void *in, void *out, size_t n) {
+  API_BEGIN
+  return vec_from_mont(ctx, (const Fr *)in, (Fr *)out, n);
+}
+int32_t tkm_fr_vec_op(tkm_ctx *ctx, int32_t op, const void *a, const void *b, void *out, size_t n) {
+  API_BEGIN
+  return vec_op(ctx, op, (const Fr *)a, (const Fr *)b, (Fr *)out, n);
+}
+int32_t tkm_fr_vec_scale(tkm_ctx *ctx, const uint8_t s32[32], const void *a, void *out, size_t n) {
+  API_BEGIN
+  TKM_REQUIRE(s32, "null scalar");
+  return vec_scale(ctx, fr_from_bytes_host(s32), (const Fr *)a, (Fr *)out, n);
+}
+int32_t tkm_fr_vec_inv(tkm_ctx *ctx, const void *a, void *out, size_t n) {
+  API_BEGIN
+  return vec_inv(ctx, (const Fr *)a, (Fr *)out, n);
+}
+int32_t tkm_fr_vec_op_host(tkm_ctx *ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n) {
+  API_BEGIN
+  TKM_REQUIRE(a && b && out, "null argument");
+  Scratch<Fr> da, db;
+  TKM_TRY(da.alloc(ctx, n));
+  TKM_TRY(db.alloc(ctx, n));
+  TKM_CUDA(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (op == TKM_OP_MUL || op == TKM_OP_DIV) {
+    // (aR)*b/R = ab ; (aR) * (bR)^-1 ... keep it simple: both to Montgomery, result back
+    TKM_TRY(vec_to_mont(ctx, da.p, da.p, n));
+    TKM_TRY(vec_to_mont(ctx, db.p, db.p, n));
+    TKM_TRY(vec_op(ctx, op, da.p, db.p, da.p, n));
+    TKM_TRY(vec_from_mont(ctx, da.p, da.p, n));
+  } else {
+    TKM_TRY(vec_op(ctx, op, da.p, db.p, da.p, n));  // add/sub are form-agnostic
+  }
+  TKM_CUDA(cudaMemcpyAsync(out, da.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_bintt(tkm_ctx *ctx, const void *in, void *out, size_t x_size, size_t y_size, int32_t dir, const uint8_t *cx, const uint8_t *cy) {
+  API_BEGIN
+  TKM_REQUIRE(in && out, "null argument");
+  Fr gx, gy;
+  if (cx) gx = fr_from_bytes_host(cx);
+  if (cy) gy = fr_from_bytes_host(cy);
+  return bintt_dev(ctx, (const Fr *)in, (Fr *)out, x_size, y_size, dir, cx ? &gx : nullptr, cy ? &gy : nullptr);
+}
+
+int32_t tkm_bintt_host(tkm_ctx *ctx, const uint8_t *in, uint8_t *out, size_t x_size, size_t y_size, int32_t dir, const uint8_t *cx,
+                       const uint8_t *cy) {
+  API_BEGIN
+  TKM_REQUIRE(in && out, "null argument");
+  size_t n = x_size * y_size;
+  Scratch<Fr> d;
+  TKM_TRY(d.alloc(ctx, n));
+  TKM_CUDA(cudaMemcpyAsync(d.p, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_TRY(vec_to_mont(ctx, d.p, d.p, n));
+  TKM_TRY(tkm_bintt(ctx, d.p, d.p, x_size, y_size, dir, cx, cy));
+  TKM_TRY(vec_from_mont(ctx, d.p, d.p, n));
+  TKM_CUDA(cudaMemcpyAsync(out, d.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_ntt_batch(tkm_ctx *ctx, const void *in, void *out, size_t n, size_t batch, int32_t columns_batch, int32_t dir,
+                      const uint8_t *coset32) {
+  API_BEGIN
+  TKM_REQUIRE(in && out, "null argument");
+  Fr g;
+  if (coset32) g = fr_from_bytes_host(coset32);
+  if (columns_batch) return ntt_axis(ctx, (const Fr *)in, (Fr *)out, 1, n, batch, dir, coset32 ? &g : nullptr);
+  return ntt_axis(ctx, (const Fr *)in, (Fr *)out, batch, n, 1, dir, coset32 ? &g : nullptr);
+}
+
+int32_t tkm_g1_bases_to_mont(tkm_ctx *ctx, const void *in, void *out, size_t n) {
+  API_BEGIN
+  return g1_to_mont_dev(ctx, (const G1Affine *)in, (G1Affine *)out, n);
+}
+
+int32_t tkm_msm_g1_rect(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, size_t s_stride, const void *bases, size_t b_stride,
+                        size_t rows, size_t cols, uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(out96, "null out pointer");
+  TKM_REQUIRE(rows * cols == 0 || (scalars && bases), "null argument");
+  MsmInput in;
+  in.scalars = (const Fr *)scalars;
+  in.scalars_mont = scalars_mont != 0;
+  in.scalar_row_stride = s_stride;
+  in.bases = (const G1Affine *)bases;
+  in.base_row_stride = b_stride;
+  in.rows = rows;
+  in.cols = cols;
+  in.idx = nullptr;
+  return msm_run(ctx, in, out96);
+}
+int32_t tkm_msm_g1(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, const void *bases, size_t n, uint8_t out96[96]) {
+  return tkm_msm_g1_rect(ctx, scalars, scalars_mont, n, bases, n, 1, n, out96);
+}
+int32_t tkm_msm_g1_indexed(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, const void *bases, const void *idx, size_t n,
+                           uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(out96, "null out pointer");
+  TKM_REQUIRE(n == 0 || (scalars && bases && idx), "null argument");
+  MsmInput in;
+  in.scalars = (const Fr *)scalars;
+  in.scalars_mont = scalars_mont != 0;
+  in.scalar_row_stride = n;
+  in.bases = (const G1Affine *)bases;
+  in.base_row_stride = n;
+  in.rows = 1;
+  in.cols = n;
+  in.idx = (const uint32_t *)idx;
+  return msm_run(ctx, in, out96);
+}
+int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(out96, "null out pointer");
+  if (n == 0) {
+    memset(out96, 0, 96);
+    return TKM_OK;
+  }
+  TKM_REQUIRE(scalars && bases, "null argument");
+  Scratch<Fr> ds;
+  Scratch<G1Affine> db;
+  TKM_TRY(ds.alloc(ctx, n));
+  TKM_TRY(db.alloc(ctx, n));
+  TKM_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaMemcpyAsync(db.p, bases, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_TRY(g1_to_mont_dev(ctx, db.p, db.p, n));
+  return tkm_msm_g1(ctx, ds.p, 0, db.p, n, out96);
+}
+
+int32_t tkm_g1_fixed_base_mul(tkm_ctx *ctx, const uint8_t base96[96], const void *scalars, int32_t scalars_mont, size_t n, void *out) {
+  API_BEGIN
+  TKM_REQUIRE(base96 && out, "null argument");
+  if (n == 0) return TKM_OK;
+  TKM_REQUIRE(scalars, "null scalars");
+  Scratch<G1Affine> table;
+  TKM_TRY(table.alloc(ctx, FB_WINDOWS * 16));
+  G1Affine b;
+  memcpy(&b, base96, 96);
+  k_fixed_base_table<<<1, 32, 0, ctx->stream>>>(b, table.p);
+  TKM_TRY(launch_check(ctx, "k_fixed_base_table"));
+  k_fixed_base_mul<<<grid_for(n, 128, ctx->sm_count), 128, 0, ctx->stream>>>(table.p, (const Fr *)scalars, scalars_mont, n,
+                                                                            (G1Affine *)out);
+  return launch_check(ctx, "k_fixed_base_mul");
+}
+
+int32_t tkm_g1_add(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t b96[96], uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(a96 && b96 && out96, "null argument");
+  Scratch<G1Affine> d;
+  Scratch<uint32_t> r;
+  TKM_TRY(d.alloc(ctx, 2));
+  TKM_TRY(r.alloc(ctx, 24));
+  TKM_CUDA(cudaMemcpyAsync(d.p, a96, 96, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaMemcpyAsync(d.p + 1, b96, 96, cudaMemcpyHostToDevice, ctx->stream));
+  k_g1_add_single<<<1, 32, 0, ctx->stream>>>(d.p, d.p + 1, r.p);
+  TKM_TRY(launch_check(ctx, "k_g1_add_single"));
+  TKM_CUDA(cudaMemcpyAsync(out96, r.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_g1_mul(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t k32[32], uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(a96 && k32 && out96, "null argument");
+  Scratch<Fr> s;
+  Scratch<G1Affine> r;
+  TKM_TRY(s.alloc(ctx, 1));
+  TKM_TRY(r.alloc(ctx, 1));
+  TKM_CUDA(cudaMemcpyAsync(s.p, k32, 32, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_TRY(tkm_g1_fixed_base_mul(ctx, a96, s.p, 0, 1, r.p));
+  TKM_CUDA(cudaMemcpyAsync(out96, r.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_crs_from_device(tkm_ctx *ctx, void *dev_points, size_t rows, size_t cols, int32_t take_ownership, tkm_crs **out) {
+  API_BEGIN
+  TKM_REQUIRE(dev_points && out, "null argument");
+  tkm_crs *c = new (std::nothrow) tkm_crs();
+  if (!c) return fail(TKM_ERR_ALLOCATION, "out of host memory");
+  c->d = (G1Affine *)dev_points;
+  c->rows = rows;
+  c->cols = cols;
+  c->owned = take_ownership != 0;
+  int32_t st = g1_to_mont_dev(ctx, c->d, c->d, rows * cols);
+  if (st != TKM_OK) {
+    delete c;
+    return st;
+  }
+  *out = c;
+  return TKM_OK;
+}
+int32_t tkm_crs_upload(tkm_ctx *ctx, const uint8_t *points96, size_t rows, size_t cols, tkm_crs **out) {
+  API_BEGIN
+  TKM_REQUIRE(points96 && out, "null argument");
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, rows * cols * 96 + 16);
+  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMalloc(%zu) failed: %s", rows * cols * 96, cudaGetErrorString(e));
+  e = cudaMemcpyAsync(d, points96, rows * cols * 96, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(TKM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  }
+  int32_t st = tkm_crs_from_device(ctx, d, rows, cols, 1, out);
+  if (st != TKM_OK) cudaFree(d);
+  return st;
+}
+int32_t tkm_crs_free(tkm_ctx *ctx, tkm_crs *crs) {
+  API_BEGIN
+  if (!crs) return TKM_OK;
+  cudaStreamSynchronize(ctx->stream);
+  if (crs->owned && crs->d) cudaFree(crs->d);
+  delete crs;
+  return TKM_OK;
+}
+int32_t tkm_crs_device_ptr(tkm_crs *crs, void **out_dev, size_t *rows, size_t *cols) {
+  if (!crs) return fail(TKM_ERR_INVALID_ARGUMENT, "null crs");
+  if (out_dev) *out_dev = crs->d;
+  if (rows) *rows = crs->rows;
+  if (cols) *cols = crs->cols;
+  return TKM_OK;
+}
+
+int32_t tkm_event_time_begin(tkm_ctx *ctx) {
+  API_BEGIN
+  TKM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  return TKM_OK;
+}
+int32_t tkm_event_time_end(tkm_ctx *ctx, float *out_ms) {
+  API_BEGIN
+  TKM_REQUIRE(out_ms, "null out pointer");
+  TKM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  TKM_CUDA(cudaEventSynchronize(ctx->ev1));
+  TKM_CUDA(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+  return TKM_OK;
+}
+int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out) {
+  API_BEGIN
+  TKM_REQUIRE(out, "null out pointer");
+  *out = ctx->launches;
+  return TKM_OK;
+}
+
+int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
+  API_BEGIN
+  TKM_REQUIRE(out_ops_per_s, "null out pointer");
+  Scratch<uint32_t> sink;
+  TKM_TRY(sink.alloc(ctx, 4));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  int iters;
+  double ops_per_iter;
+  for (int rep = 0; rep < 2; rep++) {  // rep 0 = warm-up
+    TKM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    switch (kind) {
+      case 0: iters = 4096; ops_per_iter = 8; k_microbench<0><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 1: iters = 4096; ops_per_iter = 8; k_microbench<1><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 2: iters = 512; ops_per_iter = 2; k_microbench<2><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 3: iters = 256; ops_per_iter = 2; k_microbench<3><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 4: iters = 64; ops_per_iter = 1; k_microbench<4><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown microbench kind %d", kind);
+    }
+    TKM_TRY(launch_check(ctx, "k_microbench"));
+    TKM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    TKM_CUDA(cudaEventSynchronize(ctx->ev1));
+  }
+  float ms = 0;
+  TKM_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *out_ops_per_s = (double)blocks * threads * iters * ops_per_iter / (ms * 1e-3);
+  return TKM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Shared host-side plumbing of libtokamak_b200: status/error handling, the context object,
+// stream-ordered scratch allocation and launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/tokamak_b200.h"
+#include "g1.cuh"
+
+namespace tkm {
+
+// Thread-local last-error text returned by tkm_last_error().
+std::string &last_error();
+int32_t fail(int32_t code, const char *fmt, ...);
+
+#define TKM_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return ::tkm::fail(TKM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,         \
+                                               cudaGetErrorString(_e), __FILE__, __LINE__);         \
+  } while (0)
+
+#define TKM_TRY(expr)                 \
+  do {                                \
+    int32_t _s = (expr);              \
+    if (_s != TKM_OK) return _s;      \
+  } while (0)
+
+#define TKM_REQUIRE(cond, ...)                                           \
+  do {                                                                   \
+    if (!(cond)) return ::tkm::fail(TKM_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+}  // namespace tkm
+
+struct tkm_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  // NTT domain: tw[k] = omega_M^k in Montgomery form, k = 0..M/2 (tw[M/2] = -1), M = 2^domain_log2.
+  int32_t domain_log2 = -1;
+  tkm::Fr *twiddles = nullptr;
+  tkm::Fr inv_pow2[33];  // 2^-k in Montgomery form (1/n factors of the inverse transforms)
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct tkm_poly {
+  tkm::Fr *d = nullptr;  // row-major [x_size][y_size], Montgomery form
+  size_t x_size = 0, y_size = 0;
+};
+
+struct tkm_crs {
+  tkm::G1Affine *d = nullptr;  // row-major [rows][cols], Montgomery form
+  size_t rows = 0, cols = 0;
+  bool owned = true;
+};
+
+namespace tkm {
+
+// Stream-ordered scratch buffer (cudaMallocAsync pool; freed on the same stream).
+template <class T>
+struct Scratch {
+  T *p = nullptr;
+  cudaStream_t s = nullptr;
+  Scratch() = default;
+  Scratch(const Scratch &) = delete;
+  Scratch &operator=(const Scratch &) = delete;
+  int32_t alloc(tkm_ctx *ctx, size_t count) {
+    s = ctx->stream;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), s);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(TKM_ERR_ALLOCATION, "cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return TKM_OK;
+  }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+inline bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+inline uint32_t log2_exact(size_t v) {
+  uint32_t l = 0;
+  while (((size_t)1 << l) < v) l++;
+  return l;
+}
+inline size_t next_pow2(size_t v) {
+  // _find_size_as_twopower (bivariate_polynomial/mod.rs:72-86)
+  if (is_pow2(v)) return v;
+  size_t r = 1;
+  while (r <= v) r <<= 1;
+  return r;
+}
+inline unsigned grid_for(size_t work, unsigned block, unsigned sm_count, unsigned waves = 8) {
+  size_t blocks = (work + block - 1) / block;
+  size_t cap = (size_t)sm_count * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// Host-side scalar helpers (tiny, run on the device via one-thread kernels is overkill; these are
+// exact big-integer-free Montgomery ops through the host emulation of ff.cuh).
+Fr fr_from_bytes_host(const uint8_t *b32);  // canonical bytes -> Montgomery
+void fr_to_bytes_host(const Fr &a, uint8_t *b32);
+
+// Internal cross-file entry points ------------------------------------------------------------
+int32_t launch_check(tkm_ctx *ctx, const char *what);
+int32_t vec_to_mont(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n);
+int32_t vec_from_mont(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n);
+int32_t vec_op(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, Fr *out, size_t n);
+int32_t vec_scale(tkm_ctx *ctx, const Fr &s, const Fr *a, Fr *out, size_t n);
+int32_t vec_inv(tkm_ctx *ctx, const Fr *a, Fr *out, size_t n);
+int32_t bintt_dev(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x, size_t y, int dir, const Fr *coset_x,
+                  const Fr *coset_y);
+int32_t ntt_axis(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, size_t n, size_t inner, int dir, const Fr *coset);
+int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n);
+struct MsmInput {
+  const Fr *scalars;
+  bool scalars_mont;
+  size_t scalar_row_stride;
+  const G1Affine *bases;
+  size_t base_row_stride;
+  size_t rows, cols;
+  const uint32_t *idx;  // optional gather indices into bases (rows must be 1)
+};
+int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]);
+
+}  // namespace tkm

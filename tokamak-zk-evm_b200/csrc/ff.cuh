@@ -1,0 +1,272 @@
+// Montgomery prime fields on 32-bit limbs for sm_100a: BLS12-381 Fr (8 limbs) and Fq (12 limbs).
+//
+// Replaces the field arithmetic the reference obtains from ICICLE's ScalarField / BaseField
+// (icicle-bls12-381 v3.8.0; imports at libs/src/bivariate_polynomial/mod.rs:2-8 and
+// libs/src/group_structures/mod.rs:12-15).  Device values are kept in Montgomery form
+// (R = 2^(32*N)); the C-ABI converts at the boundary, where the reference's canonical
+// little-endian layout is kept.
+//
+// Multiplication: two column-interleaved accumulators ("even"/"odd" columns) so that every
+// 32x32 partial product is one mad.lo.cc/madc.hi.cc pair on an aligned register pair, which
+// ptxas fuses into a single IMAD.WIDE.U32.X with predicate carry-in/out (checked with
+// cuobjdump -sass): N^2 wide IMADs for a*b plus N^2 for the interleaved reduction.
+//
+// The carry-chain primitives have a host emulation (thread-local carry flag) so the exact same
+// algorithm text is unit-tested on the CPU against the oracle (tests/test_host_arith.py).
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define TKM_HD __host__ __device__ __forceinline__
+#define TKM_D __device__ __forceinline__
+#else
+#define TKM_HD inline
+#define TKM_D inline
+#endif
+
+namespace tkm {
+
+// ---------------------------------------------------------------- carry-chain primitives
+#if defined(__CUDA_ARCH__)
+TKM_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+TKM_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+TKM_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+TKM_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+TKM_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+TKM_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+TKM_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+TKM_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+TKM_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+TKM_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+TKM_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+TKM_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// Host emulation of the PTX condition-code register.
+inline uint32_t &cc_flag() { static thread_local uint32_t cc = 0; return cc; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; cc_flag() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + cc_flag(); cc_flag() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cc_flag(); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; cc_flag() = (uint32_t)(s >> 63); return (uint32_t)s; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - cc_flag(); cc_flag() = (uint32_t)(s >> 63); return (uint32_t)s; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cc_flag(); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(a * b) + c; cc_flag() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(a * b) + c + cc_flag(); cc_flag() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (((uint64_t)a * b) >> 32) + c + cc_flag(); cc_flag() = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + cc_flag()); }
+#endif
+
+// ---------------------------------------------------------------- field parameters
+struct FrParams {
+  static constexpr int N = 8;
+  static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+  TKM_HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t M[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return M[i];
+  }
+  TKM_HD static constexpr uint32_t r2(int i) {  // R^2 mod r
+    constexpr uint32_t M[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+    return M[i];
+  }
+  TKM_HD static constexpr uint32_t one(int i) {  // R mod r
+    constexpr uint32_t M[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+    return M[i];
+  }
+};
+struct FqParams {
+  static constexpr int N = 12;
+  static constexpr uint32_t INV = 0xfffcfffdu;  // -q^-1 mod 2^32
+  TKM_HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t M[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return M[i];
+  }
+  TKM_HD static constexpr uint32_t r2(int i) {
+    constexpr uint32_t M[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+    return M[i];
+  }
+  TKM_HD static constexpr uint32_t one(int i) {
+    constexpr uint32_t M[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+    return M[i];
+  }
+};
+
+// ---------------------------------------------------------------- field element
+template <class P>
+struct alignas(16) Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  TKM_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r;
+  }
+  TKM_HD static Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  TKM_HD static Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+  TKM_HD bool is_zero() const {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) acc |= v[i];
+    return acc == 0;
+  }
+  TKM_HD bool operator==(const Fp &o) const {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) acc |= v[i] ^ o.v[i];
+    return acc == 0;
+  }
+  TKM_HD bool operator!=(const Fp &o) const { return !(*this == o); }
+
+  // r = t - p if t >= p else t   (t < 2p)
+  TKM_HD static void final_sub(uint32_t *t) {
+    uint32_t d[N];
+    d[0] = sub_cc(t[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) d[i] = subc_cc(t[i], P::mod(i));
+    uint32_t borrow = subc(0, 0);  // 0xffffffff if t < p
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = borrow ? t[i] : d[i];
+  }
+
+  TKM_HD friend Fp operator+(const Fp &a, const Fp &b) {
+    Fp r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+    r.v[N - 1] = addc(a.v[N - 1], b.v[N - 1]);  // both moduli leave headroom in the top limb
+    final_sub(r.v);
+    return r;
+  }
+  TKM_HD friend Fp operator-(const Fp &a, const Fp &b) {
+    Fp r;
+    r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+    uint32_t mask = subc(0, 0);  // all-ones if a < b
+    r.v[0] = add_cc(r.v[0], P::mod(0) & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], P::mod(i) & mask);
+    r.v[N - 1] = addc(r.v[N - 1], P::mod(N - 1) & mask);
+    return r;
+  }
+  TKM_HD Fp neg() const { return zero() - *this; }
+  TKM_HD Fp dbl() const { return *this + *this; }
+
+  // ---- Montgomery product.  E = accumulator aligned at column 0, O = aligned at column 1:
+  // running total T = E + 2^32 * O.  See the derivation in DESIGN.md ("Field multiplication").
+  // (lo,hi)(acc[j],acc[j+1]) += a[j]*b for j = 0,2,..,N-2, one carry chain; returns with CC = carry out.
+  TKM_HD static void chain_mad(uint32_t *acc, const uint32_t *a, uint32_t b) {
+    acc[0] = mad_lo_cc(a[0], b, acc[0]);
+    acc[1] = madc_hi_cc(a[0], b, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = madc_lo_cc(a[j], b, acc[j]);
+      acc[j + 1] = madc_hi_cc(a[j], b, acc[j + 1]);
+    }
+  }
+  TKM_HD static void chain_mad_mod(uint32_t *acc, int first, uint32_t m) {
+    acc[0] = mad_lo_cc(P::mod(first), m, acc[0]);
+    acc[1] = madc_hi_cc(P::mod(first), m, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = madc_lo_cc(P::mod(first + j), m, acc[j]);
+      acc[j + 1] = madc_hi_cc(P::mod(first + j), m, acc[j + 1]);
+    }
+  }
+  // Reduction half-row: make column 0 of T vanish.  E aligned at column 0, O at column 1.
+  TKM_HD static void reduce_row(uint32_t *E, uint32_t *O) {
+    uint32_t m = mul_lo(E[0], P::INV);
+    chain_mad_mod(O, 1, m);  // odd limbs of p land on columns (1,2),(3,4),..; no carry out (T bound)
+    chain_mad_mod(E, 0, m);  // even limbs of p land on columns (0,1),(2,3),..
+    O[N - 1] = addc(O[N - 1], 0);  // carry out of column N-1 -> column N = O[N-1]
+  }
+  TKM_HD friend Fp operator*(const Fp &a, const Fp &b) {
+    uint32_t X[N], Y[N];
+    // row 0: X holds columns of even limbs of a, Y (shifted by one column) the odd limbs.
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      X[j] = mul_lo(a.v[j], b.v[0]);
+      X[j + 1] = mul_hi(a.v[j], b.v[0]);
+      Y[j] = mul_lo(a.v[j + 1], b.v[0]);
+      Y[j + 1] = mul_hi(a.v[j + 1], b.v[0]);
+    }
+    reduce_row(X, Y);
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      // Entering: T = E + 2^32*O with E[0] == 0.  T/2^32 = O + (E >> 32): O becomes the column-0
+      // accumulator (plus the stray word E[1]); E >> 64 becomes the column-1 accumulator.
+      uint32_t *E = (i & 1) ? X : Y;
+      uint32_t *O = (i & 1) ? Y : X;
+      uint32_t bi = b.v[i];
+      O[0] = add_cc(O[0], E[1]);
+#pragma unroll
+      for (int j = 1; j < N - 1; j += 2) {
+        E[j - 1] = madc_lo_cc(a.v[j], bi, E[j + 1]);
+        E[j] = madc_hi_cc(a.v[j], bi, E[j + 2]);
+      }
+      E[N - 2] = madc_lo_cc(a.v[N - 1], bi, 0);
+      E[N - 1] = madc_hi(a.v[N - 1], bi, 0);
+      chain_mad(O, a.v, bi);
+      E[N - 1] = addc(E[N - 1], 0);
+      reduce_row(O, E);
+    }
+    // N is even: after the last row E = Y (column 0, Y[0] == 0), O = X.  Result = O + (E >> 32).
+    Fp r;
+    r.v[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+    r.v[N - 1] = addc(X[N - 1], 0);
+    final_sub(r.v);
+    return r;
+  }
+  TKM_HD Fp sqr() const { return *this * *this; }
+
+  TKM_HD Fp to_mont() const { return *this * r2(); }
+  TKM_HD Fp from_mont() const {
+    Fp o = zero();
+    o.v[0] = 1;
+    return *this * o;
+  }
+  // a^e for a small public exponent.
+  TKM_HD Fp pow_u64(uint64_t e) const {
+    Fp acc = one(), base = *this;
+    while (e) {
+      if (e & 1) acc = acc * base;
+      base = base.sqr();
+      e >>= 1;
+    }
+    return acc;
+  }
+  // Fermat inverse a^(p-2); inv(0) = 0 like the reference backend (bivariate_polynomial/mod.rs:2011-2013).
+  TKM_HD Fp inv() const {
+    Fp acc = one(), base = *this;
+    uint32_t borrow = 2;  // exponent limbs of p - 2, borrow rippling up (r ends in ...00000001)
+    for (int i = 0; i < N; i++) {
+      uint32_t m = P::mod(i);
+      uint32_t e = m - borrow;
+      borrow = (m < borrow) ? 1u : 0u;
+      for (int b = 0; b < 32; b++) {
+        if ((e >> b) & 1) acc = acc * base;
+        base = base.sqr();
+      }
+    }
+    return acc;
+  }
+};
+
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+}  // namespace tkm

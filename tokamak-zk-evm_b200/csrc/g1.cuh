@@ -1,0 +1,149 @@
+// BLS12-381 G1 (y^2 = x^3 + 4) point arithmetic in extended Jacobian "XYZZ" coordinates.
+//
+// Replaces the G1Affine / G1Projective arithmetic the reference reaches through ICICLE
+// (libs/src/group_structures/mod.rs:888-947 G1serde ops; msm::msm at iotools/mod.rs:2093-2099).
+// A point is (X, Y, ZZ, ZZZ) with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; ZZ == 0 is the identity.
+// Affine points (x, y) use the reference's convention (0, 0) = identity
+// (group_structures/mod.rs:889-893).  All coordinates are in Montgomery form on the device.
+//
+// Formulas: Explicit-Formulas Database, short Weierstrass a = 0, "xyzz": madd-2008-s (8M+2S),
+// add-2008-s (12M+2S), dbl-2008-s-1 (6M+4S... 9 products here), mdbl-2008-s-1.
+// Every exceptional case (identity operands, P + P, P + (-P)) is handled so results are exact.
+#pragma once
+#include "ff.cuh"
+
+namespace tkm {
+
+struct alignas(16) G1Affine {
+  Fq x, y;
+  TKM_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
+  TKM_HD static G1Affine identity() { return G1Affine{Fq::zero(), Fq::zero()}; }
+  TKM_HD G1Affine neg() const { return is_identity() ? *this : G1Affine{x, y.neg()}; }
+};
+
+struct alignas(16) G1Xyzz {
+  Fq X, Y, ZZ, ZZZ;
+  TKM_HD bool is_identity() const { return ZZ.is_zero(); }
+  TKM_HD static G1Xyzz identity() { return G1Xyzz{Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()}; }
+  TKM_HD static G1Xyzz from_affine(const G1Affine &p) {
+    if (p.is_identity()) return identity();
+    return G1Xyzz{p.x, p.y, Fq::one(), Fq::one()};
+  }
+  TKM_HD G1Xyzz neg() const { return G1Xyzz{X, Y.neg(), ZZ, ZZZ}; }
+};
+
+// 2 * (x, y) for an affine, non-identity point (mdbl-2008-s-1).  y != 0 on G1 (odd prime order).
+TKM_HD G1Xyzz g1_mdbl(const G1Affine &p) {
+  Fq U = p.y.dbl();
+  Fq V = U.sqr();
+  Fq W = U * V;
+  Fq S = p.x * V;
+  Fq XX = p.x.sqr();
+  Fq M = XX.dbl() + XX;
+  G1Xyzz r;
+  r.X = M.sqr() - S.dbl();
+  r.Y = M * (S - r.X) - W * p.y;
+  r.ZZ = V;
+  r.ZZZ = W;
+  return r;
+}
+
+// 2 * P (dbl-2008-s-1).
+TKM_HD G1Xyzz g1_dbl(const G1Xyzz &p) {
+  if (p.is_identity()) return p;
+  Fq U = p.Y.dbl();
+  Fq V = U.sqr();
+  Fq W = U * V;
+  Fq S = p.X * V;
+  Fq XX = p.X.sqr();
+  Fq M = XX.dbl() + XX;
+  G1Xyzz r;
+  r.X = M.sqr() - S.dbl();
+  r.Y = M * (S - r.X) - W * p.Y;
+  r.ZZ = V * p.ZZ;
+  r.ZZZ = W * p.ZZZ;
+  return r;
+}
+
+// acc += (x, y)  (madd-2008-s), all exceptional cases handled.
+TKM_HD void g1_madd(G1Xyzz &acc, const G1Affine &p) {
+  if (p.is_identity()) return;
+  if (acc.is_identity()) {
+    acc = G1Xyzz{p.x, p.y, Fq::one(), Fq::one()};
+    return;
+  }
+  Fq U2 = p.x * acc.ZZ;
+  Fq S2 = p.y * acc.ZZZ;
+  Fq Pd = U2 - acc.X;
+  Fq Rd = S2 - acc.Y;
+  if (Pd.is_zero()) {
+    if (Rd.is_zero())
+      acc = g1_mdbl(p);
+    else
+      acc = G1Xyzz::identity();
+    return;
+  }
+  Fq PP = Pd.sqr();
+  Fq PPP = Pd * PP;
+  Fq Q = acc.X * PP;
+  Fq X3 = Rd.sqr() - PPP - Q.dbl();
+  Fq Y3 = Rd * (Q - X3) - acc.Y * PPP;
+  acc.X = X3;
+  acc.Y = Y3;
+  acc.ZZ = acc.ZZ * PP;
+  acc.ZZZ = acc.ZZZ * PPP;
+}
+
+// acc += q  (add-2008-s), all exceptional cases handled.
+TKM_HD void g1_add(G1Xyzz &acc, const G1Xyzz &q) {
+  if (q.is_identity()) return;
+  if (acc.is_identity()) {
+    acc = q;
+    return;
+  }
+  Fq U1 = acc.X * q.ZZ;
+  Fq U2 = q.X * acc.ZZ;
+  Fq S1 = acc.Y * q.ZZZ;
+  Fq S2 = q.Y * acc.ZZZ;
+  Fq Pd = U2 - U1;
+  Fq Rd = S2 - S1;
+  if (Pd.is_zero()) {
+    if (Rd.is_zero())
+      acc = g1_dbl(acc);
+    else
+      acc = G1Xyzz::identity();
+    return;
+  }
+  Fq PP = Pd.sqr();
+  Fq PPP = Pd * PP;
+  Fq Q = U1 * PP;
+  Fq X3 = Rd.sqr() - PPP - Q.dbl();
+  Fq Y3 = Rd * (Q - X3) - S1 * PPP;
+  acc.X = X3;
+  acc.Y = Y3;
+  acc.ZZ = acc.ZZ * q.ZZ * PP;
+  acc.ZZZ = acc.ZZZ * q.ZZZ * PPP;
+}
+
+// Affine (x, y) = (X/ZZ, Y/ZZZ) with one field inversion; identity -> (0, 0).
+TKM_HD G1Affine g1_to_affine(const G1Xyzz &p) {
+  if (p.is_identity()) return G1Affine::identity();
+  Fq t = (p.ZZ * p.ZZZ).inv();
+  Fq zz_inv = t * p.ZZZ;
+  Fq zzz_inv = t * p.ZZ;
+  return G1Affine{p.X * zz_inv, p.Y * zzz_inv};
+}
+
+// k * P by left-to-right double-and-add, k canonical (non-Montgomery) little-endian limbs.
+// Used for the handful of single scalar multiplications of the prover
+// (G1serde * ScalarField, group_structures/mod.rs:929-947).
+TKM_HD G1Xyzz g1_mul_scalar(const G1Affine &p, const uint32_t *k, int nlimbs) {
+  G1Xyzz acc = G1Xyzz::identity();
+  for (int i = nlimbs * 32 - 1; i >= 0; i--) {
+    acc = g1_dbl(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1) g1_madd(acc, p);
+  }
+  return acc;
+}
+
+}  // namespace tkm

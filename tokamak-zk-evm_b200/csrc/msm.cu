@@ -1,0 +1,440 @@
+// BLS12-381 G1 multi-scalar multiplication for sm_100a: signed-digit Pippenger.
+//
+// Replaces msm::msm(scalars, bases, MSMConfig::default(), out[1]) as the reference calls it for every
+// commitment (libs/src/iotools/mod.rs:2093-2099; libs/src/group_structures/mod.rs:108-114,135-141).
+//
+// Pipeline (all on the context stream, no host synchronisation until the 96-byte result is read):
+//   1. k_decompose     one thread per scalar: (optional from-Montgomery,) signed c-bit digits;
+//                      emits (bucket key, base index | sign) pairs, window-major, zero digits keyed
+//                      to a trash bucket that sorts last.
+//   2. cub radix sort  of the pairs by bucket key (only the significant key bits).
+//   3. k_accumulate    one thread per fixed-length chunk of the sorted list, so work is balanced for
+//                      ANY scalar distribution: XYZZ mixed additions of gathered affine bases; runs
+//                      that lie strictly inside a chunk are final and go straight to their bucket,
+//                      the first/last run of every chunk go to a (key, point) partial list.
+//   4. k_segreduce     warp-cooperative segmented reduction of the partial list (shuffle tree of
+//                      full XYZZ additions, 32 entries per warp), repeated until one warp remains.
+//   5. k_bucket_seg /  parallel window reduction: running sums over 16-bucket segments, then per
+//      k_bucket_bits   window a masked tree-sum per index bit (sum_d d*B_d = sum_k 2^k sum_{d: bit k} B_d),
+//   6. k_final         per-window recombination in parallel lanes, Horner over windows, one inversion
+//                      to affine.
+// Integer-pipe bound: N*W mixed additions of ~10 Fq products each; no tensor cores.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace tkm {
+
+struct MsmGeom {
+  uint32_t c;        // window bits
+  uint32_t W;        // windows
+  uint32_t B;        // buckets per window = 2^(c-1)
+  uint32_t logB;
+  uint32_t nbuckets; // W*B (+1 trash bucket at index nbuckets)
+  uint32_t g;        // bucket segment length for the window reduction
+  uint32_t logg;
+  uint32_t nseg;     // segments per window = B/g
+  uint32_t nbits;    // log2(nseg)
+};
+
+static MsmGeom pick_geom(size_t n) {
+  // minimise W*(n + 3*2^(c-1)) -- mixed adds plus ~3 madd-equivalents per bucket of reduction
+  double best = 1e300;
+  uint32_t bc = 8;
+  for (uint32_t c = 4; c <= 20; c++) {
+    uint32_t W = (256 + c - 1) / c;
+    double cost = (double)W * ((double)n + 3.0 * (double)(1u << (c - 1)));
+    if (cost < best) {
+      best = cost;
+      bc = c;
+    }
+  }
+  MsmGeom m;
+  m.c = bc;
+  m.W = (256 + bc - 1) / bc;
+  m.logB = bc - 1;
+  m.B = 1u << m.logB;
+  m.nbuckets = m.W * m.B;
+  m.logg = m.logB < 4 ? m.logB : 4;
+  m.g = 1u << m.logg;
+  m.nseg = m.B >> m.logg;
+  m.nbits = m.logB - m.logg;
+  return m;
+}
+
+__device__ __forceinline__ G1Affine ldg_affine(const G1Affine *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 r[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) r[i] = __ldg(q + i);
+  G1Affine a;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    a.x.v[4 * i + 0] = r[i].x; a.x.v[4 * i + 1] = r[i].y; a.x.v[4 * i + 2] = r[i].z; a.x.v[4 * i + 3] = r[i].w;
+    a.y.v[4 * i + 0] = r[i + 3].x; a.y.v[4 * i + 1] = r[i + 3].y; a.y.v[4 * i + 2] = r[i + 3].z; a.y.v[4 * i + 3] = r[i + 3].w;
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------- 1. digit decomposition
+__global__ void __launch_bounds__(256) k_decompose(const Fr *__restrict__ scalars, int scalars_mont, size_t s_row_stride,
+                                                   size_t b_row_stride, const uint32_t *__restrict__ gather,
+                                                   uint32_t rows, uint32_t cols, MsmGeom m, uint32_t *__restrict__ keys,
+                                                   uint32_t *__restrict__ vals) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    uint32_t i = (uint32_t)(k / cols), j = (uint32_t)(k % cols);
+    Fr s = scalars[(size_t)i * s_row_stride + j];
+    if (scalars_mont) s = s.from_mont();
+    uint32_t base_idx = gather ? gather[k] : (uint32_t)((size_t)i * b_row_stride + j);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < m.W; w++) {
+      uint32_t bit = w * m.c;
+      uint32_t limb = bit >> 5, sh = bit & 31;
+      uint32_t raw = 0;
+      if (limb < 8) {
+        uint64_t two = s.v[limb];
+        if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+        raw = (uint32_t)(two >> sh) & ((1u << m.c) - 1);
+      }
+      raw += carry;
+      uint32_t neg = 0, mag = raw;
+      carry = 0;
+      if (raw > m.B) {
+        mag = (1u << m.c) - raw;
+        neg = 1;
+        carry = 1;
+      }
+      size_t slot = (size_t)w * n + k;
+      keys[slot] = mag ? (w * m.B + mag - 1) : m.nbuckets;
+      vals[slot] = base_idx | (neg << 31);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- 3. chunked bucket accumulation
+__device__ __forceinline__ void store_xyzz(G1Xyzz *dst, const G1Xyzz &p) {
+  uint4 *q = reinterpret_cast<uint4 *>(dst);
+  const Fq *f[4] = {&p.X, &p.Y, &p.ZZ, &p.ZZZ};
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) q[3 * c + i] = make_uint4(f[c]->v[4 * i], f[c]->v[4 * i + 1], f[c]->v[4 * i + 2], f[c]->v[4 * i + 3]);
+}
+__device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *src) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(src);
+  G1Xyzz p;
+  Fq *f[4] = {&p.X, &p.Y, &p.ZZ, &p.ZZZ};
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      uint4 v = q[3 * c + i];
+      f[c]->v[4 * i] = v.x; f[c]->v[4 * i + 1] = v.y; f[c]->v[4 * i + 2] = v.z; f[c]->v[4 * i + 3] = v.w;
+    }
+  return p;
+}
+
+constexpr int ACC_THREADS = 128;
+
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                           size_t M, uint32_t chunk, const G1Affine *__restrict__ bases,
+                                                           uint32_t invalid_key, G1Xyzz *__restrict__ buckets,
+                                                           uint32_t *__restrict__ pkeys, G1Xyzz *__restrict__ ppts,
+                                                           size_t nthreads) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= nthreads) return;
+  size_t start = t * chunk, end = start + chunk;
+  if (end > M) end = M;
+  uint32_t cur = keys[start];
+  G1Xyzz acc = G1Xyzz::identity();
+  bool first_run = true;
+  // software pipeline: the next base is in flight while the current addition runs
+  uint32_t nk = cur, nv = vals[start];
+  G1Affine npt = (nk != invalid_key) ? ldg_affine(bases + (nv & 0x7fffffffu)) : G1Affine::identity();
+  for (size_t i = start; i < end; i++) {
+    uint32_t k = nk, v = nv;
+    G1Affine pt = npt;
+    if (k == invalid_key && cur == invalid_key) break;  // sorted last: nothing but zero digits from here on
+    if (i + 1 < end) {
+      nk = keys[i + 1];
+      nv = vals[i + 1];
+      if (nk != invalid_key) npt = ldg_affine(bases + (nv & 0x7fffffffu));
+    }
+    if (k != cur) {
+      if (first_run) {
+        pkeys[2 * t] = cur;
+        store_xyzz(ppts + 2 * t, acc);
+        first_run = false;
+      } else {
+        store_xyzz(buckets + cur, acc);
+      }
+      acc = G1Xyzz::identity();
+      cur = k;
+      if (k == invalid_key) break;
+    }
+    if (v >> 31) pt.y = pt.y.neg();
+    g1_madd(acc, pt);
+  }
+  if (first_run) {
+    pkeys[2 * t] = cur;
+    store_xyzz(ppts + 2 * t, acc);
+    pkeys[2 * t + 1] = cur;
+    store_xyzz(ppts + 2 * t + 1, G1Xyzz::identity());
+  } else {
+    pkeys[2 * t + 1] = cur;
+    store_xyzz(ppts + 2 * t + 1, acc);
+  }
+}
+
+// ---------------------------------------------------------------- 4. warp-cooperative segmented reduction
+__device__ __forceinline__ Fq shfl_down_fq(const Fq &a, int d) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < Fq::N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+  return r;
+}
+
+constexpr int SEG_THREADS = 128;
+
+// Entries [32*w, 32*w+32) belong to warp w.  Sorted keys: equal keys are contiguous.  First run of a
+// warp -> slot 2w, last run -> slot 2w+1 (identity if the warp holds one run), runs strictly inside
+// the warp are final.  When `last` (one warp left) every run is final.
+__global__ void __launch_bounds__(SEG_THREADS) k_segreduce(const uint32_t *__restrict__ keys_in, const G1Xyzz *__restrict__ pts_in,
+                                                          size_t P, G1Xyzz *__restrict__ buckets, uint32_t *__restrict__ keys_out,
+                                                          G1Xyzz *__restrict__ pts_out, int last, uint32_t pad_key) {
+  const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t nwarps = (P + 31) >> 5;
+  if (warp >= nwarps) return;
+  const size_t i = warp * 32 + lane;
+  uint32_t key = pad_key;
+  G1Xyzz pt = G1Xyzz::identity();
+  if (i < P) {
+    key = keys_in[i];
+    pt = load_xyzz(pts_in + i);
+  }
+  const uint32_t key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (key_prev != key);
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+    G1Xyzz o;
+    o.X = shfl_down_fq(pt.X, d);
+    o.Y = shfl_down_fq(pt.Y, d);
+    o.ZZ = shfl_down_fq(pt.ZZ, d);
+    o.ZZZ = shfl_down_fq(pt.ZZZ, d);
+    if (lane + d < 32 && ok == key) g1_add(pt, o);
+  }
+  const uint32_t key_first = __shfl_sync(0xffffffffu, key, 0);
+  const uint32_t key_last = __shfl_sync(0xffffffffu, key, 31);
+  if (head) {
+    if (last) {
+      store_xyzz(buckets + key, pt);
+    } else if (key == key_first) {
+      keys_out[2 * warp] = key;
+      store_xyzz(pts_out + 2 * warp, pt);
+      if (key_last == key_first) {
+        keys_out[2 * warp + 1] = key;
+        store_xyzz(pts_out + 2 * warp + 1, G1Xyzz::identity());
+      }
+    } else if (key == key_last) {
+      keys_out[2 * warp + 1] = key;
+      store_xyzz(pts_out + 2 * warp + 1, pt);
+    } else {
+      store_xyzz(buckets + key, pt);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- 5. window reduction
+// Segment s of window w covers digits d = s*g+1 .. s*g+g (bucket slots w*B + s*g .. +g-1).
+// run = sum B_d, acc = sum (d - s*g) B_d.  Then  sum_d d*B_d = sum_s acc_s + g * sum_s s*run_s.
+__global__ void __launch_bounds__(128) k_bucket_seg(const G1Xyzz *__restrict__ buckets, MsmGeom m, G1Xyzz *__restrict__ seg_acc,
+                                                   G1Xyzz *__restrict__ seg_run) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t total = (size_t)m.W * m.nseg;
+  if (t >= total) return;
+  const G1Xyzz *b = buckets + t * m.g;
+  G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
+  for (int k = (int)m.g - 1; k >= 0; k--) {
+    G1Xyzz p = load_xyzz(b + k);
+    g1_add(run, p);
+    g1_add(acc, run);
+  }
+  store_xyzz(seg_acc + t, acc);
+  store_xyzz(seg_run + t, run);
+}
+
+constexpr int BITS_THREADS = 128;
+// Block (w, k): k < nbits -> M_k = sum over segments s with bit k set of run_s ; k == nbits -> A = sum_s acc_s.
+__global__ void __launch_bounds__(BITS_THREADS) k_bucket_bits(const G1Xyzz *__restrict__ seg_acc, const G1Xyzz *__restrict__ seg_run,
+                                                             MsmGeom m, G1Xyzz *__restrict__ out) {
+  __shared__ G1Xyzz sh[BITS_THREADS];
+  const uint32_t w = blockIdx.x / (m.nbits + 1), k = blockIdx.x % (m.nbits + 1);
+  const G1Xyzz *src = (k == m.nbits ? seg_acc : seg_run) + (size_t)w * m.nseg;
+  G1Xyzz acc = G1Xyzz::identity();
+  for (uint32_t s = threadIdx.x; s < m.nseg; s += BITS_THREADS) {
+    if (k == m.nbits || ((s >> k) & 1)) {
+      G1Xyzz p = load_xyzz(src + s);
+      g1_add(acc, p);
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int stride = BITS_THREADS / 2; stride > 0; stride >>= 1) {
+    if ((int)threadIdx.x < stride) {
+      G1Xyzz a = sh[threadIdx.x], b = sh[threadIdx.x + stride];
+      g1_add(a, b);
+      sh[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
+}
+
+// ---------------------------------------------------------------- 6. recombination
+// Lane w: S_w = A_w + g * sum_k 2^k M_{w,k}.  Lane 0 then runs Horner over windows and converts to affine.
+__global__ void __launch_bounds__(32) k_final(const G1Xyzz *__restrict__ parts, MsmGeom m, G1Xyzz *__restrict__ window_sums,
+                                             G1Affine *__restrict__ out_mont, uint32_t *__restrict__ out_canonical) {
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t w = lane; w < m.W; w += 32) {
+    const G1Xyzz *pw = parts + (size_t)w * (m.nbits + 1);
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int k = (int)m.nbits - 1; k >= 0; k--) {
+      acc = g1_dbl(acc);
+      G1Xyzz mk = load_xyzz(pw + k);
+      g1_add(acc, mk);
+    }
+    for (uint32_t k = 0; k < m.logg; k++) acc = g1_dbl(acc);
+    G1Xyzz a = load_xyzz(pw + m.nbits);
+    g1_add(acc, a);
+    store_xyzz(window_sums + w, acc);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int w = (int)m.W - 1; w >= 0; w--) {
+      for (uint32_t k = 0; k < m.c; k++) acc = g1_dbl(acc);
+      G1Xyzz s = load_xyzz(window_sums + w);
+      g1_add(acc, s);
+    }
+    G1Affine r = g1_to_affine(acc);
+    if (out_mont) *out_mont = r;
+    Fq x = r.x.from_mont(), y = r.y.from_mont();
+    for (int i = 0; i < 12; i++) {
+      out_canonical[i] = x.v[i];
+      out_canonical[12 + i] = y.v[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill_identity(G1Xyzz *p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    store_xyzz(p + i, G1Xyzz::identity());
+}
+
+__global__ void __launch_bounds__(256) k_g1_to_mont(const G1Affine *__restrict__ in, G1Affine *__restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    G1Affine a = in[i];
+    a.x = a.x.to_mont();
+    a.y = a.y.to_mont();
+    out[i] = a;
+  }
+}
+
+int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  k_g1_to_mont<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);
+  return launch_check(ctx, "k_g1_to_mont");
+}
+
+int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
+  const size_t n = in.rows * in.cols;
+  if (n == 0) {  // msm_g1_bases returns the identity for empty input (group_structures/mod.rs:131-133)
+    memset(out96, 0, 96);
+    return TKM_OK;
+  }
+  if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
+  if (in.idx && in.rows != 1) return fail(TKM_ERR_INVALID_ARGUMENT, "indexed MSM must be one row");
+  const MsmGeom m = pick_geom(n);
+  const size_t M = n * m.W;
+  const uint32_t invalid = m.nbuckets;
+  uint32_t key_bits = 1;
+  while ((1ull << key_bits) <= invalid) key_bits++;
+
+  Scratch<uint32_t> keys, vals, keys_s, vals_s;
+  TKM_TRY(keys.alloc(ctx, M));
+  TKM_TRY(vals.alloc(ctx, M));
+  TKM_TRY(keys_s.alloc(ctx, M));
+  TKM_TRY(vals_s.alloc(ctx, M));
+  k_decompose<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in.scalars, in.scalars_mont ? 1 : 0, in.scalar_row_stride,
+                                                                        in.base_row_stride, in.idx, (uint32_t)in.rows,
+                                                                        (uint32_t)in.cols, m, keys.p, vals.p);
+  TKM_TRY(launch_check(ctx, "k_decompose"));
+
+  size_t temp_bytes = 0;
+  TKM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)M, 0, (int)key_bits,
+                                           ctx->stream));
+  Scratch<uint8_t> temp;
+  TKM_TRY(temp.alloc(ctx, temp_bytes));
+  TKM_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)M, 0, (int)key_bits,
+                                           ctx->stream));
+  ctx->launches += 4;  // cub's histogram + onesweep passes (approximate; they are library launches)
+
+  Scratch<G1Xyzz> buckets;
+  TKM_TRY(buckets.alloc(ctx, (size_t)m.nbuckets + 1));
+  k_fill_identity<<<grid_for((size_t)m.nbuckets + 1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, (size_t)m.nbuckets + 1);
+  TKM_TRY(launch_check(ctx, "k_fill_identity"));
+
+  // chunk length: long enough to amortise the two partial slots per thread, short enough to fill the GPU
+  uint32_t chunk = 128;
+  while (chunk > 8 && (M / chunk) < (size_t)ctx->sm_count * 4 * ACC_THREADS / 2) chunk >>= 1;
+  const size_t T = (M + chunk - 1) / chunk;
+  size_t P = 2 * T;
+  Scratch<uint32_t> pk_a, pk_b;
+  Scratch<G1Xyzz> pp_a, pp_b;
+  TKM_TRY(pk_a.alloc(ctx, P));
+  TKM_TRY(pp_a.alloc(ctx, P));
+  const size_t P2 = 2 * ((P + 31) / 32);
+  TKM_TRY(pk_b.alloc(ctx, P2));
+  TKM_TRY(pp_b.alloc(ctx, P2));
+  k_accumulate<<<(unsigned)((T + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+      keys_s.p, vals_s.p, M, chunk, in.bases, invalid, buckets.p, pk_a.p, pp_a.p, T);
+  TKM_TRY(launch_check(ctx, "k_accumulate"));
+
+  uint32_t *kin = pk_a.p, *kout = pk_b.p;
+  G1Xyzz *pin = pp_a.p, *pout = pp_b.p;
+  for (;;) {
+    const size_t nwarps = (P + 31) / 32;
+    const int last = nwarps == 1;
+    const size_t threads = nwarps * 32;
+    k_segreduce<<<(unsigned)((threads + SEG_THREADS - 1) / SEG_THREADS), SEG_THREADS, 0, ctx->stream>>>(kin, pin, P, buckets.p, kout, pout,
+                                                                                                  last, invalid);
+    TKM_TRY(launch_check(ctx, "k_segreduce"));
+    if (last) break;
+    P = 2 * nwarps;
+    uint32_t *tk = kin; kin = kout; kout = tk;
+    G1Xyzz *tp = pin; pin = pout; pout = tp;
+  }
+
+  const size_t nsegs = (size_t)m.W * m.nseg;
+  Scratch<G1Xyzz> seg_acc, seg_run, parts, wsum;
+  Scratch<uint32_t> res;
+  TKM_TRY(seg_acc.alloc(ctx, nsegs));
+  TKM_TRY(seg_run.alloc(ctx, nsegs));
+  TKM_TRY(parts.alloc(ctx, (size_t)m.W * (m.nbits + 1)));
+  TKM_TRY(wsum.alloc(ctx, m.W));
+  TKM_TRY(res.alloc(ctx, 24));
+  k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets.p, m, seg_acc.p, seg_run.p);
+  TKM_TRY(launch_check(ctx, "k_bucket_seg"));
+  k_bucket_bits<<<m.W * (m.nbits + 1), BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, parts.p);
+  TKM_TRY(launch_check(ctx, "k_bucket_bits"));
+  k_final<<<1, 32, 0, ctx->stream>>>(parts.p, m, wsum.p, nullptr, res.p);
+  TKM_TRY(launch_check(ctx, "k_final"));
+  TKM_CUDA(cudaMemcpyAsync(out96, res.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+}  // namespace tkm

@@ -1,0 +1,678 @@
+// Device-resident bivariate polynomial engine: the DensePolynomialExt operations of the reference
+// (libs/src/bivariate_polynomial/mod.rs) without its host round-trips.  Coefficients live on the
+// device in Montgomery form, row-major [x_size][y_size] (X = row index, Y contiguous;
+// bivariate_polynomial/mod.rs:1756).  Every kernel here is HBM-bound (a few field ops per 32-byte
+// element): 128-bit accesses, threads walk the contiguous Y axis.
+#include "common.cuh"
+
+namespace tkm {
+
+int32_t fill_powers_public(tkm_ctx *ctx, Fr *out, const Fr &base, const Fr &scale, size_t count);
+
+// ---------------------------------------------------------------- shape management
+// dst[(i+ox)*dy + (j+oy)] = src[i*sy + j], i < rows, j < cols   (resize / mul_monomial / clone)
+__global__ void __launch_bounds__(256) k_copy_rect(Fr *__restrict__ dst, size_t dy, size_t ox, size_t oy, const Fr *__restrict__ src,
+                                                   size_t sy, size_t rows, size_t cols) {
+  size_t total = rows * cols;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    size_t i = k / cols, j = k % cols;
+    dst[(i + ox) * dy + (j + oy)] = src[i * sy + j];
+  }
+}
+
+// find_degree (bivariate_polynomial/mod.rs:1480-1515): highest row / column holding a non-zero coefficient.
+__global__ void __launch_bounds__(256) k_find_degree(const Fr *__restrict__ c, size_t x_size, size_t y_size, int *__restrict__ deg) {
+  size_t total = x_size * y_size;
+  int mx = -1, my = -1;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    Fr v = c[k];
+    if (!v.is_zero()) {
+      int i = (int)(k / y_size), j = (int)(k % y_size);
+      mx = max(mx, i);
+      my = max(my, j);
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    my = max(my, __shfl_xor_sync(0xffffffffu, my, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mx >= 0) atomicMax(deg, mx);
+    if (my >= 0) atomicMax(deg + 1, my);
+  }
+}
+
+// out = ca*a + cb*b on the union shape (operator impls, bivariate_polynomial/mod.rs:532-763, and poly_comb!).
+__global__ void __launch_bounds__(256) k_axpby(Fr *__restrict__ out, size_t ox, size_t oy, const Fr *__restrict__ a, size_t ax, size_t ay,
+                                               Fr ca, int ca_one, const Fr *__restrict__ b, size_t bx, size_t by, Fr cb, int cb_one) {
+  size_t total = ox * oy;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    size_t i = k / oy, j = k % oy;
+    Fr r = Fr::zero();
+    if (i < ax && j < ay) {
+      Fr v = a[i * ay + j];
+      r = ca_one ? v : v * ca;
+    }
+    if (b && i < bx && j < by) {
+      Fr v = b[i * by + j];
+      r = r + (cb_one ? v : v * cb);
+    }
+    out[k] = r;
+  }
+}
+
+__global__ void k_add_scalar(Fr *c, Fr s) { c[0] = c[0] + s; }
+
+// c_ij * px[i] * py[j]  (scale_coeffs_x / _y, bivariate_polynomial/mod.rs:1553-1613)
+__global__ void __launch_bounds__(256) k_scale_coeffs(Fr *__restrict__ out, const Fr *__restrict__ in, size_t x_size, size_t y_size,
+                                                      const Fr *__restrict__ px, const Fr *__restrict__ py) {
+  size_t total = x_size * y_size;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    size_t i = k / y_size, j = k % y_size;
+    Fr v = in[k];
+    if (px) { Fr s = px[i]; v = v * s; }
+    if (py) { Fr s = py[j]; v = v * s; }
+    out[k] = v;
+  }
+}
+
+// ---------------------------------------------------------------- evaluation
+__device__ __forceinline__ Fr warp_sum(Fr v) {
+  for (int d = 16; d > 0; d >>= 1) {
+    Fr o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.v[i] = __shfl_xor_sync(0xffffffffu, v.v[i], d);
+    v = v + o;
+  }
+  return v;
+}
+// out[i] = sum_j c[i][j] * w[j]: one warp per row (eval_y, bivariate_polynomial/mod.rs:1731-1740).
+__global__ void __launch_bounds__(256) k_row_dot(Fr *__restrict__ out, const Fr *__restrict__ c, size_t rows, size_t cols,
+                                                 const Fr *__restrict__ w) {
+  size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  int lane = threadIdx.x & 31;
+  for (size_t i = warp; i < rows; i += nwarps) {
+    Fr acc = Fr::zero();
+    for (size_t j = lane; j < cols; j += 32) {
+      Fr v = c[i * cols + j], s = w[j];
+      acc = acc + v * s;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[i] = acc;
+  }
+}
+// partial[chunk][j] = sum_{i in chunk} c[i][j] * w[i]   (eval_x, bivariate_polynomial/mod.rs:1719-1729)
+__global__ void __launch_bounds__(128) k_col_dot_partial(Fr *__restrict__ partial, const Fr *__restrict__ c, size_t rows, size_t cols,
+                                                         const Fr *__restrict__ w, size_t rows_per_chunk) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t chunk = blockIdx.y;
+  if (j >= cols) return;
+  size_t lo = chunk * rows_per_chunk, hi = lo + rows_per_chunk;
+  if (hi > rows) hi = rows;
+  Fr acc = Fr::zero();
+  for (size_t i = lo; i < hi; i++) {
+    Fr v = c[i * cols + j];
+    if (w) { Fr s = w[i]; v = v * s; }
+    acc = acc + v;
+  }
+  partial[chunk * cols + j] = acc;
+}
+
+// ---------------------------------------------------------------- division by vanishing polynomials
+// div_by_vanishing_opt (bivariate_polynomial/mod.rs:2284-2410), restated as two chain kernels.
+// Kernel 1: thread (lx < c, yy < d) folds the m X-blocks and walks its Y chain (stride d):
+//   qy[lx][y] = qy[lx][y-d] - acc[lx][y] for y < y_size - d, else 0.
+__global__ void __launch_bounds__(256) k_vanish_qy(Fr *__restrict__ qy, const Fr *__restrict__ p, size_t x_size, size_t y_size, size_t c,
+                                                   size_t d) {
+  size_t total = c * d;
+  size_t m = x_size / c, n = y_size / d;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    size_t lx = t / d, yy = t % d;
+    Fr prev = Fr::zero();
+    for (size_t k = 0; k < n; k++) {
+      size_t y = yy + k * d;
+      Fr q = Fr::zero();
+      if (k + 1 < n) {
+        Fr acc = Fr::zero();
+        for (size_t bx = 0; bx < m; bx++) {
+          Fr v = p[(bx * c + lx) * y_size + y];
+          acc = acc + v;
+        }
+        q = prev - acc;
+        prev = q;
+      }
+      qy[lx * y_size + y] = q;
+    }
+  }
+}
+// Kernel 2: thread (lx < c, y) walks its X chain (stride c) over B = P + (Y^d - 1) qy:
+//   qx[x][y] = qx[x-c][y] - B[x][y] for x < x_size - c, else 0.
+__global__ void __launch_bounds__(256) k_vanish_qx(Fr *__restrict__ qx, const Fr *__restrict__ p, const Fr *__restrict__ qy, size_t x_size,
+                                                   size_t y_size, size_t c, size_t d) {
+  size_t total = c * y_size;
+  size_t m = x_size / c;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    size_t lx = t / y_size, y = t % y_size;
+    Fr prev = Fr::zero();
+    for (size_t bx = 0; bx < m; bx++) {
+      size_t x = bx * c + lx;
+      Fr q = Fr::zero();
+      if (bx + 1 < m) {
+        Fr b = p[x * y_size + y];
+        if (bx == 0 && y_size > d) {
+          if (y < y_size - d) { Fr t1 = qy[lx * y_size + y]; b = b + t1; }
+          if (y >= d) { Fr t2 = qy[lx * y_size + y - d]; b = b - t2; }
+        }
+        q = prev - b;
+        prev = q;
+      }
+      qx[x * y_size + y] = q;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Ruffini division
+// div_by_ruffini (bivariate_polynomial/mod.rs:2412-2477).  One thread per Y column runs the
+// synthetic division along X (a Horner chain); remainders go to rx[y].
+__global__ void __launch_bounds__(128) k_ruffini_x(Fr *__restrict__ qx, Fr *__restrict__ rx, const Fr *__restrict__ p, size_t x_size,
+                                                   size_t y_size, Fr pt) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= y_size) return;
+  if (x_size < 2) {
+    rx[j] = p[j];
+    qx[j] = Fr::zero();
+    return;
+  }
+  Fr b = p[(x_size - 1) * y_size + j];
+  qx[(x_size - 1) * y_size + j] = Fr::zero();
+  qx[(x_size - 2) * y_size + j] = b;
+  for (size_t i = x_size - 2; i >= 1; i--) {
+    Fr v = p[i * y_size + j];
+    b = v + b * pt;
+    qx[(i - 1) * y_size + j] = b;
+  }
+  Fr v0 = p[j];
+  rx[j] = v0 + b * pt;
+}
+// Single chain along Y on the remainders: qy[0..y_size), r.
+__global__ void k_ruffini_y(Fr *__restrict__ qy, Fr *__restrict__ r, const Fr *__restrict__ rx, size_t y_size, Fr pt) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (y_size < 2) {
+    qy[0] = Fr::zero();
+    r[0] = rx[0];
+    return;
+  }
+  Fr b = rx[y_size - 1];
+  qy[y_size - 1] = Fr::zero();
+  qy[y_size - 2] = b;
+  for (size_t i = y_size - 2; i >= 1; i--) {
+    Fr v = rx[i];
+    b = v + b * pt;
+    qy[i - 1] = b;
+  }
+  Fr v0 = rx[0];
+  r[0] = v0 + b * pt;
+}
+
+// ---------------------------------------------------------------- host orchestration
+static int32_t poly_alloc(tkm_ctx *ctx, size_t x, size_t y, tkm_poly **out) {
+  if (!is_pow2(x) || !is_pow2(y)) return fail(TKM_ERR_INVALID_ARGUMENT, "The input sizes must be powers of two (got %zu x %zu).", x, y);
+  tkm_poly *p = new (std::nothrow) tkm_poly();
+  if (!p) return fail(TKM_ERR_ALLOCATION, "out of host memory");
+  cudaError_t e = cudaMallocAsync((void **)&p->d, x * y * sizeof(Fr), ctx->stream);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(TKM_ERR_ALLOCATION, "cudaMallocAsync(%zu bytes) failed: %s", x * y * sizeof(Fr), cudaGetErrorString(e));
+  }
+  p->x_size = x;
+  p->y_size = y;
+  *out = p;
+  return TKM_OK;
+}
+static void poly_release(tkm_ctx *ctx, tkm_poly *p) {
+  if (!p) return;
+  if (p->d) cudaFreeAsync(p->d, ctx->stream);
+  delete p;
+}
+
+int32_t poly_find_degree(tkm_ctx *ctx, const tkm_poly *p, int64_t *xd, int64_t *yd) {
+  Scratch<int> deg;
+  TKM_TRY(deg.alloc(ctx, 2));
+  TKM_CUDA(cudaMemsetAsync(deg.p, 0xff, 2 * sizeof(int), ctx->stream));
+  size_t total = p->x_size * p->y_size;
+  k_find_degree<<<grid_for(total, 256, ctx->sm_count), 256, 0, ctx->stream>>>(p->d, p->x_size, p->y_size, deg.p);
+  TKM_TRY(launch_check(ctx, "k_find_degree"));
+  int h[2];
+  TKM_CUDA(cudaMemcpyAsync(h, deg.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *xd = h[0];
+  *yd = h[1];
+  // the reference reports (-1,-1) for the zero polynomial (is_zero, bivariate_polynomial/mod.rs:134-137)
+  if (h[0] < 0 || h[1] < 0) *xd = *yd = -1;
+  return TKM_OK;
+}
+
+// New buffer of shape nx x ny holding src placed at offset (ox, oy), cropped to fit.
+static int32_t poly_reshape_into(tkm_ctx *ctx, const Fr *src, size_t sx, size_t sy, size_t nx, size_t ny, size_t ox, size_t oy, Fr *dst) {
+  TKM_CUDA(cudaMemsetAsync(dst, 0, nx * ny * sizeof(Fr), ctx->stream));
+  if (ox >= nx || oy >= ny) return TKM_OK;
+  size_t rows = sx < nx - ox ? sx : nx - ox, cols = sy < ny - oy ? sy : ny - oy;
+  if (rows * cols == 0) return TKM_OK;
+  k_copy_rect<<<grid_for(rows * cols, 256, ctx->sm_count), 256, 0, ctx->stream>>>(dst, ny, ox, oy, src, sy, rows, cols);
+  return launch_check(ctx, "k_copy_rect");
+}
+
+int32_t poly_resize(tkm_ctx *ctx, tkm_poly *p, size_t tx, size_t ty) {
+  if (tx == 0 || ty == 0) return fail(TKM_ERR_INVALID_ARGUMENT, "Invalid target sizes for resize");
+  size_t nx = next_pow2(tx), ny = next_pow2(ty);
+  if (nx == p->x_size && ny == p->y_size) return TKM_OK;
+  Fr *nd = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&nd, nx * ny * sizeof(Fr), ctx->stream);
+  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMallocAsync failed: %s", cudaGetErrorString(e));
+  int32_t st = poly_reshape_into(ctx, p->d, p->x_size, p->y_size, nx, ny, 0, 0, nd);
+  if (st != TKM_OK) {
+    cudaFreeAsync(nd, ctx->stream);
+    return st;
+  }
+  cudaFreeAsync(p->d, ctx->stream);
+  p->d = nd;
+  p->x_size = nx;
+  p->y_size = ny;
+  return TKM_OK;
+}
+
+int32_t poly_mul(tkm_ctx *ctx, const tkm_poly *a, const tkm_poly *b, tkm_poly **out) {
+  int64_t adx, ady, bdx, bdy;
+  TKM_TRY(poly_find_degree(ctx, a, &adx, &ady));
+  TKM_TRY(poly_find_degree(ctx, b, &bdx, &bdy));
+  const bool a_zero = adx < 0, b_zero = bdx < 0;
+  // scalar fast paths (bivariate_polynomial/mod.rs:1867-1877); a zero operand gives the zero polynomial
+  if (a_zero || b_zero) {
+    TKM_TRY(poly_alloc(ctx, 1, 1, out));
+    TKM_CUDA(cudaMemsetAsync((*out)->d, 0, sizeof(Fr), ctx->stream));
+    return TKM_OK;
+  }
+  const bool a_const = adx + ady == 0, b_const = bdx + bdy == 0;
+  if (a_const || b_const) {
+    const tkm_poly *cpoly = a_const ? a : b, *other = a_const ? b : a;
+    Fr s;
+    TKM_CUDA(cudaMemcpyAsync(&s, cpoly->d, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (a_const && b_const) {
+      TKM_TRY(poly_alloc(ctx, 1, 1, out));
+    } else {
+      TKM_TRY(poly_alloc(ctx, other->x_size, other->y_size, out));
+    }
+    size_t cnt = (*out)->x_size * (*out)->y_size;
+    return vec_scale(ctx, s, other->d, (*out)->d, cnt);
+  }
+  const size_t tx = (size_t)(adx + bdx + 1), ty = (size_t)(ady + bdy + 1);
+  const size_t nx = next_pow2(tx), ny = next_pow2(ty);
+  const size_t total = nx * ny;
+  tkm_poly *res = nullptr;
+  TKM_TRY(poly_alloc(ctx, nx, ny, &res));
+  Scratch<Fr> rhs;
+  int32_t st = rhs.alloc(ctx, total);
+  if (st == TKM_OK) st = poly_reshape_into(ctx, a->d, a->x_size, a->y_size, nx, ny, 0, 0, res->d);
+  if (st == TKM_OK) st = poly_reshape_into(ctx, b->d, b->x_size, b->y_size, nx, ny, 0, 0, rhs.p);
+  if (st == TKM_OK) st = bintt_dev(ctx, res->d, res->d, nx, ny, TKM_FORWARD, nullptr, nullptr);
+  if (st == TKM_OK) st = bintt_dev(ctx, rhs.p, rhs.p, nx, ny, TKM_FORWARD, nullptr, nullptr);
+  if (st == TKM_OK) st = vec_op(ctx, TKM_OP_MUL, res->d, rhs.p, res->d, total);
+  if (st == TKM_OK) st = bintt_dev(ctx, res->d, res->d, nx, ny, TKM_INVERSE, nullptr, nullptr);
+  if (st != TKM_OK) {
+    poly_release(ctx, res);
+    return st;
+  }
+  *out = res;
+  return TKM_OK;
+}
+
+// sum_i tmp[i] * w[i] style reductions built from the two dot kernels.
+static int32_t row_dot(tkm_ctx *ctx, Fr *out, const Fr *c, size_t rows, size_t cols, const Fr *w) {
+  size_t warps = rows;
+  unsigned blocks = grid_for(warps * 32, 256, ctx->sm_count);
+  k_row_dot<<<blocks, 256, 0, ctx->stream>>>(out, c, rows, cols, w);
+  return launch_check(ctx, "k_row_dot");
+}
+static int32_t col_dot(tkm_ctx *ctx, Fr *out, const Fr *c, size_t rows, size_t cols, const Fr *w) {
+  // two levels: chunks of rows -> partial[chunk][j] -> out[j]
+  size_t rows_per_chunk = 64;
+  size_t chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+  if (chunks == 1) {
+    dim3 g((unsigned)((cols + 127) / 128), 1);
+    k_col_dot_partial<<<g, 128, 0, ctx->stream>>>(out, c, rows, cols, w, rows);
+    return launch_check(ctx, "k_col_dot_partial");
+  }
+  Scratch<Fr> partial;
+  TKM_TRY(partial.alloc(ctx, chunks * cols));
+  dim3 g((unsigned)((cols + 127) / 128), (unsigned)chunks);
+  k_col_dot_partial<<<g, 128, 0, ctx->stream>>>(partial.p, c, rows, cols, w, rows_per_chunk);
+  TKM_TRY(launch_check(ctx, "k_col_dot_partial"));
+  dim3 g2((unsigned)((cols + 127) / 128), 1);
+  k_col_dot_partial<<<g2, 128, 0, ctx->stream>>>(out, partial.p, chunks, cols, nullptr, chunks);
+  return launch_check(ctx, "k_col_dot_partial");
+}
+
+}  // namespace tkm
+
+using namespace tkm;
+
+#define API_BEGIN                 \
+  if (!ctx) return fail(TKM_ERR_INVALID_ARGUMENT, "null context"); \
+  cudaSetDevice(ctx->device);
+
+extern "C" {
+
+int32_t tkm_poly_from_coeffs_host(tkm_ctx *ctx, const uint8_t *coeffs, size_t x_size, size_t y_size, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(coeffs && out, "null argument");
+  TKM_TRY(poly_alloc(ctx, x_size, y_size, out));
+  size_t n = x_size * y_size;
+  int32_t st = TKM_OK;
+  cudaError_t e = cudaMemcpyAsync((*out)->d, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) st = fail(TKM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  if (st == TKM_OK) st = vec_to_mont(ctx, (*out)->d, (*out)->d, n);
+  if (st != TKM_OK) {
+    poly_release(ctx, *out);
+    *out = nullptr;
+  }
+  return st;
+}
+
+int32_t tkm_poly_from_evals_host(tkm_ctx *ctx, const uint8_t *evals, size_t x_size, size_t y_size, const uint8_t *cx, const uint8_t *cy,
+                                 tkm_poly **out) {
+  API_BEGIN
+  TKM_TRY(tkm_poly_from_coeffs_host(ctx, evals, x_size, y_size, out));
+  int32_t st = tkm_poly_ntt_inplace(ctx, *out, TKM_INVERSE, cx, cy);
+  if (st != TKM_OK) {
+    poly_release(ctx, *out);
+    *out = nullptr;
+  }
+  return st;
+}
+
+int32_t tkm_poly_zero(tkm_ctx *ctx, size_t x_size, size_t y_size, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(out, "null argument");
+  TKM_TRY(poly_alloc(ctx, x_size, y_size, out));
+  TKM_CUDA(cudaMemsetAsync((*out)->d, 0, x_size * y_size * sizeof(Fr), ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_poly_clone(tkm_ctx *ctx, const tkm_poly *p, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(p && out, "null argument");
+  TKM_TRY(poly_alloc(ctx, p->x_size, p->y_size, out));
+  TKM_CUDA(cudaMemcpyAsync((*out)->d, p->d, p->x_size * p->y_size * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_poly_free(tkm_ctx *ctx, tkm_poly *p) {
+  API_BEGIN
+  poly_release(ctx, p);
+  return TKM_OK;
+}
+
+int32_t tkm_poly_shape(const tkm_poly *p, size_t *x_size, size_t *y_size) {
+  if (!p) return fail(TKM_ERR_INVALID_ARGUMENT, "null polynomial");
+  if (x_size) *x_size = p->x_size;
+  if (y_size) *y_size = p->y_size;
+  return TKM_OK;
+}
+
+int32_t tkm_poly_device_ptr(tkm_poly *p, void **out_dev) {
+  if (!p || !out_dev) return fail(TKM_ERR_INVALID_ARGUMENT, "null argument");
+  *out_dev = p->d;
+  return TKM_OK;
+}
+
+int32_t tkm_poly_copy_coeffs_host(tkm_ctx *ctx, const tkm_poly *p, uint8_t *out) {
+  API_BEGIN
+  TKM_REQUIRE(p && out, "null argument");
+  size_t n = p->x_size * p->y_size;
+  Scratch<Fr> tmp;
+  TKM_TRY(tmp.alloc(ctx, n));
+  TKM_TRY(vec_from_mont(ctx, p->d, tmp.p, n));
+  TKM_CUDA(cudaMemcpyAsync(out, tmp.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_poly_to_evals_host(tkm_ctx *ctx, const tkm_poly *p, const uint8_t *cx, const uint8_t *cy, uint8_t *out) {
+  API_BEGIN
+  TKM_REQUIRE(p && out, "null argument");
+  size_t n = p->x_size * p->y_size;
+  Scratch<Fr> tmp;
+  TKM_TRY(tmp.alloc(ctx, n));
+  Fr gx, gy;
+  if (cx) gx = fr_from_bytes_host(cx);
+  if (cy) gy = fr_from_bytes_host(cy);
+  TKM_TRY(bintt_dev(ctx, p->d, tmp.p, p->x_size, p->y_size, TKM_FORWARD, cx ? &gx : nullptr, cy ? &gy : nullptr));
+  TKM_TRY(vec_from_mont(ctx, tmp.p, tmp.p, n));
+  TKM_CUDA(cudaMemcpyAsync(out, tmp.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_poly_ntt_inplace(tkm_ctx *ctx, tkm_poly *p, int32_t dir, const uint8_t *cx, const uint8_t *cy) {
+  API_BEGIN
+  TKM_REQUIRE(p, "null polynomial");
+  Fr gx, gy;
+  if (cx) gx = fr_from_bytes_host(cx);
+  if (cy) gy = fr_from_bytes_host(cy);
+  return bintt_dev(ctx, p->d, p->d, p->x_size, p->y_size, dir, cx ? &gx : nullptr, cy ? &gy : nullptr);
+}
+
+int32_t tkm_poly_find_degree(tkm_ctx *ctx, const tkm_poly *p, int64_t *xd, int64_t *yd) {
+  API_BEGIN
+  TKM_REQUIRE(p && xd && yd, "null argument");
+  return poly_find_degree(ctx, p, xd, yd);
+}
+
+int32_t tkm_poly_resize(tkm_ctx *ctx, tkm_poly *p, size_t tx, size_t ty) {
+  API_BEGIN
+  TKM_REQUIRE(p, "null polynomial");
+  return poly_resize(ctx, p, tx, ty);
+}
+
+int32_t tkm_poly_optimize_size(tkm_ctx *ctx, tkm_poly *p) {
+  API_BEGIN
+  TKM_REQUIRE(p, "null polynomial");
+  int64_t xd, yd;
+  TKM_TRY(poly_find_degree(ctx, p, &xd, &yd));
+  if (xd < 0 || yd < 0) return TKM_OK;  // zero polynomial keeps its shape (bivariate_polynomial/mod.rs:1814-1816)
+  return poly_resize(ctx, p, (size_t)xd + 1, (size_t)yd + 1);
+}
+
+int32_t tkm_poly_mul_monomial(tkm_ctx *ctx, const tkm_poly *p, size_t ex, size_t ey, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(p && out, "null argument");
+  size_t nx = next_pow2(p->x_size + ex), ny = next_pow2(p->y_size + ey);
+  TKM_TRY(poly_alloc(ctx, nx, ny, out));
+  int32_t st = poly_reshape_into(ctx, p->d, p->x_size, p->y_size, nx, ny, ex, ey, (*out)->d);
+  if (st != TKM_OK) {
+    poly_release(ctx, *out);
+    *out = nullptr;
+  }
+  return st;
+}
+
+int32_t tkm_poly_axpby(tkm_ctx *ctx, const tkm_poly *a, const uint8_t *ca32, const tkm_poly *b, const uint8_t *cb32, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(a && out, "null argument");
+  size_t ox = a->x_size, oy = a->y_size;
+  if (b) {
+    if (b->x_size > ox) ox = b->x_size;
+    if (b->y_size > oy) oy = b->y_size;
+  }
+  Fr ca = Fr::one(), cb = Fr::one();
+  if (ca32) ca = fr_from_bytes_host(ca32);
+  if (cb32) cb = fr_from_bytes_host(cb32);
+  TKM_TRY(poly_alloc(ctx, ox, oy, out));
+  k_axpby<<<grid_for(ox * oy, 256, ctx->sm_count), 256, 0, ctx->stream>>>((*out)->d, ox, oy, a->d, a->x_size, a->y_size, ca,
+                                                                          ca32 ? 0 : 1, b ? b->d : nullptr, b ? b->x_size : 0,
+                                                                          b ? b->y_size : 0, cb, cb32 ? 0 : 1);
+  return launch_check(ctx, "k_axpby");
+}
+
+int32_t tkm_poly_add_scalar(tkm_ctx *ctx, tkm_poly *p, const uint8_t s32[32]) {
+  API_BEGIN
+  TKM_REQUIRE(p && s32, "null argument");
+  k_add_scalar<<<1, 1, 0, ctx->stream>>>(p->d, fr_from_bytes_host(s32));
+  return launch_check(ctx, "k_add_scalar");
+}
+
+int32_t tkm_poly_mul(tkm_ctx *ctx, const tkm_poly *a, const tkm_poly *b, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(a && b && out, "null argument");
+  return poly_mul(ctx, a, b, out);
+}
+
+int32_t tkm_poly_scale_coeffs(tkm_ctx *ctx, const tkm_poly *p, const uint8_t *sx32, const uint8_t *sy32, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(p && out, "null argument");
+  Scratch<Fr> px, py;
+  if (sx32) {
+    TKM_TRY(px.alloc(ctx, p->x_size));
+    TKM_TRY(fill_powers_public(ctx, px.p, fr_from_bytes_host(sx32), Fr::one(), p->x_size));
+  }
+  if (sy32) {
+    TKM_TRY(py.alloc(ctx, p->y_size));
+    TKM_TRY(fill_powers_public(ctx, py.p, fr_from_bytes_host(sy32), Fr::one(), p->y_size));
+  }
+  TKM_TRY(poly_alloc(ctx, p->x_size, p->y_size, out));
+  size_t n = p->x_size * p->y_size;
+  k_scale_coeffs<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>((*out)->d, p->d, p->x_size, p->y_size, sx32 ? px.p : nullptr,
+                                                                          sy32 ? py.p : nullptr);
+  return launch_check(ctx, "k_scale_coeffs");
+}
+
+int32_t tkm_poly_eval_y(tkm_ctx *ctx, const tkm_poly *p, const uint8_t y32[32], tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(p && y32 && out, "null argument");
+  Scratch<Fr> py;
+  TKM_TRY(py.alloc(ctx, p->y_size));
+  TKM_TRY(fill_powers_public(ctx, py.p, fr_from_bytes_host(y32), Fr::one(), p->y_size));
+  TKM_TRY(poly_alloc(ctx, p->x_size, 1, out));
+  return row_dot(ctx, (*out)->d, p->d, p->x_size, p->y_size, py.p);
+}
+
+int32_t tkm_poly_eval_x(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(p && x32 && out, "null argument");
+  Scratch<Fr> px;
+  TKM_TRY(px.alloc(ctx, p->x_size));
+  TKM_TRY(fill_powers_public(ctx, px.p, fr_from_bytes_host(x32), Fr::one(), p->x_size));
+  TKM_TRY(poly_alloc(ctx, 1, p->y_size, out));
+  return col_dot(ctx, (*out)->d, p->d, p->x_size, p->y_size, px.p);
+}
+
+int32_t tkm_poly_eval(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], const uint8_t y32[32], uint8_t out32[32]) {
+  API_BEGIN
+  TKM_REQUIRE(p && x32 && y32 && out32, "null argument");
+  Scratch<Fr> px, py, rows, res;
+  TKM_TRY(px.alloc(ctx, p->x_size));
+  TKM_TRY(py.alloc(ctx, p->y_size));
+  TKM_TRY(rows.alloc(ctx, p->x_size));
+  TKM_TRY(res.alloc(ctx, 1));
+  TKM_TRY(fill_powers_public(ctx, px.p, fr_from_bytes_host(x32), Fr::one(), p->x_size));
+  TKM_TRY(fill_powers_public(ctx, py.p, fr_from_bytes_host(y32), Fr::one(), p->y_size));
+  TKM_TRY(row_dot(ctx, rows.p, p->d, p->x_size, p->y_size, py.p));
+  TKM_TRY(row_dot(ctx, res.p, rows.p, 1, p->x_size, px.p));
+  Fr h;
+  TKM_CUDA(cudaMemcpyAsync(&h, res.p, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  fr_to_bytes_host(h, out32);
+  return TKM_OK;
+}
+
+int32_t tkm_poly_div_by_vanishing(tkm_ctx *ctx, tkm_poly *p, size_t c, size_t d, tkm_poly **out_qx, tkm_poly **out_qy) {
+  API_BEGIN
+  TKM_REQUIRE(p && out_qx && out_qy, "null argument");
+  if (!is_pow2(c) || !is_pow2(d)) return fail(TKM_ERR_INVALID_ARGUMENT, "The denominators must have degress as powers of two.");
+  int64_t xd, yd;
+  TKM_TRY(poly_find_degree(ctx, p, &xd, &yd));
+  if (xd >= 0 && yd >= 0) TKM_TRY(poly_resize(ctx, p, (size_t)xd + 1, (size_t)yd + 1));  // optimize_size (:2290)
+  if (xd < (int64_t)c || yd < (int64_t)d) return fail(TKM_ERR_INVALID_ARGUMENT, "The numerator must have grater degrees than denominators.");
+  const size_t x = p->x_size, y = p->y_size;
+  tkm_poly *qx = nullptr, *qy = nullptr;
+  TKM_TRY(poly_alloc(ctx, x, y, &qx));
+  int32_t st = poly_alloc(ctx, c, y, &qy);
+  if (st == TKM_OK) {
+    k_vanish_qy<<<grid_for(c * d, 256, ctx->sm_count), 256, 0, ctx->stream>>>(qy->d, p->d, x, y, c, d);
+    st = launch_check(ctx, "k_vanish_qy");
+  }
+  if (st == TKM_OK) {
+    k_vanish_qx<<<grid_for(c * y, 256, ctx->sm_count), 256, 0, ctx->stream>>>(qx->d, p->d, qy->d, x, y, c, d);
+    st = launch_check(ctx, "k_vanish_qx");
+  }
+  if (st != TKM_OK) {
+    poly_release(ctx, qx);
+    poly_release(ctx, qy);
+    return st;
+  }
+  *out_qx = qx;
+  *out_qy = qy;
+  return TKM_OK;
+}
+
+int32_t tkm_poly_div_by_ruffini(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], const uint8_t y32[32], tkm_poly **out_qx,
+                                tkm_poly **out_qy, uint8_t out_r32[32]) {
+  API_BEGIN
+  TKM_REQUIRE(p && x32 && y32 && out_qx && out_qy && out_r32, "null argument");
+  const size_t x = p->x_size, y = p->y_size;
+  tkm_poly *qx = nullptr, *qy = nullptr;
+  Scratch<Fr> rx, r;
+  TKM_TRY(rx.alloc(ctx, y));
+  TKM_TRY(r.alloc(ctx, 1));
+  TKM_TRY(poly_alloc(ctx, x, y, &qx));
+  int32_t st = poly_alloc(ctx, 1, y, &qy);
+  if (st == TKM_OK) {
+    k_ruffini_x<<<(unsigned)((y + 127) / 128), 128, 0, ctx->stream>>>(qx->d, rx.p, p->d, x, y, fr_from_bytes_host(x32));
+    st = launch_check(ctx, "k_ruffini_x");
+  }
+  if (st == TKM_OK) {
+    k_ruffini_y<<<1, 32, 0, ctx->stream>>>(qy->d, r.p, rx.p, y, fr_from_bytes_host(y32));
+    st = launch_check(ctx, "k_ruffini_y");
+  }
+  Fr h;
+  if (st == TKM_OK) {
+    cudaError_t e = cudaMemcpyAsync(&h, r.p, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = fail(TKM_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  }
+  if (st != TKM_OK) {
+    poly_release(ctx, qx);
+    poly_release(ctx, qy);
+    return st;
+  }
+  fr_to_bytes_host(h, out_r32);
+  *out_qx = qx;
+  *out_qy = qy;
+  return TKM_OK;
+}
+
+int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(p && crs && out96, "null argument");
+  int64_t xd, yd;
+  TKM_TRY(poly_find_degree(ctx, p, &xd, &yd));
+  if (xd < 0 || yd < 0) {  // zero polynomial commits to the identity (iotools/mod.rs:2057-2059)
+    memset(out96, 0, 96);
+    return TKM_OK;
+  }
+  const size_t tx = (size_t)xd + 1, ty = (size_t)yd + 1;
+  if (tx > crs->rows || ty > crs->cols) return fail(TKM_ERR_INVALID_ARGUMENT, "Insufficient length of sigma.sigma_1.xy_powers");
+  MsmInput in;
+  in.scalars = p->d;
+  in.scalars_mont = true;
+  in.scalar_row_stride = p->y_size;
+  in.bases = crs->d;
+  in.base_row_stride = crs->cols;
+  in.rows = tx;
+  in.cols = ty;
+  in.idx = nullptr;
+  return msm_run(ctx, in, out96);
+}
+
+}  // extern "C"

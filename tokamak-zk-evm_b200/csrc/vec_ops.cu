@@ -1,0 +1,136 @@
+// Element-wise Fr kernels: the device side of ICICLE's VecOps::{add,sub,mul,div,scalar_mul,inv}
+// as the reference uses them (libs/src/vector_operations/mod.rs:19-141;
+// libs/src/bivariate_polynomial/mod.rs:332-435,1974,2180).  HBM-bound: one 32-byte element per
+// thread per array, 128-bit loads/stores, grid-stride loops sized to the SM count.
+#include "common.cuh"
+
+namespace tkm {
+
+std::string &last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int32_t fail(int32_t code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+int32_t launch_check(tkm_ctx *ctx, const char *what) {
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TKM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return TKM_OK;
+}
+
+Fr fr_from_bytes_host(const uint8_t *b32) {
+  Fr t;
+  memcpy(t.v, b32, 32);
+  return t.to_mont();
+}
+void fr_to_bytes_host(const Fr &a, uint8_t *b32) {
+  Fr t = a.from_mont();
+  memcpy(b32, t.v, 32);
+}
+
+enum { K_TO_MONT = 0, K_FROM_MONT = 1 };
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_mont_convert(const Fr *__restrict__ in, Fr *__restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr a = in[i];
+    out[i] = (KIND == K_TO_MONT) ? a.to_mont() : a.from_mont();
+  }
+}
+
+// Single-element inverse helper shared by div and inv: Fermat, inv(0) = 0.
+template <int OP>
+__global__ void __launch_bounds__(256) k_vec_op(const Fr *__restrict__ a, const Fr *__restrict__ b, Fr *__restrict__ out,
+                                                size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = a[i], y = b[i], z;
+    if (OP == TKM_OP_ADD) z = x + y;
+    if (OP == TKM_OP_SUB) z = x - y;
+    if (OP == TKM_OP_MUL) z = x * y;
+    if (OP == TKM_OP_DIV) z = x * y.inv();
+    out[i] = z;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_vec_scale(Fr s, const Fr *__restrict__ a, Fr *__restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = a[i];
+    out[i] = x * s;
+  }
+}
+
+// Batched inversion: each thread inverts CH consecutive-by-stride elements with one Fermat inverse
+// (Montgomery's trick).  Zeros are skipped and map to zero (ICICLE convention inv(0) = 0).
+constexpr int INV_CH = 8;
+__global__ void __launch_bounds__(128) k_vec_inv(const Fr *__restrict__ a, Fr *__restrict__ out, size_t n) {
+  size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t groups = (n + INV_CH - 1) / INV_CH;
+  for (size_t g = t; g < groups; g += nthreads) {
+    // element k of group g lives at g + k*groups: coalesced across the warp for every k
+    Fr v[INV_CH], pre[INV_CH];
+    Fr acc = Fr::one();
+#pragma unroll
+    for (int k = 0; k < INV_CH; k++) {
+      size_t idx = g + (size_t)k * groups;
+      v[k] = (idx < n) ? a[idx] : Fr::zero();
+      pre[k] = acc;
+      if (!v[k].is_zero()) acc = acc * v[k];
+    }
+    Fr inv = acc.inv();
+#pragma unroll
+    for (int k = INV_CH - 1; k >= 0; k--) {
+      size_t idx = g + (size_t)k * groups;
+      Fr r = Fr::zero();
+      if (!v[k].is_zero()) {
+        r = inv * pre[k];
+        inv = inv * v[k];
+      }
+      if (idx < n) out[idx] = r;
+    }
+  }
+}
+
+int32_t vec_to_mont(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  k_mont_convert<K_TO_MONT><<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);
+  return launch_check(ctx, "k_mont_convert<to>");
+}
+int32_t vec_from_mont(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  k_mont_convert<K_FROM_MONT><<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);
+  return launch_check(ctx, "k_mont_convert<from>");
+}
+int32_t vec_op(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  unsigned g = grid_for(n, 256, ctx->sm_count);
+  switch (op) {
+    case TKM_OP_ADD: k_vec_op<TKM_OP_ADD><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case TKM_OP_SUB: k_vec_op<TKM_OP_SUB><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case TKM_OP_MUL: k_vec_op<TKM_OP_MUL><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case TKM_OP_DIV: k_vec_op<TKM_OP_DIV><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown vector op %d", op);
+  }
+  return launch_check(ctx, "k_vec_op");
+}
+int32_t vec_scale(tkm_ctx *ctx, const Fr &s, const Fr *a, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  k_vec_scale<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(s, a, out, n);
+  return launch_check(ctx, "k_vec_scale");
+}
+int32_t vec_inv(tkm_ctx *ctx, const Fr *a, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  size_t groups = (n + INV_CH - 1) / INV_CH;
+  k_vec_inv<<<grid_for(groups, 128, ctx->sm_count), 128, 0, ctx->stream>>>(a, out, n);
+  return launch_check(ctx, "k_vec_inv");
+}
+
+}  // namespace tkm

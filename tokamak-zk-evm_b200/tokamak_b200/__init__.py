@@ -1,0 +1,464 @@
+"""Host-side mirror of the reference's `libs` API for the hot path, over the C-ABI of libtokamak_b200.
+
+Names follow packages/backend/libs (DensePolynomialExt, BivariatePolynomial methods, Sigma1.encode_poly,
+G1serde, vector_operations) so tests read like libs/src/tests.rs.  Field elements cross this layer as
+Python ints or numpy uint64 arrays in the reference's canonical little-endian layout
+(Fr: shape (n, 4); G1 affine: shape (n, 12), all-zero row = identity).
+"""
+import ctypes
+
+import numpy as np
+
+from . import ffi
+from .ffi import TkmError, check
+
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+FORWARD, INVERSE = 0, 1
+OP_ADD, OP_SUB, OP_MUL, OP_DIV = 0, 1, 2, 3
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def fr_bytes(v):
+    """int | 4 x u64 array -> (keepalive numpy array, void*) of 32 canonical LE bytes, or (None, None)."""
+    if v is None:
+        return None, None
+    if isinstance(v, (int, np.integer)):
+        a = np.frombuffer(int(v % R_MOD).to_bytes(32, "little"), dtype=np.uint64).copy()
+    else:
+        a = np.ascontiguousarray(v, dtype=np.uint64).reshape(4)
+    return a, _vp(a)
+
+
+def fr_to_int(a):
+    return int.from_bytes(np.ascontiguousarray(a, dtype=np.uint64).tobytes(), "little")
+
+
+def frs_from_ints(vs):
+    return np.frombuffer(b"".join(int(v % R_MOD).to_bytes(32, "little") for v in vs), dtype=np.uint64).reshape(-1, 4).copy()
+
+
+def frs_to_ints(a):
+    b = np.ascontiguousarray(a, dtype=np.uint64).tobytes()
+    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+
+
+def _as_fr_array(a):
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    return frs_from_ints(list(a))
+
+
+class Context:
+    """One device + one stream (utils::check_device, libs/src/utils/mod.rs:88-110). Not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = ffi.load()
+        h = ctypes.c_void_p()
+        check(self.lib.tkm_ctx_create(device, ctypes.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tkm_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- streams / timing ------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        check(self.lib.tkm_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def sync(self):
+        check(self.lib.tkm_ctx_sync(self.h))
+
+    def time_begin(self):
+        check(self.lib.tkm_event_time_begin(self.h))
+
+    def time_end(self):
+        ms = ctypes.c_float()
+        check(self.lib.tkm_event_time_end(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        v = ctypes.c_uint64()
+        check(self.lib.tkm_launch_count(self.h, ctypes.byref(v)))
+        return v.value
+
+    def microbench(self, kind):
+        v = ctypes.c_double()
+        check(self.lib.tkm_microbench(self.h, kind, ctypes.byref(v)))
+        return v.value
+
+    # -- NTT domain (init_ntt_domain_for_size, bivariate_polynomial/mod.rs:33-55) --------------------
+    def init_ntt_domain_for_size(self, size):
+        if size == 0:
+            raise ValueError("NTT domain size must be non-zero.")
+        if size & (size - 1):
+            raise ValueError("NTT domain size must be a power of two.")
+        check(self.lib.tkm_ntt_domain_init(self.h, size.bit_length() - 1))
+
+    def release_ntt_domain(self):
+        check(self.lib.tkm_ntt_domain_release(self.h))
+
+    def ntt_domain_log2(self):
+        v = ctypes.c_int32()
+        check(self.lib.tkm_ntt_domain_log2(self.h, ctypes.byref(v)))
+        return v.value
+
+    def get_root_of_unity(self, n):
+        out = np.zeros(4, dtype=np.uint64)
+        check(self.lib.tkm_root_of_unity(n.bit_length() - 1, _vp(out)))
+        return fr_to_int(out)
+
+    # -- raw device buffers -------------------------------------------------------------------
+    def dev_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        check(self.lib.tkm_dev_alloc(self.h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, ptr):
+        check(self.lib.tkm_dev_free(self.h, ctypes.c_void_p(ptr)))
+
+    def h2d(self, ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        check(self.lib.tkm_memcpy_h2d(self.h, ctypes.c_void_p(ptr), _vp(arr), arr.nbytes))
+
+    def d2h(self, arr, ptr):
+        check(self.lib.tkm_memcpy_d2h(self.h, _vp(arr), ctypes.c_void_p(ptr), arr.nbytes))
+
+    def upload_fr(self, a, to_mont=True):
+        a = _as_fr_array(a)
+        p = self.dev_alloc(a.nbytes)
+        self.h2d(p, a)
+        if to_mont:
+            check(self.lib.tkm_fr_to_mont(self.h, ctypes.c_void_p(p), ctypes.c_void_p(p), a.shape[0]))
+        return p
+
+    def download_fr(self, ptr, n, from_mont=True):
+        out = np.empty((n, 4), dtype=np.uint64)
+        if from_mont:
+            tmp = self.dev_alloc(out.nbytes)
+            check(self.lib.tkm_fr_from_mont(self.h, ctypes.c_void_p(ptr), ctypes.c_void_p(tmp), n))
+            self.d2h(out, tmp)
+            self.dev_free(tmp)
+        else:
+            self.d2h(out, ptr)
+        return out
+
+    # -- host-slice forms of the ICICLE calls (HostSlice in / HostSlice out) ----------------------
+    def vec_op_host(self, op, a, b):
+        a, b = _as_fr_array(a), _as_fr_array(b)
+        out = np.empty_like(a)
+        check(self.lib.tkm_fr_vec_op_host(self.h, op, _vp(a), _vp(b), _vp(out), a.shape[0]))
+        return out
+
+    def bintt_host(self, a, x_size, y_size, direction=FORWARD, coset_x=None, coset_y=None):
+        """DensePolynomialExt::_biNTT with host slices (bivariate_polynomial/mod.rs:1422-1478)."""
+        a = _as_fr_array(a)
+        out = np.empty_like(a)
+        kx, px = fr_bytes(coset_x)
+        ky, py = fr_bytes(coset_y)
+        check(self.lib.tkm_bintt_host(self.h, _vp(a), _vp(out), x_size, y_size, direction, px, py))
+        return out
+
+    def bintt_dev(self, d_in, d_out, x_size, y_size, direction=FORWARD, coset_x=None, coset_y=None):
+        kx, px = fr_bytes(coset_x)
+        ky, py = fr_bytes(coset_y)
+        check(self.lib.tkm_bintt(self.h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), x_size, y_size, direction, px, py))
+
+    def ntt_batch_dev(self, d_in, d_out, n, batch, columns_batch=False, direction=FORWARD, coset=None):
+        k, p = fr_bytes(coset)
+        check(self.lib.tkm_ntt_batch(self.h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), n, batch, int(columns_batch), direction, p))
+
+    def msm_g1_host(self, scalars, bases):
+        """msm::msm(HostSlice scalars, HostSlice bases, MSMConfig::default()) -> affine point (12 x u64)."""
+        scalars = _as_fr_array(scalars)
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 12)
+        if scalars.shape[0] != bases.shape[0]:
+            raise ValueError("msm input length mismatch")
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_msm_g1_host(self.h, _vp(scalars), _vp(bases), scalars.shape[0], _vp(out)))
+        return out
+
+    def msm_g1_dev(self, d_scalars, scalars_mont, d_bases_mont, n):
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_msm_g1(self.h, ctypes.c_void_p(d_scalars), int(scalars_mont), ctypes.c_void_p(d_bases_mont), n, _vp(out)))
+        return out
+
+    def msm_g1_rect_dev(self, d_scalars, scalars_mont, s_stride, d_bases_mont, b_stride, rows, cols):
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_msm_g1_rect(self.h, ctypes.c_void_p(d_scalars), int(scalars_mont), s_stride, ctypes.c_void_p(d_bases_mont),
+                                       b_stride, rows, cols, _vp(out)))
+        return out
+
+    def msm_g1_indexed_dev(self, d_scalars, scalars_mont, d_bases_mont, d_idx, n):
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_msm_g1_indexed(self.h, ctypes.c_void_p(d_scalars), int(scalars_mont), ctypes.c_void_p(d_bases_mont),
+                                          ctypes.c_void_p(d_idx), n, _vp(out)))
+        return out
+
+    def upload_bases(self, bases):
+        """Canonical affine points -> device table in Montgomery form. Returns device pointer."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 12)
+        p = self.dev_alloc(bases.nbytes)
+        self.h2d(p, bases)
+        check(self.lib.tkm_g1_bases_to_mont(self.h, ctypes.c_void_p(p), ctypes.c_void_p(p), bases.shape[0]))
+        return p
+
+    def g1_fixed_base_mul(self, base, scalars):
+        """N scalar multiples of one base (from_coef_vec_to_g1serde_vec, iotools/mod.rs:1113-1135)."""
+        base = np.ascontiguousarray(base, dtype=np.uint64).reshape(12)
+        scalars = _as_fr_array(scalars)
+        n = scalars.shape[0]
+        ds = self.upload_fr(scalars, to_mont=False)
+        dout = self.dev_alloc(n * 96)
+        check(self.lib.tkm_g1_fixed_base_mul(self.h, _vp(base), ctypes.c_void_p(ds), 0, n, ctypes.c_void_p(dout)))
+        out = np.empty((n, 12), dtype=np.uint64)
+        self.d2h(out, dout)
+        self.dev_free(ds)
+        self.dev_free(dout)
+        return out
+
+    def g1_add(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(12)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(12)
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_g1_add(self.h, _vp(a), _vp(b), _vp(out)))
+        return out
+
+    def g1_mul(self, a, k):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(12)
+        kk, pk = fr_bytes(k)
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_g1_mul(self.h, _vp(a), pk, _vp(out)))
+        return out
+
+
+class Sigma1:
+    """Device-resident sigma_1.xy_powers (libs/src/group_structures/mod.rs:361-394): grid rs_x x rs_y,
+    index rs_y*h + i <-> x^h y^i."""
+
+    def __init__(self, ctx, xy_powers, rs_x, rs_y):
+        self.ctx = ctx
+        pts = np.ascontiguousarray(xy_powers, dtype=np.uint64).reshape(-1, 12)
+        assert pts.shape[0] == rs_x * rs_y
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_crs_upload(ctx.h, _vp(pts), rs_x, rs_y, ctypes.byref(h)))
+        self.h, self.rs_x, self.rs_y = h, rs_x, rs_y
+
+    def encode_poly(self, poly):
+        """Sigma1::encode_poly (group_structures/mod.rs:59-119; iotools/mod.rs:2041-2113)."""
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.ctx.lib.tkm_poly_commit(self.ctx.h, poly.h, self.h, _vp(out)))
+        return out
+
+    def device_ptr(self):
+        p = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_crs_device_ptr(self.h, ctypes.byref(p), None, None))
+        return p.value
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tkm_crs_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DensePolynomialExt:
+    """Device-resident bivariate polynomial with the BivariatePolynomial trait's method names
+    (libs/src/bivariate_polynomial/mod.rs:1283-1416)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    # -- constructors ---------------------------------------------------------------------------
+    @classmethod
+    def from_coeffs(cls, ctx, coeffs, x_size, y_size):
+        a = _as_fr_array(coeffs)
+        if x_size * y_size != a.shape[0]:
+            raise ValueError("Mismatch between the coefficient vector and the polynomial size")
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_poly_from_coeffs_host(ctx.h, _vp(a), x_size, y_size, ctypes.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_rou_evals(cls, ctx, evals, x_size, y_size, coset_x=None, coset_y=None):
+        a = _as_fr_array(evals)
+        kx, px = fr_bytes(coset_x)
+        ky, py = fr_bytes(coset_y)
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_poly_from_evals_host(ctx.h, _vp(a), x_size, y_size, px, py, ctypes.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def zero(cls, ctx, x_size=1, y_size=1):
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_poly_zero(ctx.h, x_size, y_size, ctypes.byref(h)))
+        return cls(ctx, h)
+
+    def clone(self):
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_clone(self.ctx.h, self.h, ctypes.byref(h)))
+        return DensePolynomialExt(self.ctx, h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.tkm_poly_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- shape ------------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        x, y = ctypes.c_size_t(), ctypes.c_size_t()
+        check(self.ctx.lib.tkm_poly_shape(self.h, ctypes.byref(x), ctypes.byref(y)))
+        return x.value, y.value
+
+    @property
+    def x_size(self):
+        return self.shape[0]
+
+    @property
+    def y_size(self):
+        return self.shape[1]
+
+    def device_ptr(self):
+        p = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_device_ptr(self.h, ctypes.byref(p)))
+        return p.value
+
+    def find_degree(self):
+        xd, yd = ctypes.c_int64(), ctypes.c_int64()
+        check(self.ctx.lib.tkm_poly_find_degree(self.ctx.h, self.h, ctypes.byref(xd), ctypes.byref(yd)))
+        return xd.value, yd.value
+
+    def is_zero(self):
+        return self.find_degree() == (-1, -1)
+
+    def resize(self, target_x_size, target_y_size):
+        check(self.ctx.lib.tkm_poly_resize(self.ctx.h, self.h, target_x_size, target_y_size))
+
+    def optimize_size(self):
+        check(self.ctx.lib.tkm_poly_optimize_size(self.ctx.h, self.h))
+
+    def mul_monomial(self, x_exponent, y_exponent):
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_mul_monomial(self.ctx.h, self.h, x_exponent, y_exponent, ctypes.byref(h)))
+        return DensePolynomialExt(self.ctx, h)
+
+    # -- data movement ------------------------------------------------------------------------------
+    def copy_coeffs(self):
+        x, y = self.shape
+        out = np.empty((x * y, 4), dtype=np.uint64)
+        check(self.ctx.lib.tkm_poly_copy_coeffs_host(self.ctx.h, self.h, _vp(out)))
+        return out
+
+    def coeffs_ints(self):
+        return frs_to_ints(self.copy_coeffs())
+
+    def get_coeff(self, idx_x, idx_y):
+        return self.coeffs_ints()[idx_x * self.y_size + idx_y]
+
+    def to_rou_evals(self, coset_x=None, coset_y=None):
+        x, y = self.shape
+        out = np.empty((x * y, 4), dtype=np.uint64)
+        kx, px = fr_bytes(coset_x)
+        ky, py = fr_bytes(coset_y)
+        check(self.ctx.lib.tkm_poly_to_evals_host(self.ctx.h, self.h, px, py, _vp(out)))
+        return out
+
+    # -- arithmetic -----------------------------------------------------------------------------------
+    def _axpby(self, ca, other, cb):
+        ka, pa = fr_bytes(ca)
+        kb, pb = fr_bytes(cb)
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_axpby(self.ctx.h, self.h, pa, other.h if other is not None else None, pb, ctypes.byref(h)))
+        return DensePolynomialExt(self.ctx, h)
+
+    def __add__(self, other):
+        if isinstance(other, DensePolynomialExt):
+            return self._axpby(None, other, None)
+        r = self.clone()
+        k, p = fr_bytes(int(other))
+        check(self.ctx.lib.tkm_poly_add_scalar(self.ctx.h, r.h, p))
+        return r
+
+    def __sub__(self, other):
+        if isinstance(other, DensePolynomialExt):
+            return self._axpby(None, other, R_MOD - 1)
+        return self + ((-int(other)) % R_MOD)
+
+    def __neg__(self):
+        return self._axpby(R_MOD - 1, None, None)
+
+    def __mul__(self, other):
+        if isinstance(other, DensePolynomialExt):
+            h = ctypes.c_void_p()
+            check(self.ctx.lib.tkm_poly_mul(self.ctx.h, self.h, other.h, ctypes.byref(h)))
+            return DensePolynomialExt(self.ctx, h)
+        return self._axpby(int(other), None, None)
+
+    __rmul__ = __mul__
+
+    def scale_coeffs_x(self, s):
+        return self._scale(s, None)
+
+    def scale_coeffs_y(self, s):
+        return self._scale(None, s)
+
+    def _scale(self, sx, sy):
+        kx, px = fr_bytes(sx)
+        ky, py = fr_bytes(sy)
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_scale_coeffs(self.ctx.h, self.h, px, py, ctypes.byref(h)))
+        return DensePolynomialExt(self.ctx, h)
+
+    def eval(self, x, y):
+        kx, px = fr_bytes(x)
+        ky, py = fr_bytes(y)
+        out = np.zeros(4, dtype=np.uint64)
+        check(self.ctx.lib.tkm_poly_eval(self.ctx.h, self.h, px, py, _vp(out)))
+        return fr_to_int(out)
+
+    def eval_x(self, x):
+        k, p = fr_bytes(x)
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_eval_x(self.ctx.h, self.h, p, ctypes.byref(h)))
+        return DensePolynomialExt(self.ctx, h)
+
+    def eval_y(self, y):
+        k, p = fr_bytes(y)
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_eval_y(self.ctx.h, self.h, p, ctypes.byref(h)))
+        return DensePolynomialExt(self.ctx, h)
+
+    def div_by_vanishing_opt(self, x_degree, y_degree):
+        qx, qy = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_div_by_vanishing(self.ctx.h, self.h, x_degree, y_degree, ctypes.byref(qx), ctypes.byref(qy)))
+        return DensePolynomialExt(self.ctx, qx), DensePolynomialExt(self.ctx, qy)
+
+    def div_by_ruffini(self, x, y):
+        kx, px = fr_bytes(x)
+        ky, py = fr_bytes(y)
+        qx, qy = ctypes.c_void_p(), ctypes.c_void_p()
+        r = np.zeros(4, dtype=np.uint64)
+        check(self.ctx.lib.tkm_poly_div_by_ruffini(self.ctx.h, self.h, px, py, ctypes.byref(qx), ctypes.byref(qy), _vp(r)))
+        return DensePolynomialExt(self.ctx, qx), DensePolynomialExt(self.ctx, qy), fr_to_int(r)
