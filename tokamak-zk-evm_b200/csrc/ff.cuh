@@ -61,6 +61,9 @@ inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(
 struct FrParams {
   static constexpr int N = 8;
   static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+  // r = ... ffffffff 00000001: the two low limbs are 1 and 2^32-1, so m*(p0 + p1*2^32) = m*2^64 - m*2^32 + m
+  // needs no multiplier at all (see Fp::reduce_row).
+  static constexpr bool LOW_LIMBS_ONE_MINUS_ONE = true;
   TKM_HD static constexpr uint32_t mod(int i) {
     constexpr uint32_t M[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
     return M[i];
@@ -77,6 +80,7 @@ struct FrParams {
 struct FqParams {
   static constexpr int N = 12;
   static constexpr uint32_t INV = 0xfffcfffdu;  // -q^-1 mod 2^32
+  static constexpr bool LOW_LIMBS_ONE_MINUS_ONE = false;
   TKM_HD static constexpr uint32_t mod(int i) {
     constexpr uint32_t M[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
     return M[i];
@@ -187,6 +191,42 @@ struct alignas(16) Fp {
   }
   // Reduction half-row: make column 0 of T vanish.  E aligned at column 0, O at column 1.
   TKM_HD static void reduce_row(uint32_t *E, uint32_t *O) {
+    if (P::LOW_LIMBS_ONE_MINUS_ONE) {
+      // p0 = 1, p1 = 2^32 - 1, -p^-1 = -1 mod 2^32:  m = -E[0].  Column 0: E[0] + m = 2^32*[m != 0].
+      // Columns (1,2) receive that carry plus m*p1 = m*2^32 - m, i.e. the 64-bit value
+      //   V = m ? (m << 32) - (m - 1) : 0   ->  lo = m ? 1 - m : 0,  hi = m - [m > 1]
+      // added to the aligned pair (O[0], O[1]); the carry continues into the odd-limb products.
+      uint32_t m = 0u - E[0];
+      uint32_t lo = m ? (1u - m) : 0u;
+      uint32_t hi = m - (m > 1u ? 1u : 0u);
+      O[0] = add_cc(O[0], lo);
+      O[1] = addc_cc(O[1], hi);
+      // The remaining products m*p[j] are formed as plain 64-bit products (one IMAD.WIDE each, no carry
+      // operand) and folded in with add-with-carry chains: those IADD3.X run on the ALU pipe, which is idle
+      // while the FMA pipe is the bottleneck.  (With madc chains ptxas splits each of these products into an
+      // IMAD.X + IMAD.HI.U32.X pair for the 8-limb field: 6 FMA-pipe cycles instead of 4 per product.)
+      uint32_t pl[N], ph[N];
+#pragma unroll
+      for (int j = 2; j < N; j++) {
+        uint64_t pr = (uint64_t)P::mod(j) * (uint64_t)m;
+        pl[j] = (uint32_t)pr;
+        ph[j] = (uint32_t)(pr >> 32);
+      }
+#pragma unroll
+      for (int j = 3; j < N; j += 2) {
+        O[j - 1] = addc_cc(O[j - 1], pl[j]);
+        O[j] = addc_cc(O[j], ph[j]);
+      }
+      E[2] = add_cc(E[2], pl[2]);
+      E[3] = addc_cc(E[3], ph[2]);
+#pragma unroll
+      for (int j = 4; j < N; j += 2) {
+        E[j] = addc_cc(E[j], pl[j]);
+        E[j + 1] = addc_cc(E[j + 1], ph[j]);
+      }
+      O[N - 1] = addc(O[N - 1], 0);
+      return;  // E[0] is now (logically) zero and is never read again; E[1] is untouched
+    }
     uint32_t m = mul_lo(E[0], P::INV);
     chain_mad_mod(O, 1, m);  // odd limbs of p land on columns (1,2),(3,4),..; no carry out (T bound)
     chain_mad_mod(E, 0, m);  // even limbs of p land on columns (0,1),(2,3),..

@@ -164,7 +164,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(NttPass p) {
     __syncthreads();
   }
   // ---- radix-2 DIF stages in shared memory
-  for (uint32_t u = 0; u < p.logL; u++) {
+  // In the last (or only) pass the final two stages have twiddles {1, omega_4} and {1}: they are fused into
+  // one radix-4 register butterfly with a single multiplication per four elements.
+  const bool radix4_tail = (p.pass == 2 && p.logL >= 2);
+  const uint32_t r2_stages = radix4_tail ? p.logL - 2 : p.logL;
+  for (uint32_t u = 0; u < r2_stages; u++) {
     const uint32_t logh = p.logL - 1 - u, h = 1u << logh;
     const uint32_t toff = L - (L >> u);
     for (uint32_t w = tid; w < (TILE >> 1); w += NTT_THREADS) {
@@ -179,6 +183,22 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(NttPass p) {
       Fr d = INVERSE ? (b - a) : (a - b);
       sts_fr(d_lo, d_hi, i0, s);
       sts_fr(d_lo, d_hi, i1, d * tw);
+    }
+    __syncthreads();
+  }
+  if (radix4_tail) {
+    const Fr w4 = lds_fr(t_lo, t_hi, (L - 4) + 1);  // stage logL-2 (offset L - 4), j = 1: omega_4 (or its stand-in for the inverse)
+    for (uint32_t w = tid; w < (TILE >> 2); w += NTT_THREADS) {
+      uint32_t c = w & (C - 1), q = w >> p.logC;
+      uint32_t i0 = (q << 2) * C + c, i1 = i0 + C, i2 = i1 + C, i3 = i2 + C;
+      Fr x0 = lds_fr(d_lo, d_hi, i0), x1 = lds_fr(d_lo, d_hi, i1), x2 = lds_fr(d_lo, d_hi, i2), x3 = lds_fr(d_lo, d_hi, i3);
+      Fr y0 = x0 + x2, y1 = x1 + x3;
+      Fr y2 = x0 - x2;
+      Fr y3 = (INVERSE ? (x3 - x1) : (x1 - x3)) * w4;
+      sts_fr(d_lo, d_hi, i0, y0 + y1);
+      sts_fr(d_lo, d_hi, i1, y0 - y1);
+      sts_fr(d_lo, d_hi, i2, y2 + y3);
+      sts_fr(d_lo, d_hi, i3, y2 - y3);
     }
     __syncthreads();
   }
