@@ -1,0 +1,39 @@
+//! Commitments: Sigma1::encode_poly (group_structures/mod.rs:59-119, iotools/mod.rs:2041-2113) and msm_g1_bases
+//! (:127-143) over a device-resident CRS uploaded once.
+use crate::bivariate_polynomial::DensePolynomialExt;
+use crate::{check, ctx, G1serde, ScalarField};
+use tokamak_b200_sys as sys;
+
+pub struct Sigma1Device {
+    h: *mut sys::tkm_crs,
+    pub rs_x_size: usize,
+    pub rs_y_size: usize,
+}
+
+impl Drop for Sigma1Device {
+    fn drop(&mut self) { unsafe { sys::tkm_crs_free(ctx(), self.h) }; }
+}
+
+impl Sigma1Device {
+    /// `xy_powers` as stored in the archived CRS: 2 x 48 little-endian bytes per point, index rs_y*h + i <-> x^h y^i
+    /// (iotools/mod.rs:1701-1706; prove/src/sigma_source.rs:22-32 mmaps the file, so this is one cudaMemcpy of the mapping).
+    pub fn upload(xy_powers: &[G1serde], rs_x_size: usize, rs_y_size: usize) -> Self {
+        assert_eq!(xy_powers.len(), rs_x_size * rs_y_size);
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::tkm_crs_upload(ctx(), xy_powers.as_ptr() as *const u8, rs_x_size, rs_y_size, &mut h) });
+        Self { h, rs_x_size, rs_y_size }
+    }
+    pub fn encode_poly(&self, poly: &mut DensePolynomialExt) -> G1serde {
+        let mut out = G1serde([0u8; 96]);
+        check(unsafe { sys::tkm_poly_commit(ctx(), poly.handle(), self.h, out.0.as_mut_ptr()) });
+        out
+    }
+}
+
+/// msm_g1_bases (group_structures/mod.rs:127-143): host scalars and host bases, one affine result.
+pub fn msm_g1_bases(scalars: &[ScalarField], bases: &[G1serde]) -> G1serde {
+    if scalars.len() != bases.len() { panic!("msm input length mismatch"); }
+    let mut out = G1serde([0u8; 96]);
+    check(unsafe { sys::tkm_msm_g1_host(ctx(), scalars.as_ptr() as *const u8, bases.as_ptr() as *const u8, scalars.len(), out.0.as_mut_ptr()) });
+    out
+}
