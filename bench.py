@@ -51,7 +51,8 @@ def random_scalars(seed, n):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons; started before the warm-up so that samples exist for short
+    timed regions, summarised over the [t0, t1] window of the timed region."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -62,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -71,31 +72,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [s.strip() for s in ln.split(",")]
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1 + 0.06:
+                continue
+            f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                power.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -108,6 +116,7 @@ def run_reference(args, rank, world):
     import oracle_ffi as O
 
     O.build()
+    O.set_num_threads(len(os.sched_getaffinity(0)))  # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
     log_sample = 18  # bounded sample of the 2^22 workload: ~1-2 s per step on 8 threads
     n = 1 << log_sample
     G = np.frombuffer(G1_GEN[0].to_bytes(48, "little") + G1_GEN[1].to_bytes(48, "little"), dtype=np.uint64).copy()
@@ -149,6 +158,11 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    # keep stdout clean for the one JSON line (NCCL / libraries may print banners): route fd 1 to stderr until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -213,17 +227,16 @@ def main():
 
     def timed(fn, steps):
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         l0 = ctx.launch_count()
         ctx.time_begin()
         t0 = time.perf_counter()
         for _ in range(steps):
             res = fn()
         ms = ctx.time_end()
-        wall = (time.perf_counter() - t0) * 1e3
+        t1 = time.perf_counter()
+        wall = (t1 - t0) * 1e3
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.summary(t0, t1)
         launches = ctx.launch_count() - l0
         # device-event time on the launching stream; the NCCL combine (N>1) runs on torch's stream, so take the larger of
         # the event time and the host wall time around the same region, then the max over ranks
@@ -234,6 +247,8 @@ def main():
             t = float(tt.item())
         return t / steps, launches, clocks, res
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warm):
         r0 = step_resident()
     ms_res, launches, clocks, r1 = timed(step_resident, args.steps)
@@ -308,11 +323,13 @@ def main():
                                             "api": "tkm_bintt_host (replaces _biNTT with HostSlice in/out)"}
             ctx.dev_free(d_poly)
 
-            # ---- CPU baseline beside it: the oracle port on the host cores, bounded sample, also the bit-exact check
+        if rank == 0 and world == 1:
+            # ---- CPU baseline beside it (N=1 only): the oracle port on the host cores, bounded sample, also the bit-exact check
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle_ffi as O
 
             O.build()
+            O.set_num_threads(len(os.sched_getaffinity(0)))
             ls = min(18, args.log_n)
             ns = 1 << ls
             hb = h_bases.numpy().view(np.uint64)[:ns]
@@ -332,6 +349,45 @@ def main():
                                     "sample": f"first 2^{ls} points of the same inputs, oracle/oracle.c Pippenger (OpenMP); result compared bit-exactly with the GPU",
                                     "bintt": {"value": x2 * y2 / dt_ntt / 1e9, "unit": "Gelem/s", "sample": "4096x256 forward biNTT, oracle/oracle.c radix-2 (OpenMP)"},
                                     "published_reference": "ICICLE CPU backend: 1.01 Mpts/s at 8192x511 pts; biNTT 2^23 forward 497 ms (unnamed macOS host, BASELINE.md)"}
+    if world > 1 and not args.skip_aux:
+        # ---- row-sharded bivariate NTT with the X<->Y transpose as an NCCL all-to-all
+        from tokamak_b200 import dist as D
+
+        ops = D.CudaLocalOps(ctx)
+        ctx.init_ntt_domain_for_size(NTT_X * NTT_Y)
+        nn = NTT_X * NTT_Y
+        lo, hi = D.shard_range(NTT_X, world, rank)
+        src = torch.from_numpy(random_scalars(4000 + rank, (hi - lo) * NTT_Y).view(np.int64)).cuda().view(hi - lo, NTT_Y, 4)
+        res = {}
+        for key in ("forward", "roundtrip"):
+            def one(buf):
+                ev = D.bintt_sharded_forward(ops, buf, NTT_X, NTT_Y)
+                if key == "roundtrip":
+                    ev = D.bintt_sharded_inverse(ops, ev.contiguous(), NTT_X, NTT_Y)
+                return ev
+            bufs = [src.clone() for _ in range(warm + args.steps)]
+            for i in range(warm):
+                out = one(bufs[i])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                out = one(bufs[warm + i])
+            e1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            res[key] = float(tt.item())
+            if key == "roundtrip":
+                assert torch.equal(out.view(-1), src.view(-1)), "sharded biNTT round trip is not the identity"
+            del bufs
+        if rank == 0:
+            line["bintt_sharded"] = {"shape": [NTT_X, NTT_Y], "ranks": world, "forward_ms": res["forward"], "forward_gelem_s": nn / res["forward"] / 1e6,
+                                     "roundtrip_ms": res["roundtrip"], "scaling": "strong", "exchange": "all_to_all_single (NCCL), one per direction",
+                                     "alltoall_bytes_per_rank": (world - 1) * (nn // world // world) * 32}
+    sampler.stop()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -1,0 +1,66 @@
+"""torchrun worker (one process per GPU, NCCL): sharded biNTT and sharded MSM against the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tokamak-zk-evm_b200")):
+    sys.path.insert(0, p)
+import oracle_ffi as O  # noqa: E402
+import pyref as P  # noqa: E402
+import tokamak_b200 as T  # noqa: E402
+from tokamak_b200 import dist as D  # noqa: E402
+
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+rank, world = dist.get_rank(), dist.get_world_size()
+ctx = T.Context(local_rank)
+ctx.init_ntt_domain_for_size(1 << 20)
+ops = D.CudaLocalOps(ctx)
+dev = torch.device("cuda", local_rank)
+
+
+def to_dev_mont(a):
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(dev)
+    T.check(ctx.lib.tkm_fr_to_mont(ctx.h, t.data_ptr(), t.data_ptr(), t.numel() // 4))
+    return t
+
+
+def from_dev_mont(t):
+    t = t.contiguous().clone()
+    T.check(ctx.lib.tkm_fr_from_mont(ctx.h, t.data_ptr(), t.data_ptr(), t.numel() // 4))
+    torch.cuda.synchronize()
+    return t.cpu().numpy().view(np.uint64).reshape(-1, 4)
+
+
+for (x, y, cx, cy) in ((64, 32, None, None), (2048, 64, 12345, 678910), (4096, 256, None, None)):
+    full = O.random_fr(11 + x, x * y)
+    lo, hi = D.shard_range(x, world, rank)
+    t = to_dev_mont(full.reshape(x, y, 4)[lo:hi].copy()).view(hi - lo, y, 4)
+    ev = D.bintt_sharded_forward(ops, t, x, y, cx, cy)
+    exp = O.bintt(full, x, y, False, None if cx is None else O.fr_from_int(cx), None if cy is None else O.fr_from_int(cy)).reshape(x, y, 4)
+    yb = y // world
+    got = from_dev_mont(ev).reshape(x, yb, 4)
+    assert np.array_equal(got, exp[:, rank * yb:(rank + 1) * yb]), f"forward column shard {x}x{y}"
+    back = D.bintt_sharded_inverse(ops, ev.contiguous(), x, y, cx, cy)
+    assert np.array_equal(from_dev_mont(back).reshape(hi - lo, y, 4), full.reshape(x, y, 4)[lo:hi]), "round trip"
+
+n = 50001  # ragged shards
+G = np.frombuffer(P.g1_to_bytes(P.G1_GEN), dtype=np.uint64).copy()
+pts = O.g1_fixed_base_mul_batch(G, O.random_fr(21, n))
+ss = O.random_fr(22, n)
+lo, hi = D.shard_range(n, world, rank)
+d_b = torch.from_numpy(pts[lo:hi].copy().view(np.int64)).to(dev)
+T.check(ctx.lib.tkm_g1_bases_to_mont(ctx.h, d_b.data_ptr(), d_b.data_ptr(), hi - lo))
+d_s = torch.from_numpy(ss[lo:hi].copy().view(np.int64)).to(dev)
+tot = D.msm_sharded(ops, d_s, d_b, hi - lo)
+if rank == 0:
+    assert np.array_equal(tot, O.msm_g1(ss, pts)), "sharded MSM total"
+dist.barrier()
+print(f"rank {rank} of {world} ok", flush=True)
+ctx.close()
+dist.destroy_process_group()

@@ -74,7 +74,12 @@ class Context:
 
     # -- streams / timing ------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
-        check(self.lib.tkm_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+        """Run the library on a caller-owned cudaStream_t.  None restores the context's own stream; the value 0
+        (torch's default stream) is mapped to cudaStreamLegacy (handle 0x1) so work is ordered with it."""
+        if cuda_stream_ptr is None:
+            check(self.lib.tkm_ctx_set_stream(self.h, None))
+        else:
+            check(self.lib.tkm_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr if cuda_stream_ptr else 1)))
 
     def sync(self):
         check(self.lib.tkm_ctx_sync(self.h))
