@@ -78,6 +78,14 @@ int32_t tkm_fr_vec_op(tkm_ctx *ctx, int32_t op, const void *dev_a, const void *d
 int32_t tkm_fr_vec_scale(tkm_ctx *ctx, const uint8_t s32[32], const void *dev_a, void *dev_out, size_t n);
 /* VecOps::inv, batched (Montgomery trick in-kernel), inv(0)=0 (bivariate_polynomial/mod.rs:2180). */
 int32_t tkm_fr_vec_inv(tkm_ctx *ctx, const void *dev_a, void *dev_out, size_t n);
+/* device_vec_from_scalar (bivariate_polynomial/mod.rs:452-457): out[k] = s for k < n. */
+int32_t tkm_fr_vec_fill(tkm_ctx *ctx, const uint8_t s32[32], void *dev_out, size_t n);
+/* Pointwise product with the evaluations of (X - 1) on the x_size-th roots of unity, i.e.
+ * out[i*y_size + j] = in[i*y_size + j] * (omega_x^i - 1): PolyExpr::MulXMinusOne in the evaluation domain
+ * (x_minus_one_evals, bivariate_polynomial/mod.rs:504-518) without materialising the factor matrix. */
+int32_t tkm_fr_mul_x_minus_one(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t x_size, size_t y_size);
+/* VecOps::transpose (vector_operations/mod.rs:139,168): rows x cols -> cols x rows, out != in. */
+int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t rows, size_t cols);
 /* Host-buffer forms of the same ops (HostSlice in, HostSlice out; canonical bytes). */
 int32_t tkm_fr_vec_op_host(tkm_ctx *ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
 
@@ -141,6 +149,8 @@ int32_t tkm_poly_from_coeffs_host(tkm_ctx *ctx, const uint8_t *coeffs, size_t x_
 /* from_rou_evals (:1615-1644). */
 int32_t tkm_poly_from_evals_host(tkm_ctx *ctx, const uint8_t *evals, size_t x_size, size_t y_size,
                                  const uint8_t *coset_x32, const uint8_t *coset_y32, tkm_poly **out);
+/* from_coeffs with a DeviceSlice (:1527-1551): copies x_size*y_size Montgomery-form elements from dev_coeffs. */
+int32_t tkm_poly_from_device(tkm_ctx *ctx, const void *dev_coeffs, size_t x_size, size_t y_size, tkm_poly **out);
 int32_t tkm_poly_zero(tkm_ctx *ctx, size_t x_size, size_t y_size, tkm_poly **out);
 int32_t tkm_poly_clone(tkm_ctx *ctx, const tkm_poly *p, tkm_poly **out); /* Clone (:520-530) */
 int32_t tkm_poly_free(tkm_ctx *ctx, tkm_poly *p);

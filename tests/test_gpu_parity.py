@@ -465,3 +465,67 @@ def test_encode_poly_fixed_tau(ctx, T):
     with pytest.raises(T.TkmError) as e:
         sigma.encode_poly(big)
     assert "Insufficient length" in str(e.value)
+
+
+def test_poly_expr_fused_matches_coefficients(ctx, T):
+    """test_poly_expr_fused_matches_coefficients (tests.rs:1240-1276), plus a larger instance checked against the oracle."""
+    for sx, sy, seed in ((2, 2, 400), (16, 8, 410)):
+        polys = [poly_from(T, ctx, O.random_fr(seed + k, sx * sy), sx, sy) for k in range(5)]
+        a, b, c, d, e = polys
+        E = T.PolyExpr
+        expr = E.weighted_sum([
+            (7, E.mul_x_minus_one(E.sub(E.mul(E.poly(a), E.poly(b)), E.mul(E.poly(c), E.poly(d))))),
+            (11, E.mul(E.sub(E.poly(a), E.scalar(1)), E.poly(e))),
+        ])
+        coeff_result = expr.evaluate_coeffs()
+        fused_result = expr.evaluate_fused()
+        rng = P.SplitMix64(seed)
+        for _ in range(4):
+            x, y = rng.fr(), rng.fr()
+            assert coeff_result.eval(x, y) == fused_result.eval(x, y)
+        # value check against big-int arithmetic at one point
+        x, y = rng.fr(), rng.fr()
+        ev = [P.eval_xy(to_ints(p.copy_coeffs()), sx, sy, x, y) for p in polys]
+        exp = (7 * (x - 1) * (ev[0] * ev[1] - ev[2] * ev[3]) + 11 * (ev[0] - 1) * ev[4]) % P.R_MOD
+        assert fused_result.eval(x, y) == exp
+        # a bigger domain than needed gives the same polynomial (evaluate_fused_with_domain)
+        big = expr.evaluate_fused_with_domain(4 * sx, 4 * sy)
+        assert big.eval(x, y) == exp
+        with pytest.raises(ValueError):
+            expr.evaluate_fused_with_domain(sx, sy)
+
+
+def test_transpose_fill_x_minus_one(ctx, T):
+    """VecOps::transpose (vector_operations/mod.rs:139), device_vec_from_scalar and x_minus_one_evals
+    (bivariate_polynomial/mod.rs:452-457,504-518)."""
+    import ctypes
+
+    rows, cols = 100, 37
+    a = O.random_fr(420, rows * cols)
+    d = ctx.upload_fr(a)
+    o = ctx.dev_alloc(rows * cols * 32)
+    ctx.transpose_dev(d, o, rows, cols)
+    got = ctx.download_fr(o, rows * cols).reshape(cols, rows, 4)
+    assert np.array_equal(got, a.reshape(rows, cols, 4).transpose(1, 0, 2))
+    s = frs([123456789])
+    T.check(ctx.lib.tkm_fr_vec_fill(ctx.h, s.ctypes.data, ctypes.c_void_p(o), 50))
+    assert to_ints(ctx.download_fr(o, 50)) == [123456789] * 50
+    x, y = 64, 8
+    b = O.random_fr(421, x * y)
+    db = ctx.upload_fr(b)
+    T.check(ctx.lib.tkm_fr_mul_x_minus_one(ctx.h, ctypes.c_void_p(db), ctypes.c_void_p(db), x, y))
+    w = P.root_of_unity(x)
+    bi = to_ints(b)
+    exp = [bi[i * y + j] * (pow(w, i, P.R_MOD) - 1) % P.R_MOD for i in range(x) for j in range(y)]
+    assert to_ints(ctx.download_fr(db, x * y)) == exp
+    for p in (d, o, db):
+        ctx.dev_free(p)
+
+
+def test_div_by_vanishing_legacy_name(ctx, T):
+    """div_by_vanishing (legacy entry, tests.rs:1216-1222): unique decomposition => same output as _opt."""
+    x, y, c, d = 64, 32, 16, 8
+    a = O.random_fr(430, x * y)
+    qx, qy = poly_from(T, ctx, a, x, y).div_by_vanishing(c, d)
+    eqx, eqy = O.div_by_vanishing_opt(a, x, y, c, d)
+    assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy)

@@ -244,6 +244,21 @@ int32_t tkm_fr_vec_inv(tkm_ctx *ctx, const void *a, void *out, size_t n) {
   API_BEGIN
   return vec_inv(ctx, (const Fr *)a, (Fr *)out, n);
 }
+int32_t tkm_fr_vec_fill(tkm_ctx *ctx, const uint8_t s32[32], void *out, size_t n) {
+  API_BEGIN
+  TKM_REQUIRE(s32 && (out || n == 0), "null argument");
+  return vec_fill(ctx, fr_from_bytes_host(s32), (Fr *)out, n);
+}
+int32_t tkm_fr_mul_x_minus_one(tkm_ctx *ctx, const void *in, void *out, size_t x_size, size_t y_size) {
+  API_BEGIN
+  TKM_REQUIRE(in && out, "null argument");
+  return vec_mul_x_minus_one(ctx, (const Fr *)in, (Fr *)out, x_size, y_size);
+}
+int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *in, void *out, size_t rows, size_t cols) {
+  API_BEGIN
+  TKM_REQUIRE(in && out, "null argument");
+  return vec_transpose(ctx, (const Fr *)in, (Fr *)out, rows, cols);
+}
 int32_t tkm_fr_vec_op_host(tkm_ctx *ctx, int32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n) {
   API_BEGIN
   TKM_REQUIRE(a && b && out, "null argument");

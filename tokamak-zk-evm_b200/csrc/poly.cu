@@ -391,6 +391,19 @@ int32_t tkm_poly_from_evals_host(tkm_ctx *ctx, const uint8_t *evals, size_t x_si
   return st;
 }
 
+int32_t tkm_poly_from_device(tkm_ctx *ctx, const void *dev_coeffs, size_t x_size, size_t y_size, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(dev_coeffs && out, "null argument");
+  TKM_TRY(poly_alloc(ctx, x_size, y_size, out));
+  cudaError_t e = cudaMemcpyAsync((*out)->d, dev_coeffs, x_size * y_size * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    poly_release(ctx, *out);
+    *out = nullptr;
+    return fail(TKM_ERR_CUDA, "D2D copy failed: %s", cudaGetErrorString(e));
+  }
+  return TKM_OK;
+}
+
 int32_t tkm_poly_zero(tkm_ctx *ctx, size_t x_size, size_t y_size, tkm_poly **out) {
   API_BEGIN
   TKM_REQUIRE(out, "null argument");

@@ -99,6 +99,79 @@ __global__ void __launch_bounds__(128) k_vec_inv(const Fr *__restrict__ a, Fr *_
   }
 }
 
+__global__ void __launch_bounds__(256) k_vec_fill(Fr s, Fr *__restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = s;
+}
+
+// out[i][j] = in[i][j] * (omega_x^i - 1); omega_x^i read from the domain table tw[k] = omega_M^k, k <= M/2
+// (second half of the circle: omega^(M/2 + k) = -omega^k).
+__global__ void __launch_bounds__(256) k_mul_x_minus_one(const Fr *__restrict__ in, Fr *__restrict__ out, size_t x_size, size_t y_size,
+                                                         const Fr *__restrict__ tw, uint32_t log_stride, size_t half_m) {
+  size_t total = x_size * y_size;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    size_t i = k / y_size;
+    size_t e = i << log_stride;  // exponent of omega_M
+    Fr w;
+    if (e <= half_m) {
+      w = tw[e];
+    } else {
+      Fr t = tw[e - half_m];
+      w = t.neg();
+    }
+    Fr v = in[k];
+    out[k] = v * (w - Fr::one());
+  }
+}
+
+// 32x32 tiles through shared memory, 128-bit accesses on both sides (two uint4 planes, +1 padding).
+__global__ void __launch_bounds__(256) k_transpose(const Fr *__restrict__ in, Fr *__restrict__ out, size_t rows, size_t cols) {
+  __shared__ uint4 lo[32][33], hi[32][33];
+  const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const uint4 *gin = reinterpret_cast<const uint4 *>(in);
+  uint4 *gout = reinterpret_cast<uint4 *>(out);
+  for (int k = ty; k < 32; k += 8) {
+    size_t r = r0 + k, c = c0 + tx;
+    if (r < rows && c < cols) {
+      lo[k][tx] = gin[2 * (r * cols + c)];
+      hi[k][tx] = gin[2 * (r * cols + c) + 1];
+    }
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    size_t c = c0 + k, r = r0 + tx;  // output row = input column
+    if (r < rows && c < cols) {
+      gout[2 * (c * rows + r)] = lo[tx][k];
+      gout[2 * (c * rows + r) + 1] = hi[tx][k];
+    }
+  }
+}
+
+int32_t vec_fill(tkm_ctx *ctx, const Fr &s, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  k_vec_fill<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(s, out, n);
+  return launch_check(ctx, "k_vec_fill");
+}
+int32_t vec_mul_x_minus_one(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x_size, size_t y_size) {
+  if (!is_pow2(x_size)) return fail(TKM_ERR_INVALID_ARGUMENT, "x_size must be a power of two");
+  if (ctx->domain_log2 < 0 || log2_exact(x_size) > (uint32_t)ctx->domain_log2)
+    return fail(TKM_ERR_DOMAIN, "NTT domain is not initialized or smaller than x_size = %zu", x_size);
+  size_t n = x_size * y_size;
+  if (n == 0) return TKM_OK;
+  if (x_size == 1) return vec_fill(ctx, Fr::zero(), out, n);  // X - 1 vanishes on the trivial domain {1}
+  uint32_t log_stride = (uint32_t)ctx->domain_log2 - log2_exact(x_size);
+  k_mul_x_minus_one<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, x_size, y_size, ctx->twiddles, log_stride,
+                                                                             (size_t)1 << (ctx->domain_log2 - 1));
+  return launch_check(ctx, "k_mul_x_minus_one");
+}
+int32_t vec_transpose(tkm_ctx *ctx, const Fr *in, Fr *out, size_t rows, size_t cols) {
+  if (rows * cols == 0) return TKM_OK;
+  if (in == out) return fail(TKM_ERR_INVALID_ARGUMENT, "transpose must be out of place");
+  dim3 g((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_transpose<<<g, 256, 0, ctx->stream>>>(in, out, rows, cols);
+  return launch_check(ctx, "k_transpose");
+}
+
 int32_t vec_to_mont(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n) {
   if (n == 0) return TKM_OK;
   k_mont_convert<K_TO_MONT><<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);

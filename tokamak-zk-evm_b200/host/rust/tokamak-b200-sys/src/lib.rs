@@ -35,6 +35,9 @@ extern "C" {
     pub fn tkm_fr_vec_op(ctx: *mut tkm_ctx, op: i32, a: *const c_void, b: *const c_void, out: *mut c_void, n: usize) -> i32;
     pub fn tkm_fr_vec_scale(ctx: *mut tkm_ctx, s32: *const u8, a: *const c_void, out: *mut c_void, n: usize) -> i32;
     pub fn tkm_fr_vec_inv(ctx: *mut tkm_ctx, a: *const c_void, out: *mut c_void, n: usize) -> i32;
+    pub fn tkm_fr_vec_fill(ctx: *mut tkm_ctx, s32: *const u8, dev_out: *mut c_void, n: usize) -> i32;
+    pub fn tkm_fr_mul_x_minus_one(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize) -> i32;
+    pub fn tkm_fr_transpose(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, rows: usize, cols: usize) -> i32;
     pub fn tkm_fr_vec_op_host(ctx: *mut tkm_ctx, op: i32, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> i32;
     pub fn tkm_bintt(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize, dir: i32,
                      coset_x32: *const u8, coset_y32: *const u8) -> i32;
@@ -62,6 +65,7 @@ extern "C" {
     pub fn tkm_poly_from_coeffs_host(ctx: *mut tkm_ctx, coeffs: *const u8, x_size: usize, y_size: usize, out: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_from_evals_host(ctx: *mut tkm_ctx, evals: *const u8, x_size: usize, y_size: usize, coset_x32: *const u8,
                                     coset_y32: *const u8, out: *mut *mut tkm_poly) -> i32;
+    pub fn tkm_poly_from_device(ctx: *mut tkm_ctx, dev_coeffs: *const c_void, x_size: usize, y_size: usize, out: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_zero(ctx: *mut tkm_ctx, x_size: usize, y_size: usize, out: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_clone(ctx: *mut tkm_ctx, p: *const tkm_poly, out: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_free(ctx: *mut tkm_ctx, p: *mut tkm_poly) -> i32;

@@ -210,6 +210,10 @@ class Context:
                                           ctypes.c_void_p(d_idx), n, _vp(out)))
         return out
 
+    def transpose_dev(self, d_in, d_out, rows, cols):
+        """VecOps::transpose (vector_operations/mod.rs:139,168)."""
+        check(self.lib.tkm_fr_transpose(self.h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), rows, cols))
+
     def upload_bases(self, bases):
         """Canonical affine points -> device table in Montgomery form. Returns device pointer."""
         bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 12)
@@ -460,6 +464,12 @@ class DensePolynomialExt:
         check(self.ctx.lib.tkm_poly_div_by_vanishing(self.ctx.h, self.h, x_degree, y_degree, ctypes.byref(qx), ctypes.byref(qy)))
         return DensePolynomialExt(self.ctx, qx), DensePolynomialExt(self.ctx, qy)
 
+    def div_by_vanishing(self, x_degree, y_degree, cache=None):
+        """div_by_vanishing (:2096-2282), the legacy coset-NTT formulation.  With deg_X(Q_Y) < c the decomposition
+        P = Q_X (X^c - 1) + Q_Y (Y^d - 1) is unique (X^c - 1 and Y^d - 1 are coprime), so it returns exactly the
+        polynomials of div_by_vanishing_opt; the denominator cache of the reference is not needed."""
+        return self.div_by_vanishing_opt(x_degree, y_degree)
+
     def div_by_ruffini(self, x, y):
         kx, px = fr_bytes(x)
         ky, py = fr_bytes(y)
@@ -467,3 +477,236 @@ class DensePolynomialExt:
         r = np.zeros(4, dtype=np.uint64)
         check(self.ctx.lib.tkm_poly_div_by_ruffini(self.ctx.h, self.h, px, py, ctypes.byref(qx), ctypes.byref(qy), _vp(r)))
         return DensePolynomialExt(self.ctx, qx), DensePolynomialExt(self.ctx, qy), fr_to_int(r)
+
+
+def _domain_size_for_degree(degree):
+    """domain_size_for_degree (bivariate_polynomial/mod.rs:438-444)."""
+    if degree < 0:
+        return 1
+    n = degree + 1
+    return 1 << (n - 1).bit_length()
+
+
+class PolyExpr:
+    """Expression DAG over polynomials evaluated either coefficient-wise or fused in the evaluation domain:
+    one NTT per distinct leaf (cached by object identity), pointwise device ops, one inverse NTT at the end
+    (PolyExpr, libs/src/bivariate_polynomial/mod.rs:140-436; used for prove2's p_comb, prove/src/lib.rs:2110-2146)."""
+
+    def __init__(self, kind, *args):
+        self.kind, self.args = kind, args
+
+    # -- constructors (same names as the reference) -------------------------------------------------
+    @staticmethod
+    def poly(p):
+        return PolyExpr("poly", p)
+
+    @staticmethod
+    def scalar(s):
+        return PolyExpr("scalar", int(s) % R_MOD)
+
+    @staticmethod
+    def add(lhs, rhs):
+        return PolyExpr("add", lhs, rhs)
+
+    @staticmethod
+    def sub(lhs, rhs):
+        return PolyExpr("sub", lhs, rhs)
+
+    @staticmethod
+    def mul(lhs, rhs):
+        return PolyExpr("mul", lhs, rhs)
+
+    @staticmethod
+    def scale(s, expr):
+        return PolyExpr("scale", int(s) % R_MOD, expr)
+
+    @staticmethod
+    def mul_x_minus_one(expr):
+        return PolyExpr("xm1", expr)
+
+    @staticmethod
+    def weighted_sum(terms):
+        return PolyExpr("sum", [PolyExpr.scale(s, e) for s, e in terms])
+
+    def _ctx(self):
+        if self.kind == "poly":
+            return self.args[0].ctx
+        for a in self.args:
+            if isinstance(a, PolyExpr):
+                c = a._ctx()
+                if c is not None:
+                    return c
+            if isinstance(a, list):
+                for t in a:
+                    c = t._ctx()
+                    if c is not None:
+                        return c
+        return None
+
+    # -- coefficient-domain evaluation (evaluate_coeffs, :190-218) --------------------------------------
+    def evaluate_coeffs(self, ctx=None):
+        ctx = ctx or self._ctx()
+        k, a = self.kind, self.args
+        if k == "poly":
+            return a[0].clone()
+        if k == "scalar":
+            return DensePolynomialExt.from_coeffs(ctx, frs_from_ints([a[0]]), 1, 1)
+        if k == "add":
+            return a[0].evaluate_coeffs(ctx) + a[1].evaluate_coeffs(ctx)
+        if k == "sub":
+            return a[0].evaluate_coeffs(ctx) - a[1].evaluate_coeffs(ctx)
+        if k == "mul":
+            return a[0].evaluate_coeffs(ctx) * a[1].evaluate_coeffs(ctx)
+        if k == "scale":
+            return a[1].evaluate_coeffs(ctx) * a[0]
+        if k == "xm1":
+            p = a[0].evaluate_coeffs(ctx)
+            return p.mul_monomial(1, 0) - p
+        if k == "sum":
+            if not a[0]:
+                return DensePolynomialExt.zero(ctx)
+            acc = a[0][0].evaluate_coeffs(ctx)
+            for t in a[0][1:]:
+                acc = acc + t.evaluate_coeffs(ctx)
+            return acc
+        raise ValueError(k)
+
+    # -- degree bound (:262-309) ---------------------------------------------------------------------------
+    def degree_bound(self):
+        k, a = self.kind, self.args
+        if k == "poly":
+            return a[0].find_degree()
+        if k == "scalar":
+            return (-1, -1) if a[0] == 0 else (0, 0)
+        if k in ("add", "sub"):
+            l, r = a[0].degree_bound(), a[1].degree_bound()
+            return max(l[0], r[0]), max(l[1], r[1])
+        if k == "mul":
+            l, r = a[0].degree_bound(), a[1].degree_bound()
+            if min(l + r) < 0:
+                return -1, -1
+            return l[0] + r[0], l[1] + r[1]
+        if k == "scale":
+            return (-1, -1) if a[0] == 0 else a[1].degree_bound()
+        if k == "xm1":
+            d = a[0].degree_bound()
+            return (-1, -1) if min(d) < 0 else (d[0] + 1, d[1])
+        if k == "sum":
+            out = (-1, -1)
+            for t in a[0]:
+                d = t.degree_bound()
+                out = (max(out[0], d[0]), max(out[1], d[1]))
+            return out
+        raise ValueError(k)
+
+    # -- fused evaluation (:220-260, 311-435) ------------------------------------------------------------------
+    def evaluate_fused(self, ctx=None):
+        xd, yd = self.degree_bound()
+        return self.evaluate_fused_with_domain(_domain_size_for_degree(xd), _domain_size_for_degree(yd), ctx)
+
+    def evaluate_fused_with_domain(self, target_x_size, target_y_size, ctx=None):
+        ctx = ctx or self._ctx()
+        if target_x_size & (target_x_size - 1) or target_y_size & (target_y_size - 1):
+            raise ValueError("Fused polynomial expression domains must be powers of two.")
+        xd, yd = self.degree_bound()
+        if _domain_size_for_degree(xd) > target_x_size or _domain_size_for_degree(yd) > target_y_size:
+            raise ValueError("Fused polynomial expression domain is too small for the expression degree.")
+        ev = _EvalDomain(ctx, target_x_size, target_y_size)
+        buf, owned = ev.run(self)
+        if not owned:
+            buf = ev.copy(buf)
+        check(ctx.lib.tkm_bintt(ctx.h, ctypes.c_void_p(buf), ctypes.c_void_p(buf), target_x_size, target_y_size, INVERSE, None, None))
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_poly_from_device(ctx.h, ctypes.c_void_p(buf), target_x_size, target_y_size, ctypes.byref(h)))
+        ev.release(buf)
+        ev.close()
+        return DensePolynomialExt(ctx, h)
+
+
+class _EvalDomain:
+    """Device buffers of x*y evaluations with a per-leaf cache; every node returns (device pointer, owned)."""
+
+    def __init__(self, ctx, x, y):
+        self.ctx, self.x, self.y, self.n = ctx, x, y, x * y
+        self.cache = {}
+        self.free = []
+
+    def alloc(self):
+        return self.free.pop() if self.free else self.ctx.dev_alloc(self.n * 32)
+
+    def release(self, ptr):
+        self.free.append(ptr)
+
+    def copy(self, src):
+        dst = self.alloc()
+        one = frs_from_ints([1])
+        check(self.ctx.lib.tkm_fr_vec_scale(self.ctx.h, _vp(one), ctypes.c_void_p(src), ctypes.c_void_p(dst), self.n))
+        return dst
+
+    def close(self):
+        for p in list(self.cache.values()) + self.free:
+            self.ctx.dev_free(p)
+        self.cache, self.free = {}, []
+
+    def _binary(self, op, l, r):
+        lib, h = self.ctx.lib, self.ctx.h
+        (pl, ol), (pr, orr) = self.run(l), self.run(r)
+        out = pl if ol else (pr if orr and op != OP_SUB else self.alloc())
+        check(lib.tkm_fr_vec_op(h, op, ctypes.c_void_p(pl), ctypes.c_void_p(pr), ctypes.c_void_p(out), self.n))
+        for p, o in ((pl, ol), (pr, orr)):
+            if o and p != out:
+                self.release(p)
+        return out, True
+
+    def run(self, e):
+        lib, h, n = self.ctx.lib, self.ctx.h, self.n
+        k, a = e.kind, e.args
+        if k == "poly":
+            key = id(a[0])
+            if key not in self.cache:  # eval_poly_leaf (:459-502): resize + forward NTT once per distinct leaf
+                q = a[0].clone()
+                q.resize(self.x, self.y)
+                if q.shape != (self.x, self.y):
+                    raise ValueError("leaf polynomial larger than the evaluation domain")
+                check(lib.tkm_poly_ntt_inplace(h, q.h, FORWARD, None, None))
+                buf = self.alloc()
+                one = frs_from_ints([1])
+                check(lib.tkm_fr_vec_scale(h, _vp(one), ctypes.c_void_p(q.device_ptr()), ctypes.c_void_p(buf), n))
+                q.close()
+                self.cache[key] = buf
+            return self.cache[key], False
+        if k == "scalar":
+            buf = self.alloc()
+            s = frs_from_ints([a[0]])
+            check(lib.tkm_fr_vec_fill(h, _vp(s), ctypes.c_void_p(buf), n))
+            return buf, True
+        if k == "add":
+            return self._binary(OP_ADD, a[0], a[1])
+        if k == "sub":
+            return self._binary(OP_SUB, a[0], a[1])
+        if k == "mul":
+            return self._binary(OP_MUL, a[0], a[1])
+        if k == "scale":
+            p, o = self.run(a[1])
+            if a[0] == 1:
+                return p, o
+            out = p if o else self.alloc()
+            s = frs_from_ints([a[0]])
+            check(lib.tkm_fr_vec_scale(h, _vp(s), ctypes.c_void_p(p), ctypes.c_void_p(out), n))
+            return out, True
+        if k == "xm1":
+            p, o = self.run(a[0])
+            out = p if o else self.alloc()
+            check(lib.tkm_fr_mul_x_minus_one(h, ctypes.c_void_p(p), ctypes.c_void_p(out), self.x, self.y))
+            return out, True
+        if k == "sum":
+            acc = self.alloc()
+            z = frs_from_ints([0])
+            check(lib.tkm_fr_vec_fill(h, _vp(z), ctypes.c_void_p(acc), n))
+            for t in a[0]:
+                p, o = self.run(t)
+                check(lib.tkm_fr_vec_op(h, OP_ADD, ctypes.c_void_p(acc), ctypes.c_void_p(p), ctypes.c_void_p(acc), n))
+                if o:
+                    self.release(p)
+            return acc, True
+        raise ValueError(k)

@@ -33,6 +33,9 @@ SIGNATURES = {
     "tkm_fr_vec_scale": [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_fr_vec_inv": [c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_fr_vec_op_host": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t],
+    "tkm_fr_vec_fill": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "tkm_fr_mul_x_minus_one": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t],
+    "tkm_fr_transpose": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t],
     "tkm_bintt": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p, c_void_p],
     "tkm_bintt_host": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p, c_void_p],
     "tkm_ntt_batch": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_int32, c_void_p],
@@ -50,6 +53,7 @@ SIGNATURES = {
     "tkm_crs_device_ptr": [c_void_p, P(c_void_p), P(c_size_t), P(c_size_t)],
     "tkm_poly_from_coeffs_host": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_poly_from_evals_host": [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, P(c_void_p)],
+    "tkm_poly_from_device": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_poly_zero": [c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_poly_clone": [c_void_p, c_void_p, P(c_void_p)],
     "tkm_poly_free": [c_void_p, c_void_p],
