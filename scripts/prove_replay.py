@@ -1,0 +1,178 @@
+"""Replay of the hot-path operation sequence of ONE Tokamak prove (init + prove0..prove4) at the checked-in
+circuit shape (n = m_I = 4096, s_max = 256; SURVEY.md Appendix B, from the reference's own timing artifacts),
+on synthetic polynomials of the real shapes.  It is NOT a prover: the protocol algebra, transcript and witness
+construction are SURVEY §8(f) rows.  It measures what the device-resident engine spends on the 19 dense + 3 sparse
+commitments, ~30 bivariate transforms, the vanishing/Ruffini divisions and the evaluations of one proof, so the
+number can be set beside the reference's `encode` (24.33 s CPU / 1.27 s ICICLE-CUDA) and `poly` (13.55 s / 13.19 s) spans.
+"""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
+import tokamak_b200 as T  # noqa: E402
+
+N, S_MAX, M_I = 4096, 256, 4096
+RS_X, RS_Y = 8192, 512
+G1_GEN = (
+    0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+    0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1,
+)
+
+
+def rand_fr(rng, n):
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(0x3FFFFFFFFFFFFFFF)
+    return a
+
+
+class Replay:
+    def __init__(self, ctx, seed=7):
+        self.ctx = ctx
+        self.rng = np.random.default_rng(seed)
+        self.t = {"encode": 0.0, "ntt": 0.0, "poly": 0.0}
+        self.count = {"encode": 0, "encode_points": 0, "ntt": 0, "poly": 0}
+        self.detail = {}
+
+    def timed(self, cat, fn, *a, label=None):
+        self.ctx.sync()
+        t0 = time.perf_counter()
+        r = fn(*a)
+        self.ctx.sync()
+        dt = time.perf_counter() - t0
+        self.t[cat] += dt
+        self.count[cat] += 1
+        key = label or getattr(fn, "__name__", "op")
+        d = self.detail.setdefault(key, [0, 0.0])
+        d[0] += 1
+        d[1] += dt
+        return r
+
+    def poly(self, x_extent, y_extent):
+        """Random polynomial whose non-zero rectangle is exactly x_extent x y_extent inside the next power-of-two shape."""
+        nx, ny = 1 << (x_extent - 1).bit_length(), 1 << (y_extent - 1).bit_length()
+        a = np.zeros((nx, ny, 4), dtype=np.uint64)
+        a[:x_extent, :y_extent] = rand_fr(self.rng, x_extent * y_extent).reshape(x_extent, y_extent, 4)
+        return T.DensePolynomialExt.from_coeffs(self.ctx, a.reshape(-1, 4), nx, ny)
+
+    def commit(self, sigma, x_extent, y_extent):
+        p = self.poly(x_extent, y_extent)
+        self.count["encode_points"] += x_extent * y_extent
+        return self.timed("encode", sigma.encode_poly, p)
+
+    def ntt(self, p, direction):
+        self.timed("ntt", lambda: T.check(self.ctx.lib.tkm_poly_ntt_inplace(self.ctx.h, p.h, direction, None, None)))
+
+    def product(self, x, y):
+        """Generic _mul at output shape x*y: pad, 2 forward transforms, pointwise, 1 inverse."""
+        a, b = self.poly(x // 2, y // 2), self.poly(x // 2, y // 2)
+        return self.timed("poly", lambda: a * b, label=f"mul_{x}x{y}")
+
+
+def run(ctx, sigma, table_dev, verbose=False):
+    r = Replay(ctx)
+    wall0 = time.perf_counter()
+    # ---- init: 6 INTT 2^20 (b, s0, s1, u, v, w), 1 INTT 128; A_free 128x1; sparse O_pub_free / O_mid / O_prv
+    polys = [r.poly(N, S_MAX) for _ in range(6)]
+    for p in polys:
+        r.ntt(p, T.INVERSE)
+    r.commit(sigma, 128, 1)
+    for npts in (109, 5947, 448581):
+        sc = ctx.upload_fr(rand_fr(r.rng, npts), to_mont=False)
+        idx = r.rng.integers(0, RS_X * RS_Y, size=npts, dtype=np.uint32)
+        di = ctx.dev_alloc(idx.nbytes)
+        ctx.h2d(di, idx)
+        r.timed("encode", ctx.msm_g1_indexed_dev, sc, False, table_dev, di, npts)
+        r.count["encode_points"] += npts
+        ctx.dev_free(sc)
+        ctx.dev_free(di)
+    u, v, w = polys[3], polys[4], polys[5]
+    # ---- prove0: p0 = u*v - w (8192x512), (q0,q1) = p0 / (X^n - 1, Y^s_max - 1), 6 combos, 6 commitments
+    uv = r.timed("poly", lambda: u * v, label="mul_8192x512")
+    p0 = r.timed("poly", lambda: uv - w, label="sub")
+    r.timed("poly", lambda: p0.div_by_vanishing_opt(N, S_MAX), label="div_by_vanishing_8192x512")
+    for _ in range(6):
+        r.timed("poly", lambda: u * 12345 + v, label="lincomb")
+    for ext in ((4097, 257), (4097, 257), (4099, 259), (4097, 511), (4097, 257), (4098, 258)):
+        r.commit(sigma, *ext)
+    # ---- prove1: f, g evaluations (2 NTT), pointwise division, (scan omitted: protocol row f1), 1 INTT, commit R
+    f, g = r.poly(M_I, S_MAX), r.poly(M_I, S_MAX)
+    r.ntt(f, T.FORWARD)
+    r.ntt(g, T.FORWARD)
+    n20 = M_I * S_MAX
+    r.timed("poly", lambda: T.check(ctx.lib.tkm_fr_vec_op(ctx.h, T.OP_DIV, ctypes.c_void_p(g.device_ptr()), ctypes.c_void_p(f.device_ptr()),
+                                                       ctypes.c_void_p(g.device_ptr()), n20)), label="point_div_2^20")
+    r.ntt(g, T.INVERSE)
+    r.commit(sigma, 4097, 257)
+    # ---- prove2: fused p_comb on 16384x512 (7 leaves, ~12 pointwise passes, 1 inverse), division, 3 products, 2 commitments
+    E = T.PolyExpr
+    leaves = [r.poly(M_I + 1, S_MAX // 2 + 1) for _ in range(7)]  # degree(3 leaves)(X-1) fits 16384 x 512
+    a, b, c, d, e, f2, g2 = [E.poly(p) for p in leaves]
+    expr = E.weighted_sum([
+        (3, E.mul(E.mul_x_minus_one(E.sub(E.mul(a, b), E.mul(c, d))), e)),
+        (5, E.mul(E.sub(E.mul(a, f2), E.mul(c, g2)), E.sub(e, E.scalar(1)))),
+        (7, E.mul(E.sub(a, E.scalar(1)), E.mul(f2, g2))),
+    ])
+    pc = r.timed("poly", lambda: expr.evaluate_fused_with_domain(16384, 512), label="polyexpr_fused_16384x512")
+    r.timed("poly", lambda: pc.div_by_vanishing_opt(M_I, S_MAX), label="div_by_vanishing_16384x512")
+    r.product(8192, 256)
+    r.product(8192, 512)
+    r.product(4096, 256)
+    for ext in ((8192, 511), (8191, 257)):
+        r.commit(sigma, *ext)
+    # ---- prove3: 4 bivariate evaluations of 4096x256 polynomials
+    for p in polys[:4]:
+        r.timed("poly", p.eval, 0x1234567, 0x7654321)
+    # ---- prove4: ~10 evaluations, ~25 combos, 1 product, 5 Ruffini divisions, 9 commitments
+    for k in range(10):
+        r.timed("poly", polys[k % 6].eval, 0x1234567 + k, 0x7654321 + k)
+    for _ in range(25):
+        r.timed("poly", lambda: u * 777 + w, label="lincomb")
+    r.product(8192, 512)
+    big = r.poly(8192, 512)
+    for p in (polys[0], polys[1], polys[2], big, r.poly(128, 1)):
+        r.timed("poly", p.div_by_ruffini, 0xABCDEF, 0xFEDCBA)
+    for ext in ((4098, 511), (1, 510), (4096, 256), (4096, 256), (1, 256), (1, 256), (8191, 511), (1, 510), (127, 1)):
+        r.commit(sigma, *ext)
+    wall = time.perf_counter() - wall0
+    out = {
+        "shape": {"n": N, "s_max": S_MAX, "m_I": M_I, "crs_grid": [RS_X, RS_Y]},
+        "hot_path_s": r.t["encode"] + r.t["ntt"] + r.t["poly"],
+        "encode_s": r.t["encode"], "encode_calls": r.count["encode"], "encode_points": r.count["encode_points"],
+        "ntt_s": r.t["ntt"], "ntt_calls": r.count["ntt"], "poly_s": r.t["poly"], "poly_calls": r.count["poly"],
+        "wall_incl_synthetic_input_generation_s": wall,
+        "reference": {"cpu_prove_s": 45.70, "cpu_encode_s": 24.33, "cpu_poly_s": 13.55, "icicle_cuda_prove_s": 21.08, "icicle_cuda_encode_s": 1.27,
+                      "icicle_cuda_poly_s": 13.19, "source": "BASELINE.md (reference's own artifacts, unnamed hosts)"},
+        "detail_ms": {k: [v[0], round(v[1] * 1e3, 3)] for k, v in sorted(r.detail.items(), key=lambda kv: -kv[1][1])},
+        "note": "operation replay on synthetic polynomials of the reference's shapes; not a proof (protocol driver is SURVEY 8(f) row f1)",
+    }
+    return out
+
+
+def make_sigma(ctx):
+    """8192 x 512 grid of distinct points k*G generated on the device (4.19 M fixed-base multiples)."""
+    rng = np.random.default_rng(99)
+    n = RS_X * RS_Y
+    G = np.frombuffer(G1_GEN[0].to_bytes(48, "little") + G1_GEN[1].to_bytes(48, "little"), dtype=np.uint64).copy()
+    dk = ctx.upload_fr(rand_fr(rng, n), to_mont=False)
+    dp = ctx.dev_alloc(n * 96)
+    T.check(ctx.lib.tkm_g1_fixed_base_mul(ctx.h, G.ctypes.data, ctypes.c_void_p(dk), 0, n, ctypes.c_void_p(dp)))
+    ctx.dev_free(dk)
+    h = ctypes.c_void_p()
+    T.check(ctx.lib.tkm_crs_from_device(ctx.h, ctypes.c_void_p(dp), RS_X, RS_Y, 1, ctypes.byref(h)))
+    sigma = T.Sigma1.__new__(T.Sigma1)
+    sigma.ctx, sigma.h, sigma.rs_x, sigma.rs_y = ctx, h, RS_X, RS_Y
+    return sigma, dp
+
+
+if __name__ == "__main__":
+    ctx = T.Context(0)
+    ctx.init_ntt_domain_for_size(1 << 23)
+    sigma, table = make_sigma(ctx)
+    run(ctx, sigma, table)  # warm-up (allocator pools, kernel loads)
+    print(json.dumps(run(ctx, sigma, table)))

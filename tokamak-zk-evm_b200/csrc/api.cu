@@ -179,15 +179,17 @@ int32_t tkm_ctx_sync(tkm_ctx *ctx) {
 int32_t tkm_dev_alloc(tkm_ctx *ctx, size_t bytes, void **out_dev) {
   API_BEGIN
   TKM_REQUIRE(out_dev, "null out pointer");
-  cudaError_t e = cudaMalloc(out_dev, bytes ? bytes : 1);
-  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  // stream-ordered pool allocation (release threshold = infinity): no driver round trip after warm-up.  The
+  // stream is synchronised so the pointer is immediately usable from any stream.
+  cudaError_t e = cudaMallocAsync(out_dev, bytes ? bytes : 1, ctx->stream);
+  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
   return TKM_OK;
 }
 int32_t tkm_dev_free(tkm_ctx *ctx, void *dev) {
   API_BEGIN
   if (!dev) return TKM_OK;
-  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
-  TKM_CUDA(cudaFree(dev));
+  TKM_CUDA(cudaFreeAsync(dev, ctx->stream));
   return TKM_OK;
 }
 int32_t tkm_memcpy_h2d(tkm_ctx *ctx, void *dev, const void *host, size_t bytes) {

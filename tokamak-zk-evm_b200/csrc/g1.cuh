@@ -65,6 +65,44 @@ TKM_HD G1Xyzz g1_dbl(const G1Xyzz &p) {
   return r;
 }
 
+#if defined(__CUDACC__)
+// Latency-oriented doubling for the single-chain tails (Horner over windows): four lanes hold identical copies
+// of P and split the nine products into four dependency levels (2 + 2 + 4 + 1), exchanging results with
+// shuffles, so a doubling costs four product latencies instead of nine.  Every lane of the warp must call it
+// (groups are lanes {4g..4g+3}); all lanes return the full result.
+__device__ __forceinline__ Fq g1_bcast4(const Fq &v, int src_sub) {
+  Fq r;
+  const int src = (threadIdx.x & 28) + src_sub;  // lane id within the warp: (lane & ~3) + src_sub
+#pragma unroll
+  for (int i = 0; i < Fq::N; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src);
+  return r;
+}
+__device__ __forceinline__ G1Xyzz g1_dbl_coop4(const G1Xyzz &p) {
+  if (p.is_identity()) return p;  // replicas agree, so the whole group takes the same branch
+  const int sub = threadIdx.x & 3;
+  const Fq U = p.Y.dbl();
+  // level 1: V = U^2 | XX = X^2
+  Fq r1 = ((sub & 1) ? p.X : U).sqr();
+  const Fq V = g1_bcast4(r1, 0), XX = g1_bcast4(r1, 1);
+  // level 2: W = U*V | S = X*V
+  Fq r2 = ((sub & 1) ? p.X : U) * V;
+  const Fq W = g1_bcast4(r2, 0), S = g1_bcast4(r2, 1);
+  const Fq M = XX.dbl() + XX;
+  // level 3: M^2 | W*Y | V*ZZ | W*ZZZ
+  const Fq a3 = sub == 0 ? M : (sub == 2 ? V : W);
+  const Fq b3 = sub == 0 ? M : (sub == 1 ? p.Y : (sub == 2 ? p.ZZ : p.ZZZ));
+  Fq r3 = a3 * b3;
+  const Fq MM = g1_bcast4(r3, 0), WY = g1_bcast4(r3, 1);
+  G1Xyzz r;
+  r.ZZ = g1_bcast4(r3, 2);
+  r.ZZZ = g1_bcast4(r3, 3);
+  r.X = MM - S.dbl();
+  // level 4 (redundant on all lanes)
+  r.Y = M * (S - r.X) - WY;
+  return r;
+}
+#endif
+
 // acc += (x, y)  (madd-2008-s), all exceptional cases handled.
 TKM_HD void g1_madd(G1Xyzz &acc, const G1Affine &p) {
   if (p.is_identity()) return;

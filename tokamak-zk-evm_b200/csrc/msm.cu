@@ -312,13 +312,15 @@ __global__ void __launch_bounds__(32) k_final(const G1Xyzz *__restrict__ parts, 
     store_xyzz(window_sums + w, acc);
   }
   __syncthreads();
+  // Horner over windows: one dependency chain of W*c doublings.  Every lane carries a replica of the accumulator
+  // and groups of four lanes split each doubling's products (g1_dbl_coop4) to cut the chain latency.
+  G1Xyzz acc = G1Xyzz::identity();
+  for (int w = (int)m.W - 1; w >= 0; w--) {
+    for (uint32_t k = 0; k < m.c; k++) acc = g1_dbl_coop4(acc);
+    G1Xyzz s = load_xyzz(window_sums + w);
+    g1_add(acc, s);
+  }
   if (lane == 0) {
-    G1Xyzz acc = G1Xyzz::identity();
-    for (int w = (int)m.W - 1; w >= 0; w--) {
-      for (uint32_t k = 0; k < m.c; k++) acc = g1_dbl(acc);
-      G1Xyzz s = load_xyzz(window_sums + w);
-      g1_add(acc, s);
-    }
     G1Affine r = g1_to_affine(acc);
     if (out_mont) *out_mont = r;
     Fq x = r.x.from_mont(), y = r.y.from_mont();

@@ -189,7 +189,14 @@ int32_t vec_op(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, Fr *out, size_t n
     case TKM_OP_ADD: k_vec_op<TKM_OP_ADD><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
     case TKM_OP_SUB: k_vec_op<TKM_OP_SUB><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
     case TKM_OP_MUL: k_vec_op<TKM_OP_MUL><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
-    case TKM_OP_DIV: k_vec_op<TKM_OP_DIV><<<g, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case TKM_OP_DIV: {
+      // a / b = a * inv(b) with the batched inverse (one Fermat inverse per 8 elements) instead of one per element
+      Scratch<Fr> binv;
+      TKM_TRY(binv.alloc(ctx, n));
+      TKM_TRY(vec_inv(ctx, b, binv.p, n));
+      k_vec_op<TKM_OP_MUL><<<g, 256, 0, ctx->stream>>>(a, binv.p, out, n);
+      break;
+    }
     default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown vector op %d", op);
   }
   return launch_check(ctx, "k_vec_op");
