@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="developer override of the MSM size (the graded config is 22)")
     ap.add_argument("--skip-aux", action="store_true", help="skip the biNTT / cpu-baseline / e2e legs (profiling runs)")
+    ap.add_argument("--skip-replay", action="store_true", help="skip the prove-shaped operation replay leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -349,6 +350,22 @@ def main():
                                     "sample": f"first 2^{ls} points of the same inputs, oracle/oracle.c Pippenger (OpenMP); result compared bit-exactly with the GPU",
                                     "bintt": {"value": x2 * y2 / dt_ntt / 1e9, "unit": "Gelem/s", "sample": "4096x256 forward biNTT, oracle/oracle.c radix-2 (OpenMP)"},
                                     "published_reference": "ICICLE CPU backend: 1.01 Mpts/s at 8192x511 pts; biNTT 2^23 forward 497 ms (unnamed macOS host, BASELINE.md)"}
+    if rank == 0 and world == 1 and not args.skip_aux and not args.skip_replay:
+        # ---- operation replay of one prove at the reference's circuit shape: the third part of
+        # BASELINE.json's metric ("prove s/tx") restricted to the hot path that exists so far (no protocol driver yet)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import prove_replay
+
+        ctx.init_ntt_domain_for_size(1 << 23)
+        sigma, table = prove_replay.make_sigma(ctx)
+        prove_replay.run(ctx, sigma, table)  # warm-up
+        runs = [prove_replay.run(ctx, sigma, table) for _ in range(3)]
+        runs.sort(key=lambda o: o["hot_path_s"])
+        rep = runs[1]  # median of 3
+        rep["all_runs_hot_path_s"] = [round(o["hot_path_s"], 4) for o in runs]
+        rep.pop("detail_ms", None)
+        line["prove_replay"] = rep
+        sigma.close()
     if world > 1 and not args.skip_aux:
         # ---- row-sharded bivariate NTT with the X<->Y transpose as an NCCL all-to-all
         from tokamak_b200 import dist as D

@@ -84,6 +84,9 @@ int32_t tkm_fr_vec_fill(tkm_ctx *ctx, const uint8_t s32[32], void *dev_out, size
  * out[i*y_size + j] = in[i*y_size + j] * (omega_x^i - 1): PolyExpr::MulXMinusOne in the evaluation domain
  * (x_minus_one_evals, bivariate_polynomial/mod.rs:504-518) without materialising the factor matrix. */
 int32_t tkm_fr_mul_x_minus_one(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t x_size, size_t y_size);
+/* Exclusive suffix product out[i] = prod_{k>i} in[k], out[n-1] = 1: the recursion-polynomial scan of prove1
+ * (prove/src/lib.rs:1858-1867, a serial 2^20-step loop in the reference).  in may equal out. */
+int32_t tkm_fr_suffix_product(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
 /* VecOps::transpose (vector_operations/mod.rs:139,168): rows x cols -> cols x rows, out != in. */
 int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t rows, size_t cols);
 /* Host-buffer forms of the same ops (HostSlice in, HostSlice out; canonical bytes). */

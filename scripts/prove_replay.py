@@ -175,4 +175,8 @@ if __name__ == "__main__":
     ctx.init_ntt_domain_for_size(1 << 23)
     sigma, table = make_sigma(ctx)
     run(ctx, sigma, table)  # warm-up (allocator pools, kernel loads)
-    print(json.dumps(run(ctx, sigma, table)))
+    reps = int(os.environ.get("REPLAY_REPS", "1"))
+    outs = [run(ctx, sigma, table) for _ in range(reps)]
+    best = min(outs, key=lambda o: o["hot_path_s"])
+    best["all_runs_hot_path_s"] = [round(o["hot_path_s"], 4) for o in outs]
+    print(json.dumps(best))

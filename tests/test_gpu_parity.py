@@ -529,3 +529,41 @@ def test_div_by_vanishing_legacy_name(ctx, T):
     qx, qy = poly_from(T, ctx, a, x, y).div_by_vanishing(c, d)
     eqx, eqy = O.div_by_vanishing_opt(a, x, y, c, d)
     assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy)
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 4096, 100003, 1 << 20])
+def test_suffix_product_scan(ctx, n):
+    """prove1's recursion scan (prove/src/lib.rs:1858-1867): r[n-1] = 1, r[i] = r[i+1] * s[i+1]."""
+    import ctypes
+
+    a = O.random_fr(440 + (n % 97), n)
+    if n > 3:
+        a[n // 2] = frs([1])[0]
+    d = ctx.upload_fr(a)
+    T_ = __import__("tokamak_b200")
+    T_.check(ctx.lib.tkm_fr_suffix_product(ctx.h, ctypes.c_void_p(d), ctypes.c_void_p(d), n))
+    got = ctx.download_fr(d, n)
+    ctx.dev_free(d)
+    if n <= 4096:
+        ai = to_ints(a)
+        exp = [1] * n
+        for i in range(n - 2, -1, -1):
+            exp[i] = exp[i + 1] * ai[i + 1] % P.R_MOD
+        assert to_ints(got) == exp
+    else:
+        # identity check at full size: r[i] = r[i+1] * s[i+1] for every i, and the boundary value
+        assert to_ints(got[-1:]) == [1]
+        lhs = got[:-1]
+        rhs = O.fr_vec_op("mul", got[1:], a[1:])
+        assert np.array_equal(lhs, rhs)
+
+
+def test_div_by_ruffini_long_axis(ctx, T):
+    """Segmented Ruffini path (x >= 256) on the largest prover shape."""
+    x, y = 8192, 64
+    a = O.random_fr(450, x * y)
+    p = poly_from(T, ctx, a, x, y)
+    px, py = 0x123456789ABCDEF0123, 0xFEDCBA9876543210FED
+    qx, qy, r = p.div_by_ruffini(px, py)
+    eqx, eqy, er = O.div_by_ruffini(a, x, y, fr1(px), fr1(py))
+    assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy) and r == O.fr_to_int(er)

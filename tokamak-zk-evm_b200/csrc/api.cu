@@ -256,6 +256,11 @@ int32_t tkm_fr_mul_x_minus_one(tkm_ctx *ctx, const void *in, void *out, size_t x
   TKM_REQUIRE(in && out, "null argument");
   return vec_mul_x_minus_one(ctx, (const Fr *)in, (Fr *)out, x_size, y_size);
 }
+int32_t tkm_fr_suffix_product(tkm_ctx *ctx, const void *in, void *out, size_t n) {
+  API_BEGIN
+  TKM_REQUIRE((in && out) || n == 0, "null argument");
+  return vec_suffix_product(ctx, (const Fr *)in, (Fr *)out, n);
+}
 int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *in, void *out, size_t rows, size_t cols) {
   API_BEGIN
   TKM_REQUIRE(in && out, "null argument");

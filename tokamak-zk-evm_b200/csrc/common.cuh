@@ -121,6 +121,7 @@ int32_t vec_op(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, Fr *out, size_t n
 int32_t vec_scale(tkm_ctx *ctx, const Fr &s, const Fr *a, Fr *out, size_t n);
 int32_t vec_inv(tkm_ctx *ctx, const Fr *a, Fr *out, size_t n);
 int32_t vec_fill(tkm_ctx *ctx, const Fr &s, Fr *out, size_t n);
+int32_t vec_suffix_product(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n);
 int32_t vec_mul_x_minus_one(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x_size, size_t y_size);
 int32_t vec_transpose(tkm_ctx *ctx, const Fr *in, Fr *out, size_t rows, size_t cols);
 int32_t bintt_dev(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x, size_t y, int dir, const Fr *coset_x,

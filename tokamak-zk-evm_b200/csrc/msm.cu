@@ -21,6 +21,8 @@
 // Integer-pipe bound: N*W mixed additions of ~10 Fq products each; no tensor cores.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tkm {
@@ -390,7 +392,8 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
   TKM_TRY(launch_check(ctx, "k_fill_identity"));
 
   // chunk length: long enough to amortise the two partial slots per thread, short enough to fill the GPU
-  uint32_t chunk = 128;
+  uint32_t chunk = 256;  // 2 partial-list entries per chunk: longer chunks shrink the segmented-reduction levels
+  if (const char *e = getenv("TKM_MSM_CHUNK")) chunk = (uint32_t)atoi(e);  // developer knob
   while (chunk > 8 && (M / chunk) < (size_t)ctx->sm_count * 4 * ACC_THREADS / 2) chunk >>= 1;
   const size_t T = (M + chunk - 1) / chunk;
   size_t P = 2 * T;

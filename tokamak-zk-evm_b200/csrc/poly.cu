@@ -194,6 +194,53 @@ __global__ void __launch_bounds__(128) k_ruffini_x(Fr *__restrict__ qx, Fr *__re
   Fr v0 = p[j];
   rx[j] = v0 + b * pt;
 }
+// Segmented form for long X axes: the chain b_i = p_i + b_{i+1}*x is split into segments of `seg` rows.
+//   pass 1 (thread per (segment, column)): local Horner value of the segment with zero incoming carry
+//   pass 2 (thread per column): carry into every segment, top down: in_s = c_{s+1} + in_{s+1} * x^seg
+//   pass 3 (thread per (segment, column)): re-run the segment with its carry and write the quotient rows
+__global__ void __launch_bounds__(128) k_ruffini_seg_local(Fr *__restrict__ segc, const Fr *__restrict__ p, size_t x_size, size_t y_size,
+                                                         size_t seg, Fr pt) {
+  size_t nseg = x_size / seg;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= nseg * y_size) return;
+  size_t s = t / y_size, j = t % y_size;
+  Fr c = Fr::zero();
+  for (size_t k = seg; k-- > 0;) {
+    Fr v = p[(s * seg + k) * y_size + j];
+    c = v + c * pt;
+  }
+  segc[t] = c;
+}
+__global__ void __launch_bounds__(128) k_ruffini_seg_carry(Fr *__restrict__ carry, const Fr *__restrict__ segc, size_t nseg, size_t y_size,
+                                                         Fr pt_pow_seg) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= y_size) return;
+  Fr in = Fr::zero();
+  carry[(nseg - 1) * y_size + j] = in;
+  for (size_t s = nseg - 1; s-- > 0;) {
+    Fr c = segc[(s + 1) * y_size + j];
+    in = c + in * pt_pow_seg;
+    carry[s * y_size + j] = in;
+  }
+}
+__global__ void __launch_bounds__(128) k_ruffini_seg_apply(Fr *__restrict__ qx, Fr *__restrict__ rx, const Fr *__restrict__ p,
+                                                         const Fr *__restrict__ carry, size_t x_size, size_t y_size, size_t seg, Fr pt) {
+  size_t nseg = x_size / seg;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= nseg * y_size) return;
+  size_t s = t / y_size, j = t % y_size;
+  Fr b = carry[t];
+  if (s == nseg - 1) qx[(x_size - 1) * y_size + j] = Fr::zero();
+  for (size_t k = seg; k-- > 0;) {
+    size_t i = s * seg + k;
+    Fr v = p[i * y_size + j];
+    b = v + b * pt;
+    if (i >= 1)
+      qx[(i - 1) * y_size + j] = b;
+    else
+      rx[j] = b;
+  }
+}
 // Single chain along Y on the remainders: qy[0..y_size), r.
 __global__ void k_ruffini_y(Fr *__restrict__ qy, Fr *__restrict__ r, const Fr *__restrict__ rx, size_t y_size, Fr pt) {
   if (threadIdx.x || blockIdx.x) return;
@@ -640,8 +687,27 @@ int32_t tkm_poly_div_by_ruffini(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x
   TKM_TRY(r.alloc(ctx, 1));
   TKM_TRY(poly_alloc(ctx, x, y, &qx));
   int32_t st = poly_alloc(ctx, 1, y, &qy);
-  if (st == TKM_OK) {
-    k_ruffini_x<<<(unsigned)((y + 127) / 128), 128, 0, ctx->stream>>>(qx->d, rx.p, p->d, x, y, fr_from_bytes_host(x32));
+  const Fr ptx = fr_from_bytes_host(x32);
+  const size_t seg = 64;
+  if (st == TKM_OK && x >= 4 * seg) {
+    const size_t nseg = x / seg;
+    Scratch<Fr> segc, carry;
+    st = segc.alloc(ctx, nseg * y);
+    if (st == TKM_OK) st = carry.alloc(ctx, nseg * y);
+    if (st == TKM_OK) {
+      k_ruffini_seg_local<<<(unsigned)((nseg * y + 127) / 128), 128, 0, ctx->stream>>>(segc.p, p->d, x, y, seg, ptx);
+      st = launch_check(ctx, "k_ruffini_seg_local");
+    }
+    if (st == TKM_OK) {
+      k_ruffini_seg_carry<<<(unsigned)((y + 127) / 128), 128, 0, ctx->stream>>>(carry.p, segc.p, nseg, y, ptx.pow_u64(seg));
+      st = launch_check(ctx, "k_ruffini_seg_carry");
+    }
+    if (st == TKM_OK) {
+      k_ruffini_seg_apply<<<(unsigned)((nseg * y + 127) / 128), 128, 0, ctx->stream>>>(qx->d, rx.p, p->d, carry.p, x, y, seg, ptx);
+      st = launch_check(ctx, "k_ruffini_seg_apply");
+    }
+  } else if (st == TKM_OK) {
+    k_ruffini_x<<<(unsigned)((y + 127) / 128), 128, 0, ctx->stream>>>(qx->d, rx.p, p->d, x, y, ptx);
     st = launch_check(ctx, "k_ruffini_x");
   }
   if (st == TKM_OK) {

@@ -147,6 +147,61 @@ __global__ void __launch_bounds__(256) k_transpose(const Fr *__restrict__ in, Fr
   }
 }
 
+// Exclusive suffix product out[i] = prod_{k > i} in[k] (out[n-1] = 1): the recursion polynomial's evaluations
+// in prove1 (prove/src/lib.rs:1858-1867 computes it with a serial loop over 2^20 elements).
+// Chunked three-phase scan: per-chunk products, recursive scan of the chunk products, per-chunk apply.
+constexpr size_t SCAN_CHUNK = 64;
+__global__ void __launch_bounds__(128) k_scan_chunk_products(const Fr *__restrict__ in, Fr *__restrict__ cp, size_t n) {
+  size_t nchunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  size_t lo = t * SCAN_CHUNK, hi = lo + SCAN_CHUNK;
+  if (hi > n) hi = n;
+  Fr acc = Fr::one();
+  for (size_t i = lo; i < hi; i++) {
+    Fr v = in[i];
+    acc = acc * v;
+  }
+  cp[t] = acc;
+}
+__global__ void __launch_bounds__(128) k_scan_apply(const Fr *__restrict__ in, const Fr *__restrict__ cs, Fr *__restrict__ out, size_t n) {
+  size_t nchunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  size_t lo = t * SCAN_CHUNK, hi = lo + SCAN_CHUNK;
+  if (hi > n) hi = n;
+  Fr acc = cs[t];
+  for (size_t i = hi; i-- > lo;) {
+    Fr v = in[i];  // read before the write: in == out is allowed
+    out[i] = acc;
+    acc = acc * v;
+  }
+}
+__global__ void k_scan_serial(const Fr *__restrict__ in, Fr *__restrict__ out, size_t n) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr acc = Fr::one();
+  for (size_t i = n; i-- > 0;) {
+    Fr v = in[i];
+    out[i] = acc;
+    acc = acc * v;
+  }
+}
+int32_t vec_suffix_product(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  if (n <= 256) {
+    k_scan_serial<<<1, 32, 0, ctx->stream>>>(in, out, n);
+    return launch_check(ctx, "k_scan_serial");
+  }
+  size_t nchunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  Scratch<Fr> cp;
+  TKM_TRY(cp.alloc(ctx, nchunks));
+  k_scan_chunk_products<<<(unsigned)((nchunks + 127) / 128), 128, 0, ctx->stream>>>(in, cp.p, n);
+  TKM_TRY(launch_check(ctx, "k_scan_chunk_products"));
+  TKM_TRY(vec_suffix_product(ctx, cp.p, cp.p, nchunks));
+  k_scan_apply<<<(unsigned)((nchunks + 127) / 128), 128, 0, ctx->stream>>>(in, cp.p, out, n);
+  return launch_check(ctx, "k_scan_apply");
+}
+
 int32_t vec_fill(tkm_ctx *ctx, const Fr &s, Fr *out, size_t n) {
   if (n == 0) return TKM_OK;
   k_vec_fill<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(s, out, n);

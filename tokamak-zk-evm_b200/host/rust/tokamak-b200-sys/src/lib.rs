@@ -37,6 +37,7 @@ extern "C" {
     pub fn tkm_fr_vec_inv(ctx: *mut tkm_ctx, a: *const c_void, out: *mut c_void, n: usize) -> i32;
     pub fn tkm_fr_vec_fill(ctx: *mut tkm_ctx, s32: *const u8, dev_out: *mut c_void, n: usize) -> i32;
     pub fn tkm_fr_mul_x_minus_one(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize) -> i32;
+    pub fn tkm_fr_suffix_product(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, n: usize) -> i32;
     pub fn tkm_fr_transpose(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, rows: usize, cols: usize) -> i32;
     pub fn tkm_fr_vec_op_host(ctx: *mut tkm_ctx, op: i32, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> i32;
     pub fn tkm_bintt(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize, dir: i32,
