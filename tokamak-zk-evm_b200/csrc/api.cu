@@ -75,15 +75,16 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
     uint32_t r = 0;
     for (int i = 0; i < 8; i++) r ^= a[i];
     if (r == 0x12345678u) sink[0] = r;
-  } else if (KIND == 1) {  // 8 independent IMAD.WIDE chains
-    uint64_t a[8];
-    for (int i = 0; i < 8; i++) a[i] = t + i;
-    uint32_t m = t | 1u;
-    for (int it = 0; it < iters; it++)
+  } else if (KIND == 1) {  // 16 independent mad.wide.u32 accumulators per thread: the IMAD.WIDE issue limit of the fmaheavy pipe
+    uint64_t a[16];
+    for (int i = 0; i < 16; i++) a[i] = (uint64_t)t * (i + 3);
+    uint32_t m = t | 1u, q = (t * 2654435761u) | 3u;
+    for (int it = 0; it < iters; it++) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) a[i] = (uint64_t)(uint32_t)a[i] * m + a[i];
+      for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(m), "r"(q));
+    }
     uint64_t r = 0;
-    for (int i = 0; i < 8; i++) r ^= a[i];
+    for (int i = 0; i < 16; i++) r ^= a[i];
     if (r == 0x12345678u) sink[0] = (uint32_t)r;
   } else if (KIND == 2) {
     Fr x = Fr::one(), y = Fr::r2();
@@ -507,7 +508,7 @@ int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
     TKM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     switch (kind) {
       case 0: iters = 4096; ops_per_iter = 8; k_microbench<0><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
-      case 1: iters = 4096; ops_per_iter = 8; k_microbench<1><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 1: iters = 4096; ops_per_iter = 16; k_microbench<1><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 2: iters = 512; ops_per_iter = 2; k_microbench<2><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 3: iters = 256; ops_per_iter = 2; k_microbench<3><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 4: iters = 64; ops_per_iter = 1; k_microbench<4><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;

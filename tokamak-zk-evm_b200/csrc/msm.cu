@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(32) k_final(const G1Xyzz *__restrict__ parts, 
     G1Xyzz s = load_xyzz(window_sums + w);
     g1_add(acc, s);
   }
+  G1Affine r = g1_to_affine_coop(acc);
   if (lane == 0) {
-    G1Affine r = g1_to_affine(acc);
     if (out_mont) *out_mont = r;
     Fq x = r.x.from_mont(), y = r.y.from_mont();
     for (int i = 0; i < 12; i++) {
