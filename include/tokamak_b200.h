@@ -87,6 +87,12 @@ int32_t tkm_fr_mul_x_minus_one(tkm_ctx *ctx, const void *dev_in, void *dev_out, 
 /* Exclusive suffix product out[i] = prod_{k>i} in[k], out[n-1] = 1: the recursion-polynomial scan of prove1
  * (prove/src/lib.rs:1858-1867, a serial 2^20-step loop in the reference).  in may equal out. */
 int32_t tkm_fr_suffix_product(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
+/* Reductions to one host scalar (32-byte canonical): op 0 = VecOps::sum (vector_operations/mod.rs:124,336),
+ * op 1 = VecOps::product (prove/src/lib.rs:1005-1016), op 2 = inner_product_two_vecs sum_k a[k]*b[k]
+ * (vector_operations/mod.rs:100-141; dev_b ignored for ops 0/1). */
+int32_t tkm_fr_vec_reduce(tkm_ctx *ctx, int32_t op, const void *dev_a, const void *dev_b, size_t n, uint8_t out32[32]);
+/* outer_product_two_vecs (vector_operations/mod.rs:551-600): out[i*cols + j] = col[i] * row[j]. */
+int32_t tkm_fr_outer_product(tkm_ctx *ctx, const void *dev_col, const void *dev_row, void *dev_out, size_t rows, size_t cols);
 /* VecOps::transpose (vector_operations/mod.rs:139,168): rows x cols -> cols x rows, out != in. */
 int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t rows, size_t cols);
 /* Host-buffer forms of the same ops (HostSlice in, HostSlice out; canonical bytes). */

@@ -567,3 +567,34 @@ def test_div_by_ruffini_long_axis(ctx, T):
     qx, qy, r = p.div_by_ruffini(px, py)
     eqx, eqy, er = O.div_by_ruffini(a, x, y, fr1(px), fr1(py))
     assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy) and r == O.fr_to_int(er)
+
+
+def test_vector_operations_module(ctx, T):
+    """libs/src/vector_operations helpers by their reference names (tests.rs:1487-1524,1595-1622)."""
+    from tokamak_b200 import vector_operations as V
+
+    n = 1000
+    a, b = O.random_fr(460, n), O.random_fr(461, n)
+    ai, bi = to_ints(a), to_ints(b)
+    assert np.array_equal(V.point_mul_two_vecs(ctx, a, b), O.fr_vec_op("mul", a, b))
+    assert np.array_equal(V.point_add_two_vecs(ctx, a, b), O.fr_vec_op("add", a, b))
+    assert np.array_equal(V.point_div_two_vecs(ctx, a, b), O.fr_vec_op("mul", a, O.fr_vec_inv(b)))
+    s = 0xABCDEF123456789
+    assert to_ints(V.scale_vec(ctx, s, a)) == [s * u % P.R_MOD for u in ai]
+    assert to_ints(V.scalar_vec_add(ctx, s, a)) == [(s + u) % P.R_MOD for u in ai]
+    assert to_ints(V.scalar_vec_sub(ctx, s, a)) == [(s - u) % P.R_MOD for u in ai]
+    assert V.inner_product_two_vecs(ctx, a, b) == O.fr_to_int(O.fr_inner_product(a, b))
+    assert V.vec_sum(ctx, a) == sum(ai) % P.R_MOD
+    prod = 1
+    for u in ai[:300]:
+        prod = prod * u % P.R_MOD
+    assert V.vec_product(ctx, a[:300]) == prod
+    op = V.outer_product_two_vecs(ctx, a[:13], b[:7])
+    assert to_ints(op) == [ai[i] * bi[j] % P.R_MOD for i in range(13) for j in range(7)]
+    tr = V.transpose_inplace(ctx, a[:15 * 20], 15, 20)
+    assert np.array_equal(tr.reshape(20, 15, 4), a[:300].reshape(15, 20, 4).transpose(1, 0, 2))
+    val = 0x1234567
+    lag = V.gen_evaled_lagrange_bases(ctx, val, 64)
+    assert to_ints(lag) == P.ntt([pow(val, i, P.R_MOD) for i in range(64)], inverse=True)
+    assert to_ints(V.extend_monomial_vec(ctx, frs([1, 5, 25]), 6)) == [1, 5, 25, 125, 625, 3125]
+    assert to_ints(V.resize(frs(list(range(6))), 2, 3, 3, 2)) == [0, 1, 3, 4, 0, 0]

@@ -262,6 +262,21 @@ int32_t tkm_fr_suffix_product(tkm_ctx *ctx, const void *in, void *out, size_t n)
   TKM_REQUIRE((in && out) || n == 0, "null argument");
   return vec_suffix_product(ctx, (const Fr *)in, (Fr *)out, n);
 }
+int32_t tkm_fr_vec_reduce(tkm_ctx *ctx, int32_t op, const void *a, const void *b, size_t n, uint8_t out32[32]) {
+  API_BEGIN
+  TKM_REQUIRE(out32 && (a || n == 0), "null argument");
+  TKM_REQUIRE(op >= 0 && op <= 2, "unknown reduction %d", op);
+  TKM_REQUIRE(op != 2 || b || n == 0, "inner product needs two vectors");
+  Fr r;
+  TKM_TRY(vec_reduce(ctx, op, (const Fr *)a, (const Fr *)b, n, &r));
+  fr_to_bytes_host(r, out32);
+  return TKM_OK;
+}
+int32_t tkm_fr_outer_product(tkm_ctx *ctx, const void *col, const void *row, void *out, size_t rows, size_t cols) {
+  API_BEGIN
+  TKM_REQUIRE((col && row && out) || rows * cols == 0, "null argument");
+  return vec_outer_product(ctx, (const Fr *)col, (const Fr *)row, (Fr *)out, rows, cols);
+}
 int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *in, void *out, size_t rows, size_t cols) {
   API_BEGIN
   TKM_REQUIRE(in && out, "null argument");

@@ -121,6 +121,8 @@ int32_t vec_op(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, Fr *out, size_t n
 int32_t vec_scale(tkm_ctx *ctx, const Fr &s, const Fr *a, Fr *out, size_t n);
 int32_t vec_inv(tkm_ctx *ctx, const Fr *a, Fr *out, size_t n);
 int32_t vec_fill(tkm_ctx *ctx, const Fr &s, Fr *out, size_t n);
+int32_t vec_reduce(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, size_t n, Fr *host_out);
+int32_t vec_outer_product(tkm_ctx *ctx, const Fr *col, const Fr *row, Fr *out, size_t rows, size_t cols);
 int32_t vec_suffix_product(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n);
 int32_t vec_mul_x_minus_one(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x_size, size_t y_size);
 int32_t vec_transpose(tkm_ctx *ctx, const Fr *in, Fr *out, size_t rows, size_t cols);

@@ -57,7 +57,9 @@ static MsmGeom pick_geom(size_t n) {
   m.logB = bc - 1;
   m.B = 1u << m.logB;
   m.nbuckets = m.W * m.B;
-  m.logg = m.logB < 4 ? m.logB : 4;
+  uint32_t want_logg = n < ((size_t)1 << 18) ? 3 : 4;  // segment length 8 / 16 (measured: shorter chains win when few buckets)
+  if (const char *e = getenv("TKM_MSM_LOGG")) want_logg = (uint32_t)atoi(e);  // developer knob
+  m.logg = m.logB < want_logg ? m.logB : want_logg;
   m.g = 1u << m.logg;
   m.nseg = m.B >> m.logg;
   m.nbits = m.logB - m.logg;

@@ -202,6 +202,61 @@ int32_t vec_suffix_product(tkm_ctx *ctx, const Fr *in, Fr *out, size_t n) {
   return launch_check(ctx, "k_scan_apply");
 }
 
+// ---- reductions: VecOps::sum / VecOps::product (vector_operations/mod.rs:124,336; prove/src/lib.rs:1005-1016) and
+// inner_product_two_vecs (vector_operations/mod.rs:100-141).  Grid-stride partials, warp shuffle tree, one partial per warp,
+// then the same kernel reduces the partials.
+template <int OP>  // 0 = sum(a), 1 = product(a), 2 = sum(a*b)
+__global__ void __launch_bounds__(256) k_reduce(const Fr *__restrict__ a, const Fr *__restrict__ b, size_t n, Fr *__restrict__ partial) {
+  Fr acc = (OP == 1) ? Fr::one() : Fr::zero();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v = a[i];
+    if (OP == 2) { Fr w = b[i]; v = v * w; }
+    acc = (OP == 1) ? acc * v : acc + v;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    Fr o;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o.v[k] = __shfl_xor_sync(0xffffffffu, acc.v[k], d);
+    acc = (OP == 1) ? acc * o : acc + o;
+  }
+  if ((threadIdx.x & 31) == 0) partial[(blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5] = acc;
+}
+int32_t vec_reduce(tkm_ctx *ctx, int op, const Fr *a, const Fr *b, size_t n, Fr *host_out) {
+  if (n == 0) {
+    *host_out = (op == 1) ? Fr::one() : Fr::zero();
+    return TKM_OK;
+  }
+  unsigned blocks = grid_for(n, 256, ctx->sm_count, 2);
+  size_t nwarps = (size_t)blocks * 8;
+  Scratch<Fr> p1, p2;
+  TKM_TRY(p1.alloc(ctx, nwarps));
+  TKM_TRY(p2.alloc(ctx, 8));
+  if (op == 0) k_reduce<0><<<blocks, 256, 0, ctx->stream>>>(a, nullptr, n, p1.p);
+  else if (op == 1) k_reduce<1><<<blocks, 256, 0, ctx->stream>>>(a, nullptr, n, p1.p);
+  else k_reduce<2><<<blocks, 256, 0, ctx->stream>>>(a, b, n, p1.p);
+  TKM_TRY(launch_check(ctx, "k_reduce"));
+  if (op == 1) k_reduce<1><<<1, 32, 0, ctx->stream>>>(p1.p, nullptr, nwarps, p2.p);
+  else k_reduce<0><<<1, 32, 0, ctx->stream>>>(p1.p, nullptr, nwarps, p2.p);
+  TKM_TRY(launch_check(ctx, "k_reduce"));
+  TKM_CUDA(cudaMemcpyAsync(host_out, p2.p, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+// outer_product_two_vecs (vector_operations/mod.rs:551-600): out[i*cols + j] = col[i] * row[j]
+__global__ void __launch_bounds__(256) k_outer_product(const Fr *__restrict__ col, const Fr *__restrict__ row, Fr *__restrict__ out, size_t rows,
+                                                       size_t cols) {
+  size_t total = rows * cols;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    Fr u = col[k / cols], v = row[k % cols];
+    out[k] = u * v;
+  }
+}
+int32_t vec_outer_product(tkm_ctx *ctx, const Fr *col, const Fr *row, Fr *out, size_t rows, size_t cols) {
+  if (rows * cols == 0) return TKM_OK;
+  k_outer_product<<<grid_for(rows * cols, 256, ctx->sm_count), 256, 0, ctx->stream>>>(col, row, out, rows, cols);
+  return launch_check(ctx, "k_outer_product");
+}
+
 int32_t vec_fill(tkm_ctx *ctx, const Fr &s, Fr *out, size_t n) {
   if (n == 0) return TKM_OK;
   k_vec_fill<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(s, out, n);

@@ -38,6 +38,8 @@ extern "C" {
     pub fn tkm_fr_vec_fill(ctx: *mut tkm_ctx, s32: *const u8, dev_out: *mut c_void, n: usize) -> i32;
     pub fn tkm_fr_mul_x_minus_one(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize) -> i32;
     pub fn tkm_fr_suffix_product(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, n: usize) -> i32;
+    pub fn tkm_fr_vec_reduce(ctx: *mut tkm_ctx, op: i32, dev_a: *const c_void, dev_b: *const c_void, n: usize, out32: *mut u8) -> i32;
+    pub fn tkm_fr_outer_product(ctx: *mut tkm_ctx, dev_col: *const c_void, dev_row: *const c_void, dev_out: *mut c_void, rows: usize, cols: usize) -> i32;
     pub fn tkm_fr_transpose(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, rows: usize, cols: usize) -> i32;
     pub fn tkm_fr_vec_op_host(ctx: *mut tkm_ctx, op: i32, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> i32;
     pub fn tkm_bintt(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize, dir: i32,
