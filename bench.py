@@ -213,10 +213,7 @@ def main():
         dist.all_gather(out, t)
         if rank != 0:
             return partial
-        acc = out[0].cpu().numpy().view(np.uint64)
-        for o in out[1:]:
-            acc = ctx.g1_add(acc, o.cpu().numpy().view(np.uint64))
-        return acc
+        return ctx.g1_sum(torch.stack(out).cpu().numpy().view(np.uint64))
 
     def step_resident():
         return combine(ctx.msm_g1_dev(d_scalars, False, d_bases, n))

@@ -140,6 +140,8 @@ int32_t tkm_g1_fixed_base_mul(tkm_ctx *ctx, const uint8_t base96[96], const void
 /* G1serde ops (group_structures/mod.rs:895-947): out = a + b ; out = k * a.  Host bytes. */
 int32_t tkm_g1_add(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t b96[96], uint8_t out96[96]);
 int32_t tkm_g1_mul(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t k32[32], uint8_t out96[96]);
+/* Sum of n affine points (host bytes): combines the per-GPU partial sums of a point-range-sharded MSM in one launch. */
+int32_t tkm_g1_sum(tkm_ctx *ctx, const uint8_t *points96, size_t n, uint8_t out96[96]);
 
 /* ---- CRS tables: Sigma1.xy_powers and friends (libs/src/group_structures/mod.rs:361-394;
  *      archived form iotools/mod.rs:1701-1783) ------------------------------------------------------- */

@@ -598,3 +598,14 @@ def test_vector_operations_module(ctx, T):
     assert to_ints(lag) == P.ntt([pow(val, i, P.R_MOD) for i in range(64)], inverse=True)
     assert to_ints(V.extend_monomial_vec(ctx, frs([1, 5, 25]), 6)) == [1, 5, 25, 125, 625, 3125]
     assert to_ints(V.resize(frs(list(range(6))), 2, 3, 3, 2)) == [0, 1, 3, 4, 0, 0]
+
+
+def test_g1_sum(ctx):
+    pts = [P.g1_mul(P.G1_GEN, k) for k in (3, 5, 7, 11)]
+    arr = g1s(pts + [None, pts[0], P.g1_neg(pts[1])])
+    exp = None
+    for p in pts + [None, pts[0], P.g1_neg(pts[1])]:
+        exp = P.g1_add(exp, p)
+    assert g1_tuple(ctx.g1_sum(arr)) == exp
+    assert g1_tuple(ctx.g1_sum(g1s([pts[2], P.g1_neg(pts[2])]))) is None
+    assert g1_tuple(ctx.g1_sum(np.zeros((0, 12), dtype=np.uint64))) is None

@@ -21,6 +21,23 @@ __global__ void k_g1_add_single(const G1Affine *a, const G1Affine *b, uint32_t *
   for (int i = 0; i < 12; i++) { out_canonical[i] = x.v[i]; out_canonical[12 + i] = y.v[i]; }
 }
 
+// Sum of n canonical affine points (partial sums of the point-range shards): one warp, every lane
+// carries a replica so the final inversion can use the cooperative two-lane ladder.
+__global__ void __launch_bounds__(32) k_g1_sum_canonical(const G1Affine *pts, size_t n, uint32_t *out_canonical) {
+  G1Xyzz acc = G1Xyzz::identity();
+  for (size_t i = 0; i < n; i++) {
+    G1Affine p = pts[i];
+    p.x = p.x.to_mont();
+    p.y = p.y.to_mont();
+    g1_madd(acc, p);
+  }
+  G1Affine r = g1_to_affine_coop(acc);
+  if (threadIdx.x == 0) {
+    Fq x = r.x.from_mont(), y = r.y.from_mont();
+    for (int i = 0; i < 12; i++) { out_canonical[i] = x.v[i]; out_canonical[12 + i] = y.v[i]; }
+  }
+}
+
 // out[i] = k_i * base for n scalars: 4-bit fixed windows over a 64 x 15 table of affine multiples held in
 // global memory (built by one small kernel), one thread per scalar, then a batched conversion to affine.
 constexpr int FB_WINDOWS = 64;
@@ -424,6 +441,25 @@ int32_t tkm_g1_add(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t b96[96], u
   TKM_CUDA(cudaMemcpyAsync(d.p + 1, b96, 96, cudaMemcpyHostToDevice, ctx->stream));
   k_g1_add_single<<<1, 32, 0, ctx->stream>>>(d.p, d.p + 1, r.p);
   TKM_TRY(launch_check(ctx, "k_g1_add_single"));
+  TKM_CUDA(cudaMemcpyAsync(out96, r.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+int32_t tkm_g1_sum(tkm_ctx *ctx, const uint8_t *points96, size_t n, uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(out96 && (points96 || n == 0), "null argument");
+  if (n == 0) {
+    memset(out96, 0, 96);
+    return TKM_OK;
+  }
+  Scratch<G1Affine> d;
+  Scratch<uint32_t> r;
+  TKM_TRY(d.alloc(ctx, n));
+  TKM_TRY(r.alloc(ctx, 24));
+  TKM_CUDA(cudaMemcpyAsync(d.p, points96, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  k_g1_sum_canonical<<<1, 32, 0, ctx->stream>>>(d.p, n, r.p);
+  TKM_TRY(launch_check(ctx, "k_g1_sum_canonical"));
   TKM_CUDA(cudaMemcpyAsync(out96, r.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
   TKM_CUDA(cudaStreamSynchronize(ctx->stream));
   return TKM_OK;

@@ -59,6 +59,7 @@ extern "C" {
     pub fn tkm_g1_fixed_base_mul(ctx: *mut tkm_ctx, base96: *const u8, dev_scalars: *const c_void, scalars_mont: i32, n: usize,
                                  dev_out_affine: *mut c_void) -> i32;
     pub fn tkm_g1_add(ctx: *mut tkm_ctx, a96: *const u8, b96: *const u8, out96: *mut u8) -> i32;
+    pub fn tkm_g1_sum(ctx: *mut tkm_ctx, points96: *const u8, n: usize, out96: *mut u8) -> i32;
     pub fn tkm_g1_mul(ctx: *mut tkm_ctx, a96: *const u8, k32: *const u8, out96: *mut u8) -> i32;
     pub fn tkm_crs_upload(ctx: *mut tkm_ctx, points96: *const u8, rows: usize, cols: usize, out: *mut *mut tkm_crs) -> i32;
     pub fn tkm_crs_from_device(ctx: *mut tkm_ctx, dev_points: *mut c_void, rows: usize, cols: usize, take_ownership: i32,

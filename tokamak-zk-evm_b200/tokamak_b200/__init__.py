@@ -243,6 +243,13 @@ class Context:
         check(self.lib.tkm_g1_add(self.h, _vp(a), _vp(b), _vp(out)))
         return out
 
+    def g1_sum(self, points):
+        """Sum of affine points (n x 12 u64, canonical): one launch, used to combine sharded MSM partial sums."""
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.lib.tkm_g1_sum(self.h, _vp(pts), pts.shape[0], _vp(out)))
+        return out
+
     def g1_mul(self, a, k):
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(12)
         kk, pk = fr_bytes(k)

@@ -39,6 +39,9 @@ class CudaLocalOps:
     def g1_add(self, a, b):
         return self.ctx.g1_add(a, b)
 
+    def g1_sum(self, points):
+        return self.ctx.g1_sum(points)
+
 
 def shard_range(total, world, rank):
     """Contiguous point / row range of `rank`: sizes differ by at most one (ragged totals allowed)."""
@@ -61,9 +64,12 @@ def msm_sharded(ops, scalars_t, bases_t, n_local, group=None):
     dist.all_gather(gathered, t, group=group)
     if rank != 0:
         return part
-    acc = gathered[0].cpu().numpy().view(np.uint64)
-    for g in gathered[1:]:
-        acc = ops.g1_add(acc, g.cpu().numpy().view(np.uint64))
+    parts = torch.stack(gathered).cpu().numpy().view(np.uint64)
+    if hasattr(ops, "g1_sum"):
+        return ops.g1_sum(parts)  # one launch for the G-1 additions and the affine conversion
+    acc = parts[0]
+    for g in parts[1:]:
+        acc = ops.g1_add(acc, g)
     return acc
 
 

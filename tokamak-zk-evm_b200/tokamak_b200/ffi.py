@@ -50,6 +50,7 @@ SIGNATURES = {
     "tkm_g1_fixed_base_mul": [c_void_p, c_void_p, c_void_p, c_int32, c_size_t, c_void_p],
     "tkm_g1_add": [c_void_p, c_void_p, c_void_p, c_void_p],
     "tkm_g1_mul": [c_void_p, c_void_p, c_void_p, c_void_p],
+    "tkm_g1_sum": [c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_crs_upload": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_crs_from_device": [c_void_p, c_void_p, c_size_t, c_size_t, c_int32, P(c_void_p)],
     "tkm_crs_free": [c_void_p, c_void_p],
