@@ -150,6 +150,10 @@ int32_t tkm_crs_upload(tkm_ctx *ctx, const uint8_t *points96, size_t rows, size_
 /* Wrap points already on the device in canonical form (converted in place to Montgomery). */
 int32_t tkm_crs_from_device(tkm_ctx *ctx, void *dev_points, size_t rows, size_t cols, int32_t take_ownership,
                             tkm_crs **out);
+/* Optional, for provers that keep one CRS across many proofs: build fixed-base tables 2^(c*w) * P for every CRS point
+ * (W = ceil(256/c) tables, e.g. 13 x 384 MiB at c = 20).  tkm_poly_commit then folds all digit windows into one shared
+ * bucket set: fewer additions per point, no per-window reduction, no Horner tail.  Results are identical. */
+int32_t tkm_crs_precompute(tkm_ctx *ctx, tkm_crs *crs, uint32_t window_bits);
 int32_t tkm_crs_free(tkm_ctx *ctx, tkm_crs *crs);
 int32_t tkm_crs_device_ptr(tkm_crs *crs, void **out_dev, size_t *rows, size_t *cols);
 

@@ -174,6 +174,12 @@ if __name__ == "__main__":
     ctx = T.Context(0)
     ctx.init_ntt_domain_for_size(1 << 23)
     sigma, table = make_sigma(ctx)
+    pre_c = int(os.environ.get("REPLAY_PRECOMPUTE", "0"))
+    if pre_c:
+        t0 = time.perf_counter()
+        sigma.precompute(pre_c)
+        ctx.sync()
+        print(f"fixed-base tables c={pre_c}: {time.perf_counter() - t0:.3f} s", file=sys.stderr)
     run(ctx, sigma, table)  # warm-up (allocator pools, kernel loads)
     reps = int(os.environ.get("REPLAY_REPS", "1"))
     outs = [run(ctx, sigma, table) for _ in range(reps)]

@@ -61,6 +61,7 @@ tot = D.msm_sharded(ops, d_s, d_b, hi - lo)
 if rank == 0:
     assert np.array_equal(tot, O.msm_g1(ss, pts)), "sharded MSM total"
 dist.barrier()
-print(f"rank {rank} of {world} ok", flush=True)
+sys.stdout.write(f"rank{rank}of{world}ok\n")  # one write call: no interleaving between ranks
+sys.stdout.flush()
 ctx.close()
 dist.destroy_process_group()

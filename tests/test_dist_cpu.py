@@ -64,7 +64,8 @@ if rank == 0:
     assert np.array_equal(tot, O.msm_g1(ss, pts)), "sharded MSM total"
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank{rank}ok\n")  # one write call: no interleaving between ranks
+sys.stdout.flush()
 '''
 
 
@@ -79,7 +80,7 @@ def test_sharded_paths_world2_gloo(tmp_path):
            "--master-port", "29653", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank0ok" in r.stdout and "rank1ok" in r.stdout
 
 
 def test_shard_range_covers_everything():

@@ -21,4 +21,4 @@ def test_sharded_paths_nccl():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for k in range(world):
-        assert f"rank {k} of {world} ok" in r.stdout
+        assert f"rank{k}of{world}ok" in r.stdout

@@ -609,3 +609,31 @@ def test_g1_sum(ctx):
     assert g1_tuple(ctx.g1_sum(arr)) == exp
     assert g1_tuple(ctx.g1_sum(g1s([pts[2], P.g1_neg(pts[2])]))) is None
     assert g1_tuple(ctx.g1_sum(np.zeros((0, 12), dtype=np.uint64))) is None
+
+
+@pytest.mark.parametrize("c", [8, 13, 16, 20])
+def test_commit_with_fixed_base_tables(ctx, T, c):
+    """tkm_crs_precompute: commitments through the fixed-base tables equal the plain ones and the oracle MSM."""
+    G = g1s([P.G1_GEN])[0]
+    rs_x, rs_y = 64, 32
+    grid = O.g1_fixed_base_mul_batch(G, O.random_fr(470, rs_x * rs_y))
+    grid[5] = 0  # an identity point inside the CRS
+    sigma = T.Sigma1(ctx, grid, rs_x, rs_y)
+    polys = []
+    for (x, y, seed) in ((64, 32, 471), (32, 16, 472), (16, 32, 473)):
+        a = O.random_fr(seed, x * y)
+        a[::7] = 0
+        a[3] = frs([P.R_MOD - 1])[0]
+        a[4] = frs([1])[0]
+        polys.append((a, x, y))
+    plain = [sigma.encode_poly(poly_from(T, ctx, a, x, y)) for a, x, y in polys]
+    sigma.precompute(c)
+    for (a, x, y), ref in zip(polys, plain):
+        got = sigma.encode_poly(poly_from(T, ctx, a, x, y))
+        assert np.array_equal(got, ref)
+        assert np.array_equal(got, O.msm_g1_rect(a, y, grid, rs_y, x, y))
+    sparse = [0] * (64 * 32)
+    sparse[0], sparse[40 * 32 + 9] = 5, P.R_MOD - 2
+    exp = O.msm_g1_rect(frs(sparse), 32, grid, rs_y, 64, 32)
+    assert np.array_equal(sigma.encode_poly(poly_from(T, ctx, frs(sparse), 64, 32)), exp)
+    assert g1_tuple(sigma.encode_poly(T.DensePolynomialExt.zero(ctx, 8, 8))) is None

@@ -511,10 +511,24 @@ int32_t tkm_crs_upload(tkm_ctx *ctx, const uint8_t *points96, size_t rows, size_
   if (st != TKM_OK) cudaFree(d);
   return st;
 }
+int32_t tkm_crs_precompute(tkm_ctx *ctx, tkm_crs *crs, uint32_t window_bits) {
+  API_BEGIN
+  TKM_REQUIRE(crs, "null crs");
+  if (crs->pre) {
+    if (crs->pre_c == window_bits) return TKM_OK;
+    TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(crs->pre);
+    crs->pre = nullptr;
+  }
+  TKM_TRY(crs_precompute(ctx, crs->d, crs->rows * crs->cols, window_bits, &crs->pre, &crs->pre_W));
+  crs->pre_c = window_bits;
+  return TKM_OK;
+}
 int32_t tkm_crs_free(tkm_ctx *ctx, tkm_crs *crs) {
   API_BEGIN
   if (!crs) return TKM_OK;
   cudaStreamSynchronize(ctx->stream);
+  if (crs->pre) cudaFree(crs->pre);
   if (crs->owned && crs->d) cudaFree(crs->d);
   delete crs;
   return TKM_OK;

@@ -60,6 +60,8 @@ struct tkm_crs {
   tkm::G1Affine *d = nullptr;  // row-major [rows][cols], Montgomery form
   size_t rows = 0, cols = 0;
   bool owned = true;
+  tkm::G1Affine *pre = nullptr;  // optional fixed-base tables [pre_W][rows*cols]: 2^(pre_c*w) * P
+  uint32_t pre_c = 0, pre_W = 0;
 };
 
 namespace tkm {
@@ -138,7 +140,10 @@ struct MsmInput {
   size_t base_row_stride;
   size_t rows, cols;
   const uint32_t *idx;  // optional gather indices into bases (rows must be 1)
+  uint32_t pre_c = 0;       // fixed-base tables: window bits the tables were built for (0 = plain bases)
+  uint32_t pre_stride = 0;  // fixed-base tables: points per table (table w starts at bases + w*pre_stride)
 };
+int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c, G1Affine **out_table, uint32_t *out_W);
 int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]);
 
 }  // namespace tkm

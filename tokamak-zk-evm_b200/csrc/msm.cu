@@ -29,7 +29,9 @@ namespace tkm {
 
 struct MsmGeom {
   uint32_t c;        // window bits
-  uint32_t W;        // windows
+  uint32_t Wd;       // digit windows of the scalar decomposition
+  uint32_t val_stride;  // 0, or (fixed-base tables) offset of window w's table: base index += w*val_stride
+  uint32_t W;        // bucket windows (= Wd; 1 when precomputed tables fold every window into one bucket set)
   uint32_t B;        // buckets per window = 2^(c-1)
   uint32_t logB;
   uint32_t nbuckets; // W*B (+1 trash bucket at index nbuckets)
@@ -39,7 +41,7 @@ struct MsmGeom {
   uint32_t nbits;    // log2(nseg)
 };
 
-static MsmGeom pick_geom(size_t n) {
+static MsmGeom pick_geom(size_t n, uint32_t fixed_c = 0, uint32_t table_stride = 0) {
   // minimise W*(n + 3*2^(c-1)) -- mixed adds plus ~3 madd-equivalents per bucket of reduction
   double best = 1e300;
   uint32_t bc = 8;
@@ -51,9 +53,12 @@ static MsmGeom pick_geom(size_t n) {
       bc = c;
     }
   }
+  if (fixed_c) bc = fixed_c;
   MsmGeom m;
   m.c = bc;
-  m.W = (256 + bc - 1) / bc;
+  m.Wd = (256 + bc - 1) / bc;
+  m.val_stride = table_stride;
+  m.W = fixed_c ? 1 : m.Wd;
   m.logB = bc - 1;
   m.B = 1u << m.logB;
   m.nbuckets = m.W * m.B;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256) k_decompose(const Fr *__restrict__ scalar
     if (scalars_mont) s = s.from_mont();
     uint32_t base_idx = gather ? gather[k] : (uint32_t)((size_t)i * b_row_stride + j);
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < m.W; w++) {
+    for (uint32_t w = 0; w < m.Wd; w++) {
       uint32_t bit = w * m.c;
       uint32_t limb = bit >> 5, sh = bit & 31;
       uint32_t raw = 0;
@@ -110,8 +115,8 @@ __global__ void __launch_bounds__(256) k_decompose(const Fr *__restrict__ scalar
         carry = 1;
       }
       size_t slot = (size_t)w * n + k;
-      keys[slot] = mag ? (w * m.B + mag - 1) : m.nbuckets;
-      vals[slot] = base_idx | (neg << 31);
+      keys[slot] = mag ? ((m.W == 1 ? 0u : w * m.B) + mag - 1) : m.nbuckets;
+      vals[slot] = (base_idx + w * m.val_stride) | (neg << 31);
     }
   }
 }
@@ -349,6 +354,68 @@ __global__ void __launch_bounds__(256) k_g1_to_mont(const G1Affine *__restrict__
   }
 }
 
+// Fixed-base tables for a resident CRS: out[w*n + i] = 2^(c*w) * P_i in affine form, w < W.  With them every digit
+// window of a commitment lands in ONE shared bucket set (no per-window reduction, no Horner tail) and the window can be
+// wider (fewer additions per point).  One thread per base: c*(W-1) doublings, then all W-1 conversions to affine share a
+// single inversion (Montgomery's trick over the thread's own points).  HBM capacity is what makes this affordable:
+// 13 tables of the 8192 x 512 grid are 5.2 GB.
+constexpr int PRE_MAX_W = 32;
+__global__ void __launch_bounds__(128) k_crs_precompute(const G1Affine *__restrict__ base, size_t n, uint32_t c, uint32_t W,
+                                                       G1Xyzz *__restrict__ tmp, G1Affine *__restrict__ out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine P = base[i];
+  out[i] = P;
+  G1Xyzz Q = G1Xyzz::from_affine(P);
+  Fq pref[PRE_MAX_W];
+  Fq acc = Fq::one();
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t k = 0; k < c; k++) Q = g1_dbl(Q);
+    store_xyzz(tmp + (size_t)(w - 1) * n + i, Q);
+    pref[w - 1] = acc;
+    if (!Q.is_identity()) acc = acc * (Q.ZZ * Q.ZZZ);
+  }
+  Fq inv = acc.inv();
+  for (uint32_t w = W - 1; w >= 1; w--) {
+    G1Xyzz R = load_xyzz(tmp + (size_t)(w - 1) * n + i);
+    G1Affine a = G1Affine::identity();
+    if (!R.is_identity()) {
+      Fq zinv = inv * pref[w - 1];  // 1 / (ZZ*ZZZ)
+      inv = inv * (R.ZZ * R.ZZZ);
+      a.x = R.X * (zinv * R.ZZZ);
+      a.y = R.Y * (zinv * R.ZZ);
+    }
+    out[(size_t)w * n + i] = a;
+  }
+}
+
+int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c, G1Affine **out_table, uint32_t *out_W) {
+  if (c < 4 || c > 22) return fail(TKM_ERR_INVALID_ARGUMENT, "window bits %u out of range [4,22]", c);
+  const uint32_t W = (256 + c - 1) / c;
+  if (W > PRE_MAX_W) return fail(TKM_ERR_INVALID_ARGUMENT, "too many windows");
+  if ((size_t)W * n >= ((size_t)1 << 31)) return fail(TKM_ERR_INVALID_ARGUMENT, "table of %u x %zu points exceeds the 31-bit index space", W, n);
+  G1Affine *table = nullptr;
+  cudaError_t e = cudaMalloc((void **)&table, (size_t)W * n * sizeof(G1Affine));
+  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMalloc(%zu) failed: %s", (size_t)W * n * sizeof(G1Affine), cudaGetErrorString(e));
+  Scratch<G1Xyzz> tmp;
+  int32_t st = tmp.alloc(ctx, (size_t)(W - 1) * n);
+  if (st == TKM_OK) {
+    k_crs_precompute<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(base, n, c, W, tmp.p, table);
+    st = launch_check(ctx, "k_crs_precompute");
+  }
+  if (st == TKM_OK) {
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (e2 != cudaSuccess) st = fail(TKM_ERR_CUDA, "k_crs_precompute failed: %s", cudaGetErrorString(e2));
+  }
+  if (st != TKM_OK) {
+    cudaFree(table);
+    return st;
+  }
+  *out_table = table;
+  *out_W = W;
+  return TKM_OK;
+}
+
 int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n) {
   if (n == 0) return TKM_OK;
   k_g1_to_mont<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);
@@ -363,8 +430,8 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
   }
   if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
   if (in.idx && in.rows != 1) return fail(TKM_ERR_INVALID_ARGUMENT, "indexed MSM must be one row");
-  const MsmGeom m = pick_geom(n);
-  const size_t M = n * m.W;
+  const MsmGeom m = pick_geom(n, in.pre_c, in.pre_stride);
+  const size_t M = n * m.Wd;
   const uint32_t invalid = m.nbuckets;
   uint32_t key_bits = 1;
   while ((1ull << key_bits) <= invalid) key_bits++;

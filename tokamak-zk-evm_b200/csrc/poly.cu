@@ -746,11 +746,15 @@ int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t o
   in.scalars = p->d;
   in.scalars_mont = true;
   in.scalar_row_stride = p->y_size;
-  in.bases = crs->d;
+  in.bases = crs->pre ? crs->pre : crs->d;
   in.base_row_stride = crs->cols;
   in.rows = tx;
   in.cols = ty;
   in.idx = nullptr;
+  if (crs->pre) {  // fixed-base tables (tkm_crs_precompute): one shared bucket set, no Horner tail
+    in.pre_c = crs->pre_c;
+    in.pre_stride = (uint32_t)(crs->rows * crs->cols);
+  }
   return msm_run(ctx, in, out96);
 }
 

@@ -64,6 +64,7 @@ extern "C" {
     pub fn tkm_crs_upload(ctx: *mut tkm_ctx, points96: *const u8, rows: usize, cols: usize, out: *mut *mut tkm_crs) -> i32;
     pub fn tkm_crs_from_device(ctx: *mut tkm_ctx, dev_points: *mut c_void, rows: usize, cols: usize, take_ownership: i32,
                                out: *mut *mut tkm_crs) -> i32;
+    pub fn tkm_crs_precompute(ctx: *mut tkm_ctx, crs: *mut tkm_crs, window_bits: u32) -> i32;
     pub fn tkm_crs_free(ctx: *mut tkm_ctx, crs: *mut tkm_crs) -> i32;
     pub fn tkm_crs_device_ptr(crs: *mut tkm_crs, out_dev: *mut *mut c_void, rows: *mut usize, cols: *mut usize) -> i32;
     pub fn tkm_poly_from_coeffs_host(ctx: *mut tkm_ctx, coeffs: *const u8, x_size: usize, y_size: usize, out: *mut *mut tkm_poly) -> i32;

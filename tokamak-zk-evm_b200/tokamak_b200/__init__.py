@@ -270,6 +270,10 @@ class Sigma1:
         check(ctx.lib.tkm_crs_upload(ctx.h, _vp(pts), rs_x, rs_y, ctypes.byref(h)))
         self.h, self.rs_x, self.rs_y = h, rs_x, rs_y
 
+    def precompute(self, window_bits=20):
+        """Build fixed-base tables for this CRS (for provers that reuse one CRS across many proofs)."""
+        check(self.ctx.lib.tkm_crs_precompute(self.ctx.h, self.h, window_bits))
+
     def encode_poly(self, poly):
         """Sigma1::encode_poly (group_structures/mod.rs:59-119; iotools/mod.rs:2041-2113)."""
         out = np.zeros(12, dtype=np.uint64)

@@ -53,6 +53,7 @@ SIGNATURES = {
     "tkm_g1_sum": [c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_crs_upload": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_crs_from_device": [c_void_p, c_void_p, c_size_t, c_size_t, c_int32, P(c_void_p)],
+    "tkm_crs_precompute": [c_void_p, c_void_p, c_uint32],
     "tkm_crs_free": [c_void_p, c_void_p],
     "tkm_crs_device_ptr": [c_void_p, P(c_void_p), P(c_size_t), P(c_size_t)],
     "tkm_poly_from_coeffs_host": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
