@@ -362,6 +362,17 @@ def main():
         rep["all_runs_hot_path_s"] = [round(o["hot_path_s"], 4) for o in runs]
         rep.pop("detail_ms", None)
         line["prove_replay"] = rep
+        # serving mode: one CRS reused across proofs -> fixed-base tables (13 x 384 MiB at c = 20) built once
+        t0 = time.perf_counter()
+        sigma.precompute(20)
+        ctx.sync()
+        t_tables = time.perf_counter() - t0
+        prove_replay.run(ctx, sigma, table)
+        runs = sorted((prove_replay.run(ctx, sigma, table) for _ in range(3)), key=lambda o: o["hot_path_s"])
+        line["prove_replay_fixed_base_tables"] = {"hot_path_s": runs[1]["hot_path_s"], "encode_s": runs[1]["encode_s"], "poly_s": runs[1]["poly_s"],
+                                                  "ntt_s": runs[1]["ntt_s"], "table_build_s_once_per_crs": t_tables, "window_bits": 20,
+                                                  "table_bytes": 13 * 8192 * 512 * 96,
+                                                  "all_runs_hot_path_s": [round(o["hot_path_s"], 4) for o in runs]}
         sigma.close()
     if world > 1 and not args.skip_aux:
         # ---- row-sharded bivariate NTT with the X<->Y transpose as an NCCL all-to-all

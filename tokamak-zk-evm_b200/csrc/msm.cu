@@ -276,14 +276,19 @@ __global__ void __launch_bounds__(128) k_bucket_seg(const G1Xyzz *__restrict__ b
 }
 
 constexpr int BITS_THREADS = 128;
-// Block (w, k): k < nbits -> M_k = sum over segments s with bit k set of run_s ; k == nbits -> A = sum_s acc_s.
+// Block (w, k, slice): k < nbits -> partial of M_k = sum over segments s with bit k set of run_s ; k == nbits -> partial of
+// A = sum_s acc_s.  Each block tree-sums one slice of the window's segments (`splits` slices per (w, k)) so the
+// reduction stays parallel when there are few windows (fixed-base tables: one window, 2^19 buckets).
 __global__ void __launch_bounds__(BITS_THREADS) k_bucket_bits(const G1Xyzz *__restrict__ seg_acc, const G1Xyzz *__restrict__ seg_run,
-                                                             MsmGeom m, G1Xyzz *__restrict__ out) {
+                                                             MsmGeom m, uint32_t splits, G1Xyzz *__restrict__ out) {
   __shared__ G1Xyzz sh[BITS_THREADS];
-  const uint32_t w = blockIdx.x / (m.nbits + 1), k = blockIdx.x % (m.nbits + 1);
+  const uint32_t slice = blockIdx.x % splits, wk = blockIdx.x / splits;
+  const uint32_t w = wk / (m.nbits + 1), k = wk % (m.nbits + 1);
   const G1Xyzz *src = (k == m.nbits ? seg_acc : seg_run) + (size_t)w * m.nseg;
+  const uint32_t per = (m.nseg + splits - 1) / splits;
+  const uint32_t lo = slice * per, hi = (lo + per < m.nseg) ? lo + per : m.nseg;
   G1Xyzz acc = G1Xyzz::identity();
-  for (uint32_t s = threadIdx.x; s < m.nseg; s += BITS_THREADS) {
+  for (uint32_t s = lo + threadIdx.x; s < hi; s += BITS_THREADS) {
     if (k == m.nbits || ((s >> k) & 1)) {
       G1Xyzz p = load_xyzz(src + s);
       g1_add(acc, p);
@@ -298,6 +303,26 @@ __global__ void __launch_bounds__(BITS_THREADS) k_bucket_bits(const G1Xyzz *__re
       sh[threadIdx.x] = a;
     }
     __syncthreads();
+  }
+  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
+}
+// out[g] = sum of the `count` consecutive points in[g*count ..] (second stage of the sliced reduction).
+__global__ void __launch_bounds__(32) k_sum_groups(const G1Xyzz *__restrict__ in, uint32_t count, G1Xyzz *__restrict__ out) {
+  __shared__ G1Xyzz sh[32];
+  G1Xyzz acc = G1Xyzz::identity();
+  for (uint32_t s = threadIdx.x; s < count; s += 32) {
+    G1Xyzz p = load_xyzz(in + (size_t)blockIdx.x * count + s);
+    g1_add(acc, p);
+  }
+  sh[threadIdx.x] = acc;
+  __syncwarp();
+  for (int stride = 16; stride > 0; stride >>= 1) {
+    if ((int)threadIdx.x < stride) {
+      G1Xyzz a = sh[threadIdx.x], b = sh[threadIdx.x + stride];
+      g1_add(a, b);
+      sh[threadIdx.x] = a;
+    }
+    __syncwarp();
   }
   if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
 }
@@ -502,8 +527,24 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
   TKM_TRY(res.alloc(ctx, 24));
   k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets.p, m, seg_acc.p, seg_run.p);
   TKM_TRY(launch_check(ctx, "k_bucket_seg"));
-  k_bucket_bits<<<m.W * (m.nbits + 1), BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, parts.p);
-  TKM_TRY(launch_check(ctx, "k_bucket_bits"));
+  {
+    // slices per (window, bit): keep every thread at <= ~4 segment sums, at most 64 slices
+    uint32_t splits = (m.nseg + BITS_THREADS * 4 - 1) / (BITS_THREADS * 4);
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    const uint32_t groups = m.W * (m.nbits + 1);
+    if (splits == 1) {
+      k_bucket_bits<<<groups, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, 1, parts.p);
+      TKM_TRY(launch_check(ctx, "k_bucket_bits"));
+    } else {
+      Scratch<G1Xyzz> sliced;
+      TKM_TRY(sliced.alloc(ctx, (size_t)groups * splits));
+      k_bucket_bits<<<groups * splits, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, splits, sliced.p);
+      TKM_TRY(launch_check(ctx, "k_bucket_bits"));
+      k_sum_groups<<<groups, 32, 0, ctx->stream>>>(sliced.p, splits, parts.p);
+      TKM_TRY(launch_check(ctx, "k_sum_groups"));
+    }
+  }
   k_final<<<1, 32, 0, ctx->stream>>>(parts.p, m, wsum.p, nullptr, res.p);
   TKM_TRY(launch_check(ctx, "k_final"));
   TKM_CUDA(cudaMemcpyAsync(out96, res.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
