@@ -34,6 +34,11 @@ G1_GEN = (
 )
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/r01_ncu_k_accumulate_summary.csv: 2^22-point MSM; profiles/r01_ncu_k_ntt_pass_summary.csv: 16384 x 512 forward)
+NCU_TRAFFIC = {"k_accumulate": 11.829, "k_ntt_pass_x3": 1.459}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -275,19 +280,31 @@ def main():
         if rank == 0:
             # ---- integer-pipe roofline of the dominant kernel (k_accumulate): SURVEY.md §8d
             imad_wide = ctx.microbench(1)
+            imad_wide_x = ctx.microbench(5)
             fq_mul = ctx.microbench(3)
             madd = ctx.microbench(4)
             W = 16 if args.log_n == 22 else None
-            line["microbench"] = {"imad_wide_u32_per_s": imad_wide, "imad_u32_per_s": ctx.microbench(0), "fr_mul_per_s": ctx.microbench(2),
-                                  "fq_mul_per_s": fq_mul, "xyzz_madd_per_s": madd}
+            line["microbench"] = {"imad_wide_u32_per_s": imad_wide, "imad_wide_x_u32_per_s": imad_wide_x, "imad_u32_per_s": ctx.microbench(0),
+                                  "fr_mul_per_s": ctx.microbench(2), "fq_mul_per_s": fq_mul, "xyzz_madd_per_s": madd}
             if W:
+                # k_accumulate alone, timed live with CUDA events on the launching stream (tkm_kernel_time_last), averaged
+                acc_ms = []
+                for _ in range(max(3, min(args.steps, 10))):
+                    step_resident()
+                    acc_ms.append(ctx.kernel_time_last())
+                acc_ms = float(np.mean(acc_ms))
                 adds = n * W
                 wide_per_add = 10 * 2 * 144  # 10 Fq products x (144 a*b + 144 reduction) 32x32->64 multiply-adds
-                ach = adds * wide_per_add / (ms_res * 1e-3)
-                line["roofline"] = {"bound": "int32", "achieved": ach / 1e12, "peak": imad_wide / 1e12, "unit": "T(32x32+64 IMAD)/s", "frac": ach / imad_wide,
-                                    "traffic": None, "kernel": "k_accumulate (+ sort, reductions: whole MSM time used)",
-                                    "note": "MSM is integer-pipe bound (SURVEY.md 8d): N*W mixed additions x 2880 wide IMADs; peak = measured IMAD.WIDE.U32 stream on this GPU",
-                                    "madd_frac": adds / (ms_res * 1e-3) / madd}
+                ach = adds * wide_per_add / (acc_ms * 1e-3)
+                peak = max(imad_wide, imad_wide_x)
+                line["roofline"] = {"bound": "int32", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T(32x32+64 IMAD.WIDE)/s", "frac": ach / peak,
+                                    "traffic": NCU_TRAFFIC["k_accumulate"], "traffic_unit": "GB per launch (dram read+write, ncu --set full capture in profiles/)",
+                                    "algorithmic_gb": adds * 104 / 1e9, "kernel": "k_accumulate", "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_res,
+                                    "note": "MSM is integer-pipe bound (SURVEY.md 8d; the schema's hbm/tensor bounds do not describe it): "
+                                            "N*W mixed additions x 2880 wide IMADs per launch / k_accumulate's event-timed duration; "
+                                            "peak = best measured IMAD.WIDE.U32 stream on this GPU (64-bit-addend or carry-chain form)",
+                                    "whole_msm_frac": adds * wide_per_add / (ms_res * 1e-3) / peak,
+                                    "madd_frac": adds / (acc_ms * 1e-3) / madd}
 
             # ---- bivariate NTT 16384 x 512 (device-resident) with its HBM roofline
             hbm, how = measured_peaks()
@@ -303,11 +320,14 @@ def main():
                 for _ in range(args.steps):
                     ctx.bintt_dev(d_poly, d_poly, NTT_X, NTT_Y, direction)
                 ms = ctx.time_end() / args.steps
+                kms = ctx.kernel_time_last()  # the k_ntt_pass launches of the last transform alone
                 ach = 128.0 * nn / (ms * 1e-3) / 1e9
                 line.setdefault("bintt", {})[key] = {
                     "shape": [NTT_X, NTT_Y], "ms": ms, "value": nn / ms / 1e6, "unit": "Gelem/s", "launches_per_transform": (ctx.launch_count() - l0) // args.steps,
-                    "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                                 "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_element": 128}}
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": NCU_TRAFFIC["k_ntt_pass_x3"],
+                                 "traffic_unit": "GB per transform (dram read+write summed over the 3 launches, ncu --set full capture in profiles/)",
+                                 "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_element": 128,
+                                 "kernel": "k_ntt_pass x3", "kernel_ms": kms}}
             # e2e biNTT through the host-buffer entry point (pinned buffers)
             h_poly = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)
             h_out = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)

@@ -216,10 +216,14 @@ int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t o
 /* Times one device-resident launch sequence with CUDA events on the context stream; ms out. */
 int32_t tkm_event_time_begin(tkm_ctx *ctx);
 int32_t tkm_event_time_end(tkm_ctx *ctx, float *out_ms);
+/* Duration (CUDA events on the context stream) of the most recent dominant-kernel launch: k_accumulate of the last MSM,
+ * or all k_ntt_pass launches of the last (bi)NTT.  Used by bench.py for the per-kernel roofline. */
+int32_t tkm_kernel_time_last(tkm_ctx *ctx, float *out_ms);
 /* Kernel launches issued by this library on this context since creation. */
 int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out);
 /* Micro-benchmarks: integer pipe peak (dependent-free IMAD / IMAD.WIDE streams) and field-mul rate.
- * kind: 0 = IMAD.U32, 1 = IMAD.WIDE.U32, 2 = Fr mul, 3 = Fq mul, 4 = XYZZ mixed add.  out = ops/s. */
+ * kind: 0 = IMAD.U32, 1 = IMAD.WIDE.U32 (64-bit addend), 2 = Fr mul, 3 = Fq mul, 4 = XYZZ mixed add,
+ * 5 = IMAD.WIDE.U32.X carry chains (the form the field multiplier issues).  out = ops/s. */
 int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s);
 
 #ifdef __cplusplus

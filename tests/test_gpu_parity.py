@@ -222,6 +222,38 @@ def test_msm_empty_and_degenerate(ctx):
     assert np.array_equal(ctx.msm_g1_host(mix, pts), O.msm_g1(mix, pts))
 
 
+@pytest.mark.parametrize("n,pieces", [(1, 4), (5, 4), (1000, 3), (4097, 4), (6000, 16)])
+def test_msm_host_pipelined_pieces(ctx, n, pieces, monkeypatch):
+    """tkm_msm_g1_host cut into point ranges (copy/compute pipeline): every piece adds into the same bucket set, so the
+    result must not depend on the cut.  Includes scalars that put every piece's digits into the same buckets."""
+    G = g1s([P.G1_GEN])[0]
+    pts = O.g1_fixed_base_mul_batch(G, O.random_fr(160 + n, n))
+    ss = O.random_fr(161 + n, n)
+    exp = O.msm_g1(ss, pts)
+    monkeypatch.setenv("TKM_MSM_HOST_PIECES", str(pieces))
+    assert np.array_equal(ctx.msm_g1_host(ss, pts), exp)
+    hot = frs([0x0001000100010001000100010001000100010001000100010001000100010001 % P.R_MOD] * n)
+    assert np.array_equal(ctx.msm_g1_host(hot, pts), O.msm_g1(hot, pts))
+    monkeypatch.setenv("TKM_MSM_HOST_PIECES", "1")
+    assert np.array_equal(ctx.msm_g1_host(ss, pts), exp)
+
+
+def test_msm_host_pipelined_large(ctx):
+    """2^21 points through the default 4-piece pipeline; answer from known discrete logs (O(N) field work)."""
+    n = 1 << 21
+    G = g1s([P.G1_GEN])[0]
+    ks = O.random_fr(170, n)
+    ss = O.random_fr(171, n)
+    dk = ctx.upload_fr(ks, to_mont=False)
+    dpts = ctx.dev_alloc(n * 96)
+    ctx.lib.tkm_g1_fixed_base_mul(ctx.h, G.ctypes.data, dk, 0, n, dpts)
+    pts = np.empty((n, 12), dtype=np.uint64)
+    ctx.d2h(pts, dpts)
+    ctx.dev_free(dk)
+    ctx.dev_free(dpts)
+    assert np.array_equal(ctx.msm_g1_host(ss, pts), O.g1_mul(G, O.fr_inner_product(ss, ks)))
+
+
 @pytest.mark.parametrize("logn", [16, 18, 20])
 def test_msm_large_known_discrete_logs(ctx, logn):
     """Bases k_i*G generated on the device; answer (sum s_i k_i)*G from O(N) field work on the oracle

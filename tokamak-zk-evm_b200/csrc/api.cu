@@ -1,5 +1,7 @@
 // C-ABI entry points of libtokamak_b200 (see include/tokamak_b200.h for the reference interface each
 // one replaces).  Validation + plumbing only; the kernels live in vec_ops.cu, ntt.cu, msm.cu, poly.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tkm {
@@ -92,17 +94,37 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
     uint32_t r = 0;
     for (int i = 0; i < 8; i++) r ^= a[i];
     if (r == 0x12345678u) sink[0] = r;
-  } else if (KIND == 1) {  // 16 independent mad.wide.u32 accumulators per thread: the IMAD.WIDE issue limit of the fmaheavy pipe
+  } else if (KIND == 1) {  // 16 independent IMAD.WIDE.U32 accumulators (64-bit addend, no carry flag); the multiplier changes
+                           // every iteration so the product can not be hoisted out of the loop
     uint64_t a[16];
-    for (int i = 0; i < 16; i++) a[i] = (uint64_t)t * (i + 3);
-    uint32_t m = t | 1u, q = (t * 2654435761u) | 3u;
+    uint32_t m[16];
+    for (int i = 0; i < 16; i++) { a[i] = (uint64_t)t * (i + 3); m[i] = (t * 2654435761u + i) | 1u; }
+    uint32_t q = t | 3u;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(m), "r"(q));
+      for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(m[i]), "r"(q));
+      q ^= (uint32_t)it;
     }
     uint64_t r = 0;
     for (int i = 0; i < 16; i++) r ^= a[i];
     if (r == 0x12345678u) sink[0] = (uint32_t)r;
+  } else if (KIND == 5) {  // the form the field multiplier issues: mad.lo.cc/madc.hi.cc pairs = IMAD.WIDE.U32.X carry chains,
+                           // two independent chains of 8 wide multiply-adds per iteration
+    uint32_t E[16], O[16], a[8], b = t | 1u;
+    for (int i = 0; i < 16; i++) { E[i] = t + i; O[i] = t ^ i; }
+    for (int i = 0; i < 8; i++) a[i] = t * (2 * i + 1);
+    for (int it = 0; it < iters; it++) {
+      E[0] = mad_lo_cc(a[0], b, E[0]); E[1] = madc_hi_cc(a[0], b, E[1]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) { E[2 * j] = madc_lo_cc(a[j], b, E[2 * j]); E[2 * j + 1] = madc_hi_cc(a[j], b, E[2 * j + 1]); }
+      O[0] = mad_lo_cc(a[0], b, O[0]); O[1] = madc_hi_cc(a[0], b, O[1]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) { O[2 * j] = madc_lo_cc(a[j], b, O[2 * j]); O[2 * j + 1] = madc_hi_cc(a[j], b, O[2 * j + 1]); }
+      b ^= (uint32_t)it;
+    }
+    uint32_t r = 0;
+    for (int i = 0; i < 16; i++) r ^= E[i] ^ O[i];
+    if (r == 0x12345678u) sink[0] = r;
   } else if (KIND == 2) {
     Fr x = Fr::one(), y = Fr::r2();
     x.v[0] ^= t;
@@ -155,6 +177,8 @@ int32_t tkm_ctx_create(int32_t device_ordinal, tkm_ctx **out) {
   ctx->stream = ctx->own_stream;
   TKM_CUDA(cudaEventCreate(&ctx->ev0));
   TKM_CUDA(cudaEventCreate(&ctx->ev1));
+  TKM_CUDA(cudaEventCreate(&ctx->kev0));
+  TKM_CUDA(cudaEventCreate(&ctx->kev1));
   // keep freed scratch in the stream-ordered pool instead of returning it to the driver
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
@@ -176,6 +200,13 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
   if (ctx->twiddles) cudaFree(ctx->twiddles);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->kev0) cudaEventDestroy(ctx->kev0);
+  if (ctx->kev1) cudaEventDestroy(ctx->kev1);
+  if (ctx->copy_stream) {
+    cudaStreamDestroy(ctx->copy_stream);
+    for (cudaEvent_t e : ctx->copy_ev)
+      if (e) cudaEventDestroy(e);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return TKM_OK;
@@ -404,14 +435,10 @@ int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bas
     return TKM_OK;
   }
   TKM_REQUIRE(scalars && bases, "null argument");
-  Scratch<Fr> ds;
-  Scratch<G1Affine> db;
-  TKM_TRY(ds.alloc(ctx, n));
-  TKM_TRY(db.alloc(ctx, n));
-  TKM_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  TKM_CUDA(cudaMemcpyAsync(db.p, bases, n * 96, cudaMemcpyHostToDevice, ctx->stream));
-  TKM_TRY(g1_to_mont_dev(ctx, db.p, db.p, n));
-  return tkm_msm_g1(ctx, ds.p, 0, db.p, n, out96);
+  // Large inputs: overlap the host->device copies with the bucket accumulation, one point range at a time.
+  uint32_t pieces = n >= ((size_t)1 << 21) ? 4 : (n >= ((size_t)1 << 19) ? 2 : 1);
+  if (const char *e = getenv("TKM_MSM_HOST_PIECES")) pieces = (uint32_t)atoi(e);  // developer knob
+  return msm_host_pipelined(ctx, scalars, bases, n, pieces, out96);
 }
 
 int32_t tkm_g1_fixed_base_mul(tkm_ctx *ctx, const uint8_t base96[96], const void *scalars, int32_t scalars_mont, size_t n, void *out) {
@@ -554,6 +581,14 @@ int32_t tkm_event_time_end(tkm_ctx *ctx, float *out_ms) {
   TKM_CUDA(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
   return TKM_OK;
 }
+int32_t tkm_kernel_time_last(tkm_ctx *ctx, float *out_ms) {
+  API_BEGIN
+  TKM_REQUIRE(out_ms, "null out pointer");
+  TKM_REQUIRE(ctx->kernel_timed, "no dominant-kernel launch has been timed on this context yet");
+  TKM_CUDA(cudaEventSynchronize(ctx->kev1));
+  TKM_CUDA(cudaEventElapsedTime(out_ms, ctx->kev0, ctx->kev1));
+  return TKM_OK;
+}
 int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out) {
   API_BEGIN
   TKM_REQUIRE(out, "null out pointer");
@@ -577,6 +612,7 @@ int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
       case 2: iters = 512; ops_per_iter = 2; k_microbench<2><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 3: iters = 256; ops_per_iter = 2; k_microbench<3><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 4: iters = 64; ops_per_iter = 1; k_microbench<4><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 5: iters = 4096; ops_per_iter = 16; k_microbench<5><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown microbench kind %d", kind);
     }
     TKM_TRY(launch_check(ctx, "k_microbench"));

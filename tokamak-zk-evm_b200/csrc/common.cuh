@@ -49,6 +49,13 @@ struct tkm_ctx {
   tkm::Fr inv_pow2[33];  // 2^-k in Montgomery form (1/n factors of the inverse transforms)
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // events bracketing the most recent launch of a dominant kernel (k_accumulate, the last k_ntt_pass of a transform):
+  // bench.py's roofline divides the kernel's algorithmic work by this duration (tkm_kernel_time_last)
+  cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+  bool kernel_timed = false;
+  // copy engine side of the pipelined host-buffer MSM (created on first use)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[17] = {};
 };
 
 struct tkm_poly {
@@ -145,5 +152,6 @@ struct MsmInput {
 };
 int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c, G1Affine **out_table, uint32_t *out_W);
 int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]);
+int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t pieces, uint8_t out96[96]);
 
 }  // namespace tkm

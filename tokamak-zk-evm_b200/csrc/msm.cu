@@ -370,6 +370,18 @@ __global__ void __launch_bounds__(256) k_fill_identity(G1Xyzz *p, size_t n) {
     store_xyzz(p + i, G1Xyzz::identity());
 }
 
+// sets[0][i] += sets[1][i] + .. + sets[count-1][i]: bucket sets of the point ranges of one pipelined host MSM.
+__global__ void __launch_bounds__(128) k_bucket_merge(G1Xyzz *__restrict__ sets, size_t set_stride, uint32_t count, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Xyzz acc = load_xyzz(sets + i);
+  for (uint32_t k = 1; k < count; k++) {
+    G1Xyzz p = load_xyzz(sets + k * set_stride + i);
+    g1_add(acc, p);
+  }
+  store_xyzz(sets + i, acc);
+}
+
 __global__ void __launch_bounds__(256) k_g1_to_mont(const G1Affine *__restrict__ in, G1Affine *__restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     G1Affine a = in[i];
@@ -447,15 +459,10 @@ int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n
   return launch_check(ctx, "k_g1_to_mont");
 }
 
-int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
+// One accumulation pass over `in`: digits -> sort -> chunked bucket accumulation -> segmented reduction of the partial
+// list.  `buckets` must hold identities on entry (every bucket is written at most once per pass).
+static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGeom &m, G1Xyzz *buckets) {
   const size_t n = in.rows * in.cols;
-  if (n == 0) {  // msm_g1_bases returns the identity for empty input (group_structures/mod.rs:131-133)
-    memset(out96, 0, 96);
-    return TKM_OK;
-  }
-  if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
-  if (in.idx && in.rows != 1) return fail(TKM_ERR_INVALID_ARGUMENT, "indexed MSM must be one row");
-  const MsmGeom m = pick_geom(n, in.pre_c, in.pre_stride);
   const size_t M = n * m.Wd;
   const uint32_t invalid = m.nbuckets;
   uint32_t key_bits = 1;
@@ -480,15 +487,21 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
                                            ctx->stream));
   ctx->launches += 4;  // cub's histogram + onesweep passes (approximate; they are library launches)
 
-  Scratch<G1Xyzz> buckets;
-  TKM_TRY(buckets.alloc(ctx, (size_t)m.nbuckets + 1));
-  k_fill_identity<<<grid_for((size_t)m.nbuckets + 1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, (size_t)m.nbuckets + 1);
-  TKM_TRY(launch_check(ctx, "k_fill_identity"));
-
-  // chunk length: long enough to amortise the two partial slots per thread, short enough to fill the GPU
-  uint32_t chunk = 256;  // 2 partial-list entries per chunk: longer chunks shrink the segmented-reduction levels
-  if (const char *e = getenv("TKM_MSM_CHUNK")) chunk = (uint32_t)atoi(e);  // developer knob
-  while (chunk > 8 && (M / chunk) < (size_t)ctx->sm_count * 4 * ACC_THREADS / 2) chunk >>= 1;
+  // Chunk length.  Every thread does the same amount of work (one chunk), so the launch runs in lock-step waves of
+  // `cap` resident threads: pick the number of waves for chunks of at most ~256 entries (2 partial-list entries per chunk:
+  // longer chunks shrink the segmented-reduction levels), then size the chunk so that the waves are full.
+  static int occ = 0;
+  if (!occ) {
+    TKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate, ACC_THREADS, 0));
+    if (occ < 1) occ = 1;
+  }
+  const size_t cap = (size_t)ctx->sm_count * occ * ACC_THREADS;
+  uint32_t target = 256;
+  if (const char *e = getenv("TKM_MSM_CHUNK")) target = (uint32_t)atoi(e);  // developer knob
+  if (target < 8) target = 8;
+  const size_t waves = (M + cap * target - 1) / (cap * target);
+  uint32_t chunk = (uint32_t)((M + waves * cap - 1) / (waves * cap));
+  if (chunk < 8) chunk = 8;
   const size_t T = (M + chunk - 1) / chunk;
   size_t P = 2 * T;
   Scratch<uint32_t> pk_a, pk_b;
@@ -498,8 +511,11 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
   const size_t P2 = 2 * ((P + 31) / 32);
   TKM_TRY(pk_b.alloc(ctx, P2));
   TKM_TRY(pp_b.alloc(ctx, P2));
-  k_accumulate<<<(unsigned)((T + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
-      keys_s.p, vals_s.p, M, chunk, in.bases, invalid, buckets.p, pk_a.p, pp_a.p, T);
+  const unsigned acc_grid = (unsigned)((T + ACC_THREADS - 1) / ACC_THREADS);
+  TKM_CUDA(cudaEventRecord(ctx->kev0, ctx->stream));
+  k_accumulate<<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(keys_s.p, vals_s.p, M, chunk, in.bases, invalid, buckets, pk_a.p, pp_a.p, T);
+  TKM_CUDA(cudaEventRecord(ctx->kev1, ctx->stream));
+  ctx->kernel_timed = true;
   TKM_TRY(launch_check(ctx, "k_accumulate"));
 
   uint32_t *kin = pk_a.p, *kout = pk_b.p;
@@ -508,7 +524,7 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
     const size_t nwarps = (P + 31) / 32;
     const int last = nwarps == 1;
     const size_t threads = nwarps * 32;
-    k_segreduce<<<(unsigned)((threads + SEG_THREADS - 1) / SEG_THREADS), SEG_THREADS, 0, ctx->stream>>>(kin, pin, P, buckets.p, kout, pout,
+    k_segreduce<<<(unsigned)((threads + SEG_THREADS - 1) / SEG_THREADS), SEG_THREADS, 0, ctx->stream>>>(kin, pin, P, buckets, kout, pout,
                                                                                                   last, invalid);
     TKM_TRY(launch_check(ctx, "k_segreduce"));
     if (last) break;
@@ -516,7 +532,11 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
     uint32_t *tk = kin; kin = kout; kout = tk;
     G1Xyzz *tp = pin; pin = pout; pout = tp;
   }
+  return TKM_OK;
+}
 
+// Window reduction + recombination of a filled bucket set; reads back the 96-byte canonical affine result.
+static int32_t msm_reduce(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets, uint8_t out96[96]) {
   const size_t nsegs = (size_t)m.W * m.nseg;
   Scratch<G1Xyzz> seg_acc, seg_run, parts, wsum;
   Scratch<uint32_t> res;
@@ -525,7 +545,7 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
   TKM_TRY(parts.alloc(ctx, (size_t)m.W * (m.nbits + 1)));
   TKM_TRY(wsum.alloc(ctx, m.W));
   TKM_TRY(res.alloc(ctx, 24));
-  k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets.p, m, seg_acc.p, seg_run.p);
+  k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets, m, seg_acc.p, seg_run.p);
   TKM_TRY(launch_check(ctx, "k_bucket_seg"));
   {
     // slices per (window, bit): keep every thread at <= ~4 segment sums, at most 64 slices
@@ -550,6 +570,91 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
   TKM_CUDA(cudaMemcpyAsync(out96, res.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
   TKM_CUDA(cudaStreamSynchronize(ctx->stream));
   return TKM_OK;
+}
+
+int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
+  const size_t n = in.rows * in.cols;
+  if (n == 0) {  // msm_g1_bases returns the identity for empty input (group_structures/mod.rs:131-133)
+    memset(out96, 0, 96);
+    return TKM_OK;
+  }
+  if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
+  if (in.idx && in.rows != 1) return fail(TKM_ERR_INVALID_ARGUMENT, "indexed MSM must be one row");
+  const MsmGeom m = pick_geom(n, in.pre_c, in.pre_stride);
+  Scratch<G1Xyzz> buckets;
+  TKM_TRY(buckets.alloc(ctx, (size_t)m.nbuckets + 1));
+  k_fill_identity<<<grid_for((size_t)m.nbuckets + 1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, (size_t)m.nbuckets + 1);
+  TKM_TRY(launch_check(ctx, "k_fill_identity"));
+  TKM_TRY(msm_accumulate_pass(ctx, in, m, buckets.p));
+  return msm_reduce(ctx, m, buckets.p, out96);
+}
+
+// Host-buffer MSM (msm::msm with HostSlice scalars and bases, libs/src/iotools/mod.rs:2093-2099) as a pipeline: the
+// point range is cut into `pieces`; piece k's scalars and bases travel on the copy stream while piece k-1 is decomposed,
+// sorted and accumulated into its own bucket set on the compute stream (no read-modify-write in the hot loop); the sets
+// are summed bucket-wise and reduced once at the end.
+int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t pieces, uint8_t out96[96]) {
+  if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
+  if (pieces < 1) pieces = 1;
+  if (pieces > 16) pieces = 16;
+  if (!ctx->copy_stream) {
+    TKM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 17; i++) TKM_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+  }
+  const MsmGeom m = pick_geom(n);
+  Scratch<Fr> ds;
+  Scratch<G1Affine> db;
+  Scratch<G1Xyzz> buckets;
+  TKM_TRY(ds.alloc(ctx, n));
+  TKM_TRY(db.alloc(ctx, n));
+  const size_t set_stride = (size_t)m.nbuckets + 1;
+  const size_t per = (n + pieces - 1) / pieces;
+  pieces = (uint32_t)((n + per - 1) / per);
+  TKM_TRY(buckets.alloc(ctx, set_stride * pieces));
+  // the staging buffers come from the compute stream's pool: the copy stream may touch them only after this point
+  TKM_CUDA(cudaEventRecord(ctx->copy_ev[16], ctx->stream));
+  TKM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[16], 0));
+  uint32_t used = 0;
+  for (size_t off = 0; off < n; off += per, used++) {
+    const size_t cnt = (off + per <= n) ? per : n - off;
+    TKM_CUDA(cudaMemcpyAsync(ds.p + off, scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TKM_CUDA(cudaMemcpyAsync(db.p + off, bases + off * 96, cnt * 96, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TKM_CUDA(cudaEventRecord(ctx->copy_ev[used], ctx->copy_stream));
+  }
+  k_fill_identity<<<grid_for(set_stride * pieces, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, set_stride * pieces);
+  TKM_TRY(launch_check(ctx, "k_fill_identity"));
+  uint32_t k = 0;
+  int32_t st = TKM_OK;
+  for (size_t off = 0; off < n && st == TKM_OK; off += per, k++) {
+    const size_t cnt = (off + per <= n) ? per : n - off;
+    cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0);
+    if (e != cudaSuccess) {
+      st = fail(TKM_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    st = g1_to_mont_dev(ctx, db.p + off, db.p + off, cnt);
+    if (st != TKM_OK) break;
+    MsmInput in;
+    in.scalars = ds.p + off;
+    in.scalars_mont = false;
+    in.scalar_row_stride = cnt;
+    in.bases = db.p + off;
+    in.base_row_stride = cnt;
+    in.rows = 1;
+    in.cols = cnt;
+    in.idx = nullptr;
+    st = msm_accumulate_pass(ctx, in, m, buckets.p + k * set_stride);
+  }
+  if (st == TKM_OK && pieces > 1) {
+    k_bucket_merge<<<(unsigned)((m.nbuckets + 127) / 128), 128, 0, ctx->stream>>>(buckets.p, set_stride, pieces, m.nbuckets);
+    st = launch_check(ctx, "k_bucket_merge");
+  }
+  if (st != TKM_OK) {
+    // the staging buffers are freed on the compute stream when this scope ends: drain the copies first
+    cudaStreamSynchronize(ctx->copy_stream);
+    return st;
+  }
+  return msm_reduce(ctx, m, buckets.p, out96);
 }
 
 }  // namespace tkm

@@ -380,9 +380,13 @@ int32_t bintt_dev(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x, size_t y, int d
   const bool inverse = dir == TKM_INVERSE;
   const bool coset_y_on = coset_y && !(*coset_y == Fr::one());
   const bool defer = inverse && !coset_y_on;
+  TKM_CUDA(cudaEventRecord(ctx->kev0, ctx->stream));
   TKM_TRY(ntt_axis_impl(ctx, in, out, x, y, 1, dir, coset_y, nullptr, defer));
   const Fr *extra = defer ? &ctx->inv_pow2[log2_exact(y)] : nullptr;
-  return ntt_axis_impl(ctx, out, out, 1, x, y, dir, coset_x, extra);
+  TKM_TRY(ntt_axis_impl(ctx, out, out, 1, x, y, dir, coset_x, extra));
+  TKM_CUDA(cudaEventRecord(ctx->kev1, ctx->stream));
+  ctx->kernel_timed = true;
+  return TKM_OK;
 }
 
 // ---- domain ---------------------------------------------------------------------------------

@@ -97,6 +97,12 @@ class Context:
         check(self.lib.tkm_launch_count(self.h, ctypes.byref(v)))
         return v.value
 
+    def kernel_time_last(self):
+        """Milliseconds of the most recent dominant-kernel launch (k_accumulate / the k_ntt_pass launches of a biNTT)."""
+        ms = ctypes.c_float()
+        check(self.lib.tkm_kernel_time_last(self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
     def microbench(self, kind):
         v = ctypes.c_double()
         check(self.lib.tkm_microbench(self.h, kind, ctypes.byref(v)))

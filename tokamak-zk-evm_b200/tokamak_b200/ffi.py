@@ -85,6 +85,7 @@ SIGNATURES = {
     "tkm_event_time_end": [c_void_p, P(ctypes.c_float)],
     "tkm_launch_count": [c_void_p, P(c_uint64)],
     "tkm_microbench": [c_void_p, c_int32, P(ctypes.c_double)],
+    "tkm_kernel_time_last": [c_void_p, P(ctypes.c_float)],
 }
 STRING_FUNCS = ("tkm_last_error", "tkm_version")
 
