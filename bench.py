@@ -56,59 +56,61 @@ def random_scalars(seed, n):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons; started before the warm-up so that samples exist for short
-    timed regions, summarised over the [t0, t1] window of the timed region."""
+    """Samples SM clock / throttle reasons / power through NVML from a background thread (in-process: an `nvidia-smi -lms`
+    loop beside the benchmark was seen to stall kernel launches for tens of ms); started before the warm-up so that samples
+    exist for short timed regions, summarised over the [t0, t1] window of the timed region."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    PERIOD_S = 0.1
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []  # (t, sm_mhz, max_mhz, power_w, reasons_bitmask)
+        self.ok = False
+        self._stop = threading.Event()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            self.nv = nv
+            self.dev = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.dev, nv.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.ok = False
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                self.samples.append((time.perf_counter(), sm, self.max_mhz, pw, rs))
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
 
     def summary(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm, mx, reasons, power = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, ln in self.lines:
-            if ts < t0 or ts > t1 + 0.06:
-                continue
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-                power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(power) if power else None}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        # NVML clocks-event-reason bits
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        sel = [x for x in self.samples if t0 <= x[0] <= t1 + self.PERIOD_S]
+        if not sel and self.samples:  # very short region: take the nearest sample
+            sel = [min(self.samples, key=lambda x: abs(x[0] - t1))]
+        reasons = sorted({nm for x in sel for nm, b in bits.items() if x[4] & b})
+        return {"sm_mhz": float(np.median([x[1] for x in sel])) if sel else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sel), "power_w_max": max(x[3] for x in sel) if sel else None, "source": "NVML, in-process thread, 100 ms period"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -233,8 +235,12 @@ def main():
         l0 = ctx.launch_count()
         ctx.time_begin()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(steps):
+            ts = time.perf_counter()
             res = fn()
+            per_step.append((time.perf_counter() - ts) * 1e3)  # every step ends with a synchronous 96-byte read-back
+        timed.last_per_step = per_step
         ms = ctx.time_end()
         t1 = time.perf_counter()
         wall = (t1 - t0) * 1e3
@@ -266,6 +272,7 @@ def main():
                    "log2_points_per_gpu": args.log_n, "parallelism": f"point-range shards x{world}, partial sums all-gathered and combined on rank 0" if world > 1 else "single GPU",
                    "l2": "inputs (0.5 GiB) larger than the 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches),
+        "ms_per_step_host_clock": {"min": min(timed.last_per_step), "max": max(timed.last_per_step), "all": [round(x, 3) for x in timed.last_per_step]},
     }
 
     if not args.skip_aux:
