@@ -123,6 +123,8 @@ int32_t tkm_msm_g1(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, 
                    uint8_t out96[96]);
 /* Canonical affine bytes on the device -> Montgomery-form base table (in place allowed). */
 int32_t tkm_g1_bases_to_mont(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
+/* The inverse conversion (device Montgomery affine -> canonical), e.g. to write a generated CRS table out. */
+int32_t tkm_g1_bases_from_mont(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
 /* Strided rectangle (the trimmed (deg_x+1) x (deg_y+1) rectangle encode_poly commits,
  * iotools/mod.rs:2061-2088): scalar (i,j) at dev_scalars[i*scalar_row_stride + j],
  * base (i,j) at bases[i*base_row_stride + j], i < rows, j < cols. */

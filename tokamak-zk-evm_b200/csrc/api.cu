@@ -392,6 +392,11 @@ int32_t tkm_g1_bases_to_mont(tkm_ctx *ctx, const void *in, void *out, size_t n) 
   return g1_to_mont_dev(ctx, (const G1Affine *)in, (G1Affine *)out, n);
 }
 
+int32_t tkm_g1_bases_from_mont(tkm_ctx *ctx, const void *in, void *out, size_t n) {
+  API_BEGIN
+  return g1_from_mont_dev(ctx, (const G1Affine *)in, (G1Affine *)out, n);
+}
+
 int32_t tkm_msm_g1_rect(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, size_t s_stride, const void *bases, size_t b_stride,
                         size_t rows, size_t cols, uint8_t out96[96]) {
   API_BEGIN

@@ -139,6 +139,7 @@ int32_t bintt_dev(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x, size_t y, int d
                   const Fr *coset_y);
 int32_t ntt_axis(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, size_t n, size_t inner, int dir, const Fr *coset);
 int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n);
+int32_t g1_from_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n);
 struct MsmInput {
   const Fr *scalars;
   bool scalars_mont;

@@ -391,6 +391,15 @@ __global__ void __launch_bounds__(256) k_g1_to_mont(const G1Affine *__restrict__
   }
 }
 
+__global__ void __launch_bounds__(256) k_g1_from_mont(const G1Affine *__restrict__ in, G1Affine *__restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    G1Affine a = in[i];
+    a.x = a.x.from_mont();
+    a.y = a.y.from_mont();
+    out[i] = a;
+  }
+}
+
 // Fixed-base tables for a resident CRS: out[w*n + i] = 2^(c*w) * P_i in affine form, w < W.  With them every digit
 // window of a commitment lands in ONE shared bucket set (no per-window reduction, no Horner tail) and the window can be
 // wider (fewer additions per point).  One thread per base: c*(W-1) doublings, then all W-1 conversions to affine share a
@@ -570,6 +579,12 @@ static int32_t msm_reduce(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets,
   TKM_CUDA(cudaMemcpyAsync(out96, res.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
   TKM_CUDA(cudaStreamSynchronize(ctx->stream));
   return TKM_OK;
+}
+
+int32_t g1_from_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n) {
+  if (n == 0) return TKM_OK;
+  k_g1_from_mont<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);
+  return launch_check(ctx, "k_g1_from_mont");
 }
 
 int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {

@@ -45,6 +45,7 @@ SIGNATURES = {
     "tkm_msm_g1_host": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_msm_g1": [c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p],
     "tkm_g1_bases_to_mont": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "tkm_g1_bases_from_mont": [c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_msm_g1_rect": [c_void_p, c_void_p, c_int32, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p],
     "tkm_msm_g1_indexed": [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_g1_fixed_base_mul": [c_void_p, c_void_p, c_void_p, c_int32, c_size_t, c_void_p],

@@ -1,0 +1,156 @@
+"""The product backend of the protocol driver: every polynomial, commitment and sparse MSM runs on the B200 through the
+C-ABI of libtokamak_b200 (no CPU fallback: constructing it without a GPU fails in tkm_ctx_create).
+
+The driver talks to a backend through this small surface (the oracle-backed twin used by the tests lives in
+oracle/oracle_backend.py and implements the same methods):
+  from_coeffs / from_rou_evals -> polynomial with  + - * (poly | int), mul_monomial, scale_coeffs_x/y, eval,
+                                   div_by_vanishing_opt, div_by_ruffini, to_rou_evals, clone
+  make_table(col, row, base)    -> G1 table  T[j][i] = col[j] * row[i] * base   (Sigma1 components)
+  commit(table, poly)           -> sum_ij c_ij T[i][j]                          (Sigma1::encode_poly)
+  msm_indexed(table, idx, s)    -> sum_k s_k T.flat[idx_k]                      (msm_g1_bases over gathered rows)
+  g1_add / g1_sub / g1_mul, recursion_evals
+G1 points cross this interface as (x, y) integer tuples, None = identity."""
+import ctypes
+
+import numpy as np
+
+from .. import DensePolynomialExt, _as_fr_array, _vp, check, frs_from_ints
+from .fr import R_MOD
+
+
+def g1_to_tuple(a):
+    b = np.ascontiguousarray(a, dtype=np.uint64).reshape(12).tobytes()
+    x, y = int.from_bytes(b[:48], "little"), int.from_bytes(b[48:], "little")
+    return None if x == 0 and y == 0 else (x, y)
+
+
+def g1_from_tuple(p):
+    if p is None:
+        return np.zeros(12, dtype=np.uint64)
+    return np.frombuffer(p[0].to_bytes(48, "little") + p[1].to_bytes(48, "little"), dtype=np.uint64).copy()
+
+
+class GpuTable:
+    def __init__(self, ctx, handle, rows, cols):
+        self.ctx, self.h, self.rows, self.cols = ctx, handle, rows, cols
+
+    def device_ptr(self):
+        p = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_crs_device_ptr(self.h, ctypes.byref(p), None, None))
+        return p.value
+
+    def points_host(self):
+        """Canonical affine points (rows*cols, 12) -- test/debug only."""
+        n = self.rows * self.cols
+        tmp = self.ctx.dev_alloc(n * 96)
+        check(self.ctx.lib.tkm_g1_bases_from_mont(self.ctx.h, self.device_ptr(), tmp, n))
+        out = np.empty((n, 12), dtype=np.uint64)
+        self.ctx.d2h(out, tmp)
+        self.ctx.dev_free(tmp)
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tkm_crs_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GpuBackend:
+    name = "b200"
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    # ---- polynomials
+    def from_coeffs(self, coeffs, x_size, y_size):
+        return DensePolynomialExt.from_coeffs(self.ctx, coeffs, x_size, y_size)
+
+    def from_rou_evals(self, evals, x_size, y_size):
+        return DensePolynomialExt.from_rou_evals(self.ctx, evals, x_size, y_size)
+
+    def init_ntt_domain(self, size):
+        self.ctx.init_ntt_domain_for_size(size)
+
+    # ---- G1 tables (Sigma1 components), built and kept on the device
+    def make_table(self, col, row, base):
+        ctx = self.ctx
+        rows, cols = len(col), len(row)
+        n = rows * cols
+        d_col = ctx.upload_fr(frs_from_ints(col))
+        d_row = ctx.upload_fr(frs_from_ints(row))
+        d_s = ctx.dev_alloc(n * 32)
+        check(ctx.lib.tkm_fr_outer_product(ctx.h, d_col, d_row, d_s, rows, cols))
+        d_pts = ctx.dev_alloc(n * 96)
+        b = g1_from_tuple(base)
+        check(ctx.lib.tkm_g1_fixed_base_mul(ctx.h, _vp(b), d_s, 1, n, d_pts))
+        for p in (d_col, d_row, d_s):
+            ctx.dev_free(p)
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_crs_from_device(ctx.h, d_pts, rows, cols, 1, ctypes.byref(h)))
+        return GpuTable(ctx, h, rows, cols)
+
+    def table_from_points(self, points, rows, cols):
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_crs_upload(self.ctx.h, _vp(pts), rows, cols, ctypes.byref(h)))
+        return GpuTable(self.ctx, h, rows, cols)
+
+    def commit(self, table, poly):
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.ctx.lib.tkm_poly_commit(self.ctx.h, poly.h, table.h, _vp(out)))
+        return g1_to_tuple(out)
+
+    def msm_indexed(self, table, idx, scalars):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        s = _as_fr_array(scalars)
+        n = idx.shape[0]
+        if n == 0:
+            return None
+        assert s.shape[0] == n
+        ctx = self.ctx
+        d_s = ctx.upload_fr(s, to_mont=False)
+        d_i = ctx.dev_alloc(n * 4)
+        ctx.h2d(d_i, idx)
+        out = ctx.msm_g1_indexed_dev(d_s, False, table.device_ptr(), d_i, n)
+        ctx.dev_free(d_s)
+        ctx.dev_free(d_i)
+        return g1_to_tuple(out)
+
+    # ---- G1serde ops
+    def g1_add(self, a, b):
+        return g1_to_tuple(self.ctx.g1_add(g1_from_tuple(a), g1_from_tuple(b)))
+
+    def g1_neg(self, a):
+        from .fr import Q_MOD
+
+        return None if a is None else (a[0], (-a[1]) % Q_MOD)
+
+    def g1_sub(self, a, b):
+        return self.g1_add(a, self.g1_neg(b))
+
+    def g1_mul(self, a, k):
+        return g1_to_tuple(self.ctx.g1_mul(g1_from_tuple(a), k % R_MOD))
+
+    # ---- prove1's recursion polynomial
+    def recursion_evals(self, f_evals, g_evals, m_i, s_max):
+        """r(X,Y) on the grid (prove/src/lib.rs:1853-1870): scalers = g/f, transposed to placement-major order,
+        r[last] = 1, r[k] = r[k+1] * scalers[k+1], transposed back.  All on the device."""
+        ctx = self.ctx
+        n = m_i * s_max
+        d_f = ctx.upload_fr(_as_fr_array(f_evals))
+        d_g = ctx.upload_fr(_as_fr_array(g_evals))
+        d_t = ctx.dev_alloc(n * 32)
+        check(ctx.lib.tkm_fr_vec_op(ctx.h, 3, d_g, d_f, d_g, n))  # OP_DIV
+        check(ctx.lib.tkm_fr_transpose(ctx.h, d_g, d_t, m_i, s_max))
+        check(ctx.lib.tkm_fr_suffix_product(ctx.h, d_t, d_f, n))
+        check(ctx.lib.tkm_fr_transpose(ctx.h, d_f, d_g, s_max, m_i))
+        out = ctx.download_fr(d_g, n)
+        for p in (d_f, d_g, d_t):
+            ctx.dev_free(p)
+        return out

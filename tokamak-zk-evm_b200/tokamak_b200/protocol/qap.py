@@ -1,0 +1,87 @@
+"""Sparse R1CS products: the QAP mixture o_j(tau) for setup and the u/v/w evaluation tables of a
+placement list for the prover.  Host side like the reference's (rayon loops over sparse rows, iotools/mod.rs:1380-1608)."""
+import numpy as np
+
+from .fr import R_MOD, lagrange_bases_at
+
+
+def o_evaled(params, infos, r1cs_list, tau):
+    """o_vec[j] = alpha u_j(x) + alpha^2 v_j(x) + alpha^3 w_j(x) for every global wire j
+    (from_r1cs_to_evaled_qap_mixture, libs/src/field_structures/mod.rs:73-151; scatter by flattenMap,
+    setup/trusted-setup/src/main.rs:128-164).  u_j(X) = sum_rows A[row][j] K_row(X) over the n-th roots of unity."""
+    lag = lagrange_bases_at(tau.x, params.n)
+    a1, a2, a3 = tau.alpha % R_MOD, pow(tau.alpha, 2, R_MOD), pow(tau.alpha, 3, R_MOD)
+    o = [0] * params.m_D
+    for info, r in zip(infos, r1cs_list):
+        local = [0] * info.Nwires
+        for row, (a, b, c) in enumerate(r.constraints):
+            lr = lag[row]
+            for lc, scale in ((a, a1), (b, a2), (c, a3)):
+                f = lr * scale % R_MOD
+                for wire, coeff in lc:
+                    local[wire] = (local[wire] + coeff * f) % R_MOD
+        for loc, g in enumerate(info.flattenMap):
+            if local[loc]:
+                o[g] = local[loc]
+    return o
+
+
+def uvw_evals(params, placements, r1cs_list):
+    """Evaluation tables of u, v, w on the n x s_max grid, row-major [row][placement] (read_R1CS_gen_uvwXY +
+    eval_uvwxy_sparse_rows, iotools/mod.rs:1287-1420; the transpose at :1363-1365 is folded into the indexing).
+    Returns three (n*s_max, 4) uint64 arrays of canonical little-endian limbs."""
+    n, s_max = params.n, params.s_max
+    if len(placements) > s_max:
+        raise ValueError("placement_variables length exceeds s_max.")
+    out = [np.zeros((n * s_max, 4), dtype=np.uint64) for _ in range(3)]
+    mask = (1 << 64) - 1
+    for col, pl in enumerate(placements):
+        var = pl.variables
+        for row, abc in enumerate(r1cs_list[pl.subcircuitId].constraints):
+            for m in range(3):
+                lc = abc[m]
+                if not lc:
+                    continue
+                acc = 0
+                for wire, coeff in lc:
+                    acc += coeff * var[wire]
+                acc %= R_MOD
+                if acc:
+                    out[m][row * s_max + col] = (acc & mask, (acc >> 64) & mask, (acc >> 128) & mask, acc >> 192)
+    return out
+
+
+def interface_evals(params, placements, infos):
+    """Evaluation table of b(X,Y) on the m_I x s_max grid (gen_bXY, libs/src/polynomial_structures/mod.rs:132-162)."""
+    l, l_d, s_max = params.l, params.l_D, params.s_max
+    out = np.zeros(((l_d - l) * s_max, 4), dtype=np.uint64)
+    mask = (1 << 64) - 1
+    for col, pl in enumerate(placements):
+        fmap = infos[pl.subcircuitId].flattenMap
+        if len(fmap) != len(pl.variables):
+            raise ValueError("Corrupted placement variables.")
+        for g, v in zip(fmap, pl.variables):
+            if l <= g < l_d and v:
+                out[(g - l) * s_max + col] = (v & mask, (v >> 64) & mask, (v >> 128) & mask, v >> 192)
+    return out
+
+
+def permutation_evals(permutation, m_i, s_max, omega_m_i, omega_s_max):
+    """Evaluation tables of s0, s1 (Permutation::to_poly, iotools/mod.rs:419-455): identity w_x^row, w_y^col except at the
+    listed (row, col), which point to (X, Y)."""
+    from .fr import powers
+
+    xp, yp = powers(omega_m_i, m_i), powers(omega_s_max, s_max)
+    mask = (1 << 64) - 1
+
+    def limbs(v):
+        return (v & mask, (v >> 64) & mask, (v >> 128) & mask, v >> 192)
+
+    xl = np.array([limbs(v) for v in xp], dtype=np.uint64)
+    yl = np.array([limbs(v) for v in yp], dtype=np.uint64)
+    s0 = np.repeat(xl, s_max, axis=0)
+    s1 = np.tile(yl, (m_i, 1))
+    for p in permutation:
+        s0[p.row * s_max + p.col] = xl[p.X]
+        s1[p.row * s_max + p.col] = yl[p.Y]
+    return s0, s1
