@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="developer override of the MSM size (the graded config is 22)")
     ap.add_argument("--skip-aux", action="store_true", help="skip the biNTT / cpu-baseline / e2e legs (profiling runs)")
-    ap.add_argument("--skip-replay", action="store_true", help="skip the prove-shaped operation replay leg")
+    ap.add_argument("--skip-prove", action="store_true", help="skip the full-prove leg (setup + prove0..4 + verify at the reference shape)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -374,33 +374,39 @@ def main():
                                     "sample": f"first 2^{ls} points of the same inputs, oracle/oracle.c Pippenger (OpenMP); result compared bit-exactly with the GPU",
                                     "bintt": {"value": x2 * y2 / dt_ntt / 1e9, "unit": "Gelem/s", "sample": "4096x256 forward biNTT, oracle/oracle.c radix-2 (OpenMP)"},
                                     "published_reference": "ICICLE CPU backend: 1.01 Mpts/s at 8192x511 pts; biNTT 2^23 forward 497 ms (unnamed macOS host, BASELINE.md)"}
-    if rank == 0 and world == 1 and not args.skip_aux and not args.skip_replay:
-        # ---- operation replay of one prove at the reference's circuit shape: the third part of
-        # BASELINE.json's metric ("prove s/tx") restricted to the hot path that exists so far (no protocol driver yet)
+    if rank == 0 and world == 1 and not args.skip_aux and not args.skip_prove:
+        # ---- "prove s/tx" (first part of BASELINE.json's metric): full Prover.init + prove0..prove4 on this GPU at the
+        # reference's circuit shape, proof checked by the restated verifier; then the CPU baseline beside it on a bounded
+        # sample (every extent / 4), where the GPU and CPU proofs must be byte-identical
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
-        import prove_replay
+        import copy
 
-        ctx.init_ntt_domain_for_size(1 << 23)
-        sigma, table = prove_replay.make_sigma(ctx)
-        prove_replay.run(ctx, sigma, table)  # warm-up
-        runs = [prove_replay.run(ctx, sigma, table) for _ in range(3)]
-        runs.sort(key=lambda o: o["hot_path_s"])
-        rep = runs[1]  # median of 3
-        rep["all_runs_hot_path_s"] = [round(o["hot_path_s"], 4) for o in runs]
-        rep.pop("detail_ms", None)
-        line["prove_replay"] = rep
-        # serving mode: one CRS reused across proofs -> fixed-base tables (13 x 384 MiB at c = 20) built once
-        t0 = time.perf_counter()
-        sigma.precompute(20)
-        ctx.sync()
-        t_tables = time.perf_counter() - t0
-        prove_replay.run(ctx, sigma, table)
-        runs = sorted((prove_replay.run(ctx, sigma, table) for _ in range(3)), key=lambda o: o["hot_path_s"])
-        line["prove_replay_fixed_base_tables"] = {"hot_path_s": runs[1]["hot_path_s"], "encode_s": runs[1]["encode_s"], "poly_s": runs[1]["poly_s"],
-                                                  "ntt_s": runs[1]["ntt_s"], "table_build_s_once_per_crs": t_tables, "window_bits": 20,
-                                                  "table_bytes": 13 * 8192 * 512 * 96,
-                                                  "all_runs_hot_path_s": [round(o["hot_path_s"], 4) for o in runs]}
-        sigma.close()
+        import prove_full
+        from tokamak_b200.protocol import synthetic as S
+        from tokamak_b200.protocol.backend import GpuBackend
+
+        for p_ in (d_bases, d_scalars):
+            ctx.dev_free(p_)
+        gpu_be = GpuBackend(ctx)
+        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync)
+        full["reference"] = {"cpu_prove_s": 45.7, "icicle_cuda_prove_s": 21.08, "stage_split_cpu_s": [5.21, 10.09, 2.13, 13.37, 1.56, 13.33],
+                             "stage_split_icicle_cuda_s": [0.72, 4.03, 0.78, 7.27, 0.90, 7.37],
+                             "source": "BASELINE.md (reference's own artifacts, unnamed hosts, real template tx, 166 placements)"}
+        line["prove"] = {"metric": "prove s/tx", "value": full["prove_s"], "unit": "s", "higher_is_better": False, **full}
+        small = prove_full.run(gpu_be, prove_full.reduced_shape(), repeats=3, verify=False, sync=ctx.sync, keep_sigma=True)
+        from oracle_backend import OracleBackend, OracleTable
+
+        sg = copy.copy(small.pop("_sigma"))
+        for name in ("xy_powers", "gamma_inv_o_inst", "eta_inv_li_o_inter_alpha4_kj", "delta_inv_li_o_prv"):
+            t_ = getattr(sg, name)
+            setattr(sg, name, OracleTable(t_.points_host(), t_.rows, t_.cols))
+        cpu = prove_full.run(OracleBackend(), prove_full.reduced_shape(), repeats=1, verify=False, sigma=sg)
+        assert cpu["proof_sha256"] == small["proof_sha256"], "GPU proof and CPU-oracle proof differ on the reduced shape"
+        line.setdefault("cpu_baseline", {})["prove"] = {
+            "value": cpu["prove_s"], "unit": "s", "cores": O.num_threads(), "kind": "port",
+            "sample": "reference shape with every extent / 4 (n=1024, s_max=64, m_I=1024; 1/16 of the MSM and NTT work): protocol driver on "
+                      "the oracle backend (oracle/oracle.c, OpenMP); proof byte-identical to the GPU proof of the same input",
+            "gpu_same_sample_s": small["prove_s"], "cpu_stage_s": {k: cpu["median_run"][k] for k in ("init_s", "prove0_s", "prove1_s", "prove2_s", "prove3_s", "prove4_s", "encode_s")}}
     if world > 1 and not args.skip_aux:
         # ---- row-sharded bivariate NTT with the X<->Y transpose as an NCCL all-to-all
         from tokamak_b200 import dist as D

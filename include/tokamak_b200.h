@@ -168,6 +168,16 @@ int32_t tkm_poly_from_evals_host(tkm_ctx *ctx, const uint8_t *evals, size_t x_si
                                  const uint8_t *coset_x32, const uint8_t *coset_y32, tkm_poly **out);
 /* from_coeffs with a DeviceSlice (:1527-1551): copies x_size*y_size Montgomery-form elements from dev_coeffs. */
 int32_t tkm_poly_from_device(tkm_ctx *ctx, const void *dev_coeffs, size_t x_size, size_t y_size, tkm_poly **out);
+/* read_R1CS_gen_uvwXY (libs/src/iotools/mod.rs:1287-1420): the sparse R1CS x witness products of every placement, as
+ * the three witness polynomials u, v, w of shape n x s_max (evaluation tables [row][placement] built on the device, then
+ * one inverse biNTT each).  All pointers are HOST arrays: the library's constraints as concatenated CSR (row_ptr /
+ * wire / coeff, rp_base[3*s + m] = start of (subcircuit s, matrix m)'s row pointers, n_rows[s] constraints), the
+ * placement list (sub_of_col[c] = subcircuit of column c or 0xffffffff, var_off[c] = offset of its variables in
+ * witness32) and the variables as 32-byte canonical scalars. */
+int32_t tkm_r1cs_uvw_polys(tkm_ctx *ctx, uint32_t s_D, const uint32_t *n_rows, const uint64_t *rp_base, const uint32_t *row_ptr,
+                           size_t row_ptr_len, const uint32_t *wire, const uint8_t *coeff32, size_t nnz, const uint32_t *sub_of_col,
+                           const uint64_t *var_off, const uint8_t *witness32, size_t n_vars, size_t n, size_t s_max, tkm_poly **out_u,
+                           tkm_poly **out_v, tkm_poly **out_w);
 int32_t tkm_poly_zero(tkm_ctx *ctx, size_t x_size, size_t y_size, tkm_poly **out);
 int32_t tkm_poly_clone(tkm_ctx *ctx, const tkm_poly *p, tkm_poly **out); /* Clone (:520-530) */
 int32_t tkm_poly_free(tkm_ctx *ctx, tkm_poly *p);

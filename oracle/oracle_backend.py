@@ -128,6 +128,13 @@ class OracleBackend:
     def init_ntt_domain(self, size):
         pass
 
+    def uvw_polys(self, params, csr, wt):
+        """read_R1CS_gen_uvwXY literally: per-placement sparse-row dot products on Python integers, then three INTTs."""
+        from tokamak_b200.protocol import qap
+
+        u, v, w = qap.uvw_evals(params, wt.placements, csr.r1cs_list)
+        return tuple(self.from_rou_evals(e, params.n, params.s_max) for e in (u, v, w))
+
     def from_coeffs(self, coeffs, x, y):
         return OraclePoly(np.array(coeffs, dtype=np.uint64, copy=True), x, y)
 
@@ -159,6 +166,10 @@ class OracleBackend:
         if idx.shape[0] == 0:
             return None
         return O.g1_to_tuple(O.msm_g1(np.ascontiguousarray(scalars, dtype=np.uint64), np.ascontiguousarray(table.points[idx])))
+
+    def msm_points(self, points, scalars):
+        pts = np.stack([O.g1_from_tuple(p) for p in points])
+        return O.g1_to_tuple(O.msm_g1(O.frs_from_ints([k % R_MOD for k in scalars]), pts))
 
     def g1_add(self, a, b):
         return O.g1_to_tuple(O.g1_add(O.g1_from_tuple(a), O.g1_from_tuple(b)))

@@ -1,0 +1,55 @@
+"""Full prove on the B200 through the protocol driver: the GPU backend and the oracle backend
+must produce byte-identical proof.json contents under fixed blinding, and the restated verifier must accept."""
+import numpy as np
+import pytest
+
+from tokamak_b200.protocol import formats as F
+from tokamak_b200.protocol import preprocess as PP
+from tokamak_b200.protocol import prover as PV
+from tokamak_b200.protocol import setup as ST
+from tokamak_b200.protocol import synthetic as S
+from tokamak_b200.protocol import verifier as VF
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backends():
+    import tokamak_b200 as T
+    from oracle_backend import OracleBackend
+    from tokamak_b200.protocol.backend import GpuBackend
+
+    ctx = T.Context(0)
+    yield GpuBackend(ctx), OracleBackend()
+    ctx.close()
+
+
+def _small_shape():
+    return S.LibrarySpec(n=64, s_max=16, m_i=256, l_user_out=4, l_user=8, l_free=16, l=32, n_prv_in=10, compute=[
+        S.ComputeSpec("ALU1", 2, 5, 40), S.ComputeSpec("Poseidon", 2, 6, 64), S.ComputeSpec("Accumulator", 1, 16, 9),
+        S.ComputeSpec("DecToBit", 30, 2, 31)])
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small"])
+def test_gpu_proof_is_byte_identical_to_oracle_proof(backends, shape):
+    gpu, orc = backends
+    spec = S.tiny_shape() if shape == "tiny" else _small_shape()
+    params, infos, r1cs = S.make_library(spec, seed=3)
+    pl, perm, inst = S.synthesize(params, infos, r1cs, seed=4, small_value_fraction=0.3)
+    tau = ST.Tau.gen_fixed()
+    out = {}
+    for be in (gpu, orc):
+        sigma = ST.generate(be, params, infos, r1cs, tau)
+        pv = PV.Prover(be, params, infos, r1cs, sigma, pl, perm, inst, mixer=PV.Mixer.fixed(), checks=True)
+        points, scalars, fmt, p4t = PV.prove(pv)
+        pre = PP.preprocess(be, params, sigma, perm, inst)
+        out[be.name] = (sigma, points, scalars, fmt, pre)
+    sg, so = out["b200"][0], out["oracle"][0]
+    for name in ("xy_powers", "gamma_inv_o_inst", "eta_inv_li_o_inter_alpha4_kj", "delta_inv_li_o_prv"):
+        assert np.array_equal(getattr(sg, name).points_host(), getattr(so, name).points_host()), name
+    assert out["b200"][3] == out["oracle"][3], "proof.json differs between the GPU path and the oracle path"
+    assert F.format_preprocess(out["b200"][4]) == F.format_preprocess(out["oracle"][4])
+    sigma, points, scalars, fmt, pre = out["b200"]
+    assert VF.verify_snark(params, sigma, pre, inst, points, scalars)
+    bad = dict(scalars, R_eval=(scalars["R_eval"] + 1) % VF.R_MOD)
+    assert not VF.verify_snark(params, sigma, pre, inst, points, bad)

@@ -1,0 +1,158 @@
+"""Protocol layer on the host (no GPU): the restated setup -> prove0..4 -> preprocess -> verify flow runs end to end on the
+oracle backend, the restated verifier accepts the proof and rejects tampered ones, the file formats round-trip, and the
+pairing is pinned by the production verifier CRS embedded in the reference's browser verifier (tests/golden)."""
+import copy
+import json
+import os
+
+import pytest
+
+import pyref as P
+from tokamak_b200.protocol import formats as F
+from tokamak_b200.protocol import fr
+from tokamak_b200.protocol import pairing as PR
+from tokamak_b200.protocol import preprocess as PP
+from tokamak_b200.protocol import prover as PV
+from tokamak_b200.protocol import setup as ST
+from tokamak_b200.protocol import synthetic as S
+from tokamak_b200.protocol import verifier as VF
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _kat():
+    d = json.load(open(os.path.join(HERE, "golden", "verifier_crs_kat.json")))["points"]
+    g1 = lambda k: (int(d[k]["x"], 16), int(d[k]["y"], 16))
+    g2 = lambda k: ((int(d[k]["x"][0], 16), int(d[k]["x"][1], 16)), (int(d[k]["y"][0], 16), int(d[k]["y"][1], 16)))
+    return d, g1, g2
+
+
+def test_production_crs_points_decode_on_curve():
+    d, g1, g2 = _kat()
+    for k, v in d.items():
+        assert (P.g1_is_on_curve(g1(k)) if v["group"] == "G1" else PR.g2_is_on_curve(g2(k))), k
+    assert g1("G") == P.G1_GEN and g2("H") == PR.G2_GEN
+
+
+def test_pairing_kat_production_crs():
+    """e(sigma1.x, H) = e(G, sigma2.x) and the same for y: real reference artefacts pin the pairing."""
+    _, g1, g2 = _kat()
+    assert PR.pairing_products_equal([g1("sigma1.x")], [g2("H")], [g1("G")], [g2("sigma2.x")])
+    assert PR.pairing_products_equal([g1("sigma1.y")], [g2("H")], [g1("G")], [g2("sigma2.y")])
+    assert not PR.pairing_products_equal([g1("sigma1.x")], [g2("H")], [g1("G")], [g2("sigma2.y")])
+
+
+def test_pairing_bilinear_and_fixed_generators():
+    assert P.g1_is_on_curve(ST.G1_FIXED) and PR.g2_is_on_curve(ST.G2_FIXED)
+    assert PR.g2_mul(ST.G2_FIXED, PR.R) is None
+    a, b = 0x1234567, 0x7654321
+    assert PR.pairing_products_equal([P.g1_mul(ST.G1_FIXED, a)], [PR.g2_mul(ST.G2_FIXED, b)], [P.g1_mul(ST.G1_FIXED, a * b)], [ST.G2_FIXED])
+
+
+def test_lagrange_bases_match_inverse_ntt_of_powers():
+    """gen_evaled_lagrange_bases is defined through an inverse NTT of the power vector (vector_operations/mod.rs:19-28)."""
+    val, size = 0xABCDEF0123456789, 16
+    assert fr.lagrange_bases_at(val, size) == P.ntt(fr.powers(val, size), inverse=True)
+    w = fr.root_of_unity(size)
+    assert fr.lagrange_bases_at(pow(w, 3, fr.R_MOD), size) == [1 if k == 3 else 0 for k in range(size)]
+
+
+def test_formats_roundtrip(tmp_path):
+    params, infos, r1cs = S.make_library(S.tiny_shape())
+    pl, perm, inst = S.synthesize(params, infos, r1cs)
+    F.write_library(str(tmp_path / "lib"), params, infos, r1cs)
+    F.write_synthesizer_output(str(tmp_path / "syn"), pl, perm, inst)
+    assert F.read_library(str(tmp_path / "lib")) == (params, infos, r1cs)
+    assert F.read_synthesizer_output(str(tmp_path / "syn")) == (pl, perm, inst)
+    for p in pl:
+        assert S.check_r1cs(r1cs[p.subcircuitId], p.variables)
+    with open(tmp_path / "lib" / "r1cs" / "subcircuit0.r1cs", "r+b") as f:
+        f.write(b"xxxx")
+    with pytest.raises(ValueError):
+        F.read_r1cs(str(tmp_path / "lib" / "r1cs" / "subcircuit0.r1cs"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_r1cs_reader_on_the_reference_library():
+    lib = "/root/reference/packages/frontend/qap-compiler/subcircuits/library"
+    infos = json.load(open(os.path.join(lib, "subcircuitInfo.json")))
+    for s in infos:
+        r = F.read_r1cs(os.path.join(lib, "r1cs", f"subcircuit{s['id']}.r1cs"))
+        assert (r.n_wires, r.n_constraints) == (s["Nwires"], s["Nconsts"])
+    ref = json.load(open(os.path.join(lib, "setupParams.json")))
+    mine, _, _ = S.make_library(S.reference_shape())
+    for k in ("l_free", "l", "l_user_out", "l_user", "l_D", "n", "s_D", "s_max"):
+        assert getattr(mine, k) == ref[k], k
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from oracle_backend import OracleBackend
+
+    be = OracleBackend()
+    params, infos, r1cs = S.make_library(S.tiny_shape())
+    pl, perm, inst = S.synthesize(params, infos, r1cs)
+    sigma = ST.generate(be, params, infos, r1cs, ST.Tau.gen_fixed())
+    pv = PV.Prover(be, params, infos, r1cs, sigma, pl, perm, inst, mixer=PV.Mixer.fixed(), checks=True)
+    points, scalars, fmt, p4t = PV.prove(pv)
+    pre = PP.preprocess(be, params, sigma, perm, inst)
+    return dict(be=be, params=params, sigma=sigma, inst=inst, points=points, scalars=scalars, fmt=fmt, p4t=p4t, pre=pre, infos=infos, r1cs=r1cs, pl=pl, perm=perm)
+
+
+def test_setup_identities(tiny):
+    """The checks trusted-setup runs on its own output (setup/trusted-setup/src/main.rs:222-246): xy_powers[2 s_max] = x G,
+    xy_powers[1] = y G, encode_poly(P) = P(x, y) G."""
+    be, sigma, params = tiny["be"], tiny["sigma"], tiny["params"]
+    tau = ST.Tau.gen_fixed()
+    pts = sigma.xy_powers.points_host()
+    from oracle_ffi import g1_to_tuple
+
+    assert g1_to_tuple(pts[2 * params.s_max]) == P.g1_mul(ST.G1_FIXED, tau.x) == sigma.x
+    assert g1_to_tuple(pts[1]) == P.g1_mul(ST.G1_FIXED, tau.y) == sigma.y
+    import oracle_ffi as O
+
+    coeffs = O.random_fr(5, 8 * 4)
+    poly = be.from_coeffs(coeffs, 8, 4)
+    assert be.commit(sigma.xy_powers, poly) == P.g1_mul(ST.G1_FIXED, poly.eval(tau.x, tau.y))
+
+
+def test_full_snark_verifies_and_rejects_tampering(tiny):
+    t = tiny
+    assert VF.verify_arith(t["params"], t["sigma"], t["points"], t["scalars"], t["p4t"])
+    assert VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], t["points"], t["scalars"])
+    bad = dict(t["scalars"], V_eval=(t["scalars"]["V_eval"] + 1) % fr.R_MOD)
+    assert not VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], t["points"], bad)
+    badp = dict(t["points"], O_prv=t["be"].g1_add(t["points"]["O_prv"], t["sigma"].G))
+    assert not VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], badp, t["scalars"])
+    inst2 = copy.deepcopy(t["inst"])
+    inst2.a_pub_user[0] = (inst2.a_pub_user[0] + 1) % fr.R_MOD
+    assert not VF.verify_snark(t["params"], t["sigma"], t["pre"], inst2, t["points"], t["scalars"])
+
+
+def test_unsatisfied_witness_is_caught(tiny):
+    """A corrupted internal wire breaks the R1CS: the quotient identity check of prove0 (prove/src/lib.rs:1546-1556) fails."""
+    t = tiny
+    pl = copy.deepcopy(t["pl"])
+    pl[5].variables[-1] = (pl[5].variables[-1] + 1) % fr.R_MOD
+    pv = PV.Prover(t["be"], t["params"], t["infos"], t["r1cs"], t["sigma"], pl, t["perm"], t["inst"], mixer=PV.Mixer.fixed(), checks=True)
+    with pytest.raises(AssertionError):
+        pv.prove0()
+
+
+def test_proof_json_layout(tiny):
+    fmt = tiny["fmt"]
+    assert len(fmt["proof_entries_part1"]) == 38 and len(fmt["proof_entries_part2"]) == 42
+    assert all(len(s) == 2 + 32 for s in fmt["proof_entries_part1"]) and all(len(s) == 2 + 64 for s in fmt["proof_entries_part2"])
+    assert F.recover_proof(fmt) == (tiny["points"], tiny["scalars"])
+    pre = tiny["pre"]
+    assert F.recover_preprocess(F.format_preprocess(pre)) == pre
+
+
+def test_proof_is_deterministic_under_fixed_blinding(tiny):
+    t = tiny
+    pv = PV.Prover(t["be"], t["params"], t["infos"], t["r1cs"], t["sigma"], t["pl"], t["perm"], t["inst"], mixer=PV.Mixer.fixed())
+    assert PV.prove(pv)[2] == t["fmt"]
+    pv2 = PV.Prover(t["be"], t["params"], t["infos"], t["r1cs"], t["sigma"], t["pl"], t["perm"], t["inst"], mixer=PV.Mixer.fixed(seed=7))
+    pts2, sc2, fmt2, _ = PV.prove(pv2)
+    assert fmt2 != t["fmt"]
+    assert VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], pts2, sc2)

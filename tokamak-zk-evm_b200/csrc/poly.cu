@@ -261,6 +261,43 @@ __global__ void k_ruffini_y(Fr *__restrict__ qy, Fr *__restrict__ r, const Fr *_
   r[0] = v0 + b * pt;
 }
 
+
+// ---------------------------------------------------------------- sparse R1CS x witness (read_R1CS_gen_uvwXY)
+// One thread per (constraint row r, placement column c): the three dot products  sum_e coeff[e] * var[wire[e]]  over the
+// sparse rows of the placement's subcircuit (eval_sparse_rows, libs/src/iotools/mod.rs:1589-1608), written straight into
+// the [row][placement] evaluation tables of u, v, w (the reference's CPU loop + transpose, :1325-1365).  Canonical inputs
+// are converted on the fly; outputs are in Montgomery form.
+struct R1csView {
+  const uint32_t *row_ptr;   // concatenated CSR row pointers of every (subcircuit, matrix)
+  const uint32_t *wire;      // local wire index of every entry
+  const Fr *coeff;           // entry coefficients, canonical
+  const uint64_t *rp_base;   // [s_D * 3]: where (subcircuit, matrix)'s row pointers start in row_ptr
+  const uint32_t *n_rows;    // [s_D]: constraints of each subcircuit
+  const uint32_t *sub_of_col;  // [s_max]: subcircuit placed in each column (0xffffffff = empty)
+  const uint64_t *var_off;   // [s_max]: where the column's variables start in `witness`
+  const Fr *witness;         // all placement variables, canonical
+};
+__global__ void __launch_bounds__(128) k_r1cs_uvw(R1csView v, size_t n, size_t s_max, Fr *__restrict__ u, Fr *__restrict__ vv,
+                                                  Fr *__restrict__ w) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n * s_max) return;
+  const size_t r = t / s_max, c = t % s_max;
+  Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+  const uint32_t s = v.sub_of_col[c];
+  if (s != 0xffffffffu && r < v.n_rows[s]) {
+    const Fr *var = v.witness + v.var_off[c];
+    for (int m = 0; m < 3; m++) {
+      const uint32_t *rp = v.row_ptr + v.rp_base[3 * s + m];
+      Fr a = Fr::zero();
+      for (uint32_t e = rp[r]; e < rp[r + 1]; e++) a = a + v.coeff[e].to_mont() * var[v.wire[e]].to_mont();
+      acc[m] = a;
+    }
+  }
+  u[t] = acc[0];
+  vv[t] = acc[1];
+  w[t] = acc[2];
+}
+
 // ---------------------------------------------------------------- host orchestration
 static int32_t poly_alloc(tkm_ctx *ctx, size_t x, size_t y, tkm_poly **out) {
   if (!is_pow2(x) || !is_pow2(y)) return fail(TKM_ERR_INVALID_ARGUMENT, "The input sizes must be powers of two (got %zu x %zu).", x, y);
@@ -448,6 +485,65 @@ int32_t tkm_poly_from_device(tkm_ctx *ctx, const void *dev_coeffs, size_t x_size
     *out = nullptr;
     return fail(TKM_ERR_CUDA, "D2D copy failed: %s", cudaGetErrorString(e));
   }
+  return TKM_OK;
+}
+
+int32_t tkm_r1cs_uvw_polys(tkm_ctx *ctx, uint32_t s_D, const uint32_t *n_rows, const uint64_t *rp_base, const uint32_t *row_ptr,
+                           size_t row_ptr_len, const uint32_t *wire, const uint8_t *coeff32, size_t nnz, const uint32_t *sub_of_col,
+                           const uint64_t *var_off, const uint8_t *witness32, size_t n_vars, size_t n, size_t s_max, tkm_poly **out_u,
+                           tkm_poly **out_v, tkm_poly **out_w) {
+  API_BEGIN
+  TKM_REQUIRE(n_rows && rp_base && row_ptr && sub_of_col && var_off && witness32 && out_u && out_v && out_w, "null argument");
+  TKM_REQUIRE(nnz == 0 || (wire && coeff32), "null sparse entries");
+  TKM_REQUIRE(is_pow2(n) && is_pow2(s_max), "n and s_max must be powers of two");
+  // validate the host-side metadata so the kernel can not read out of bounds
+  for (uint32_t s = 0; s < s_D; s++) {
+    TKM_REQUIRE(n_rows[s] <= n, "n is smaller than the actual number of constraints.");
+    for (int m = 0; m < 3; m++) TKM_REQUIRE(rp_base[3 * s + m] + n_rows[s] + 1 <= row_ptr_len, "row pointer table too short");
+  }
+  for (size_t i = 0; i < row_ptr_len; i++) TKM_REQUIRE(row_ptr[i] <= nnz, "row pointer exceeds the number of entries");
+  for (size_t c = 0; c < s_max; c++)
+    TKM_REQUIRE(sub_of_col[c] == 0xffffffffu || (sub_of_col[c] < s_D && var_off[c] <= n_vars), "invalid placement column");
+  Scratch<uint32_t> d_rp, d_wire, d_nrows, d_sub;
+  Scratch<uint64_t> d_base, d_off;
+  Scratch<Fr> d_coeff, d_wit;
+  TKM_TRY(d_rp.alloc(ctx, row_ptr_len));
+  TKM_TRY(d_wire.alloc(ctx, nnz));
+  TKM_TRY(d_coeff.alloc(ctx, nnz));
+  TKM_TRY(d_nrows.alloc(ctx, s_D));
+  TKM_TRY(d_base.alloc(ctx, (size_t)s_D * 3));
+  TKM_TRY(d_sub.alloc(ctx, s_max));
+  TKM_TRY(d_off.alloc(ctx, s_max));
+  TKM_TRY(d_wit.alloc(ctx, n_vars));
+  TKM_CUDA(cudaMemcpyAsync(d_rp.p, row_ptr, row_ptr_len * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    TKM_CUDA(cudaMemcpyAsync(d_wire.p, wire, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TKM_CUDA(cudaMemcpyAsync(d_coeff.p, coeff32, nnz * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  TKM_CUDA(cudaMemcpyAsync(d_nrows.p, n_rows, (size_t)s_D * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaMemcpyAsync(d_base.p, rp_base, (size_t)s_D * 3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaMemcpyAsync(d_sub.p, sub_of_col, s_max * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TKM_CUDA(cudaMemcpyAsync(d_off.p, var_off, s_max * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_vars) TKM_CUDA(cudaMemcpyAsync(d_wit.p, witness32, n_vars * 32, cudaMemcpyHostToDevice, ctx->stream));
+  tkm_poly *p[3] = {nullptr, nullptr, nullptr};
+  int32_t st = TKM_OK;
+  for (int i = 0; i < 3 && st == TKM_OK; i++) st = poly_alloc(ctx, n, s_max, &p[i]);
+  if (st == TKM_OK) {
+    R1csView v{d_rp.p, d_wire.p, d_coeff.p, d_base.p, d_nrows.p, d_sub.p, d_off.p, d_wit.p};
+    const size_t total = n * s_max;
+    k_r1cs_uvw<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(v, n, s_max, p[0]->d, p[1]->d, p[2]->d);
+    st = launch_check(ctx, "k_r1cs_uvw");
+  }
+  for (int i = 0; i < 3 && st == TKM_OK; i++) st = tkm_poly_ntt_inplace(ctx, p[i], TKM_INVERSE, nullptr, nullptr);
+  if (st != TKM_OK) {
+    for (int i = 0; i < 3; i++) poly_release(ctx, p[i]);
+    return st;
+  }
+  // the host staging buffers above are freed in stream order; the caller may reuse its arrays after this returns
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out_u = p[0];
+  *out_v = p[1];
+  *out_w = p[2];
   return TKM_OK;
 }
 

@@ -61,6 +61,8 @@ SIGNATURES = {
     "tkm_poly_from_evals_host": [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, P(c_void_p)],
     "tkm_poly_from_device": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_poly_zero": [c_void_p, c_size_t, c_size_t, P(c_void_p)],
+    "tkm_r1cs_uvw_polys": [c_void_p, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                           c_void_p, c_size_t, c_size_t, c_size_t, P(c_void_p), P(c_void_p), P(c_void_p)],
     "tkm_poly_clone": [c_void_p, c_void_p, P(c_void_p)],
     "tkm_poly_free": [c_void_p, c_void_p],
     "tkm_poly_shape": [c_void_p, P(c_size_t), P(c_size_t)],

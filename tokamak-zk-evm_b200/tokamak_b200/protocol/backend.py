@@ -39,6 +39,10 @@ class GpuTable:
         check(self.ctx.lib.tkm_crs_device_ptr(self.h, ctypes.byref(p), None, None))
         return p.value
 
+    def precompute(self, window_bits=20):
+        """Fixed-base tables 2^(c w) P for every point (serving mode: one CRS reused across proofs)."""
+        check(self.ctx.lib.tkm_crs_precompute(self.ctx.h, self.h, window_bits))
+
     def points_host(self):
         """Canonical affine points (rows*cols, 12) -- test/debug only."""
         n = self.rows * self.cols
@@ -76,6 +80,15 @@ class GpuBackend:
 
     def init_ntt_domain(self, size):
         self.ctx.init_ntt_domain_for_size(size)
+
+    def uvw_polys(self, params, csr, wt):
+        """read_R1CS_gen_uvwXY on the device (tkm_r1cs_uvw_polys): sparse R1CS x witness + three inverse biNTTs."""
+        u, v, w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        vals = np.ascontiguousarray(wt.values)
+        check(self.ctx.lib.tkm_r1cs_uvw_polys(self.ctx.h, len(csr.n_rows), _vp(csr.n_rows), _vp(csr.rp_base), _vp(csr.row_ptr), csr.row_ptr.shape[0],
+                                              _vp(csr.wire), _vp(csr.coeff), csr.wire.shape[0], _vp(wt.sub_of_col), _vp(wt.var_off), _vp(vals),
+                                              vals.shape[0], params.n, params.s_max, ctypes.byref(u), ctypes.byref(v), ctypes.byref(w)))
+        return DensePolynomialExt(self.ctx, u), DensePolynomialExt(self.ctx, v), DensePolynomialExt(self.ctx, w)
 
     # ---- G1 tables (Sigma1 components), built and kept on the device
     def make_table(self, col, row, base):
@@ -121,6 +134,11 @@ class GpuBackend:
         ctx.dev_free(d_s)
         ctx.dev_free(d_i)
         return g1_to_tuple(out)
+
+    def msm_points(self, points, scalars):
+        """msm_g1_bases over a handful of host points (the blinding terms of the binding)."""
+        pts = np.stack([g1_from_tuple(p) for p in points])
+        return g1_to_tuple(self.ctx.msm_g1_host(frs_from_ints([k % R_MOD for k in scalars]), pts))
 
     # ---- G1serde ops
     def g1_add(self, a, b):

@@ -96,7 +96,7 @@ class Timings:
 
 
 class Prover:
-    def __init__(self, backend, params, infos, r1cs_list, sigma, placements, permutation, instance, mixer=None, checks=False):
+    def __init__(self, backend, params, infos, r1cs_list, sigma, placements, permutation, instance, mixer=None, checks=False, library_csr=None):
         """Prover::init (prove/src/lib.rs:675-1206).  `checks` re-runs the reference's debug assertions (R1CS grid check,
         quotient identities at a random point)."""
         self.be, self.p, self.sigma, self.checks = backend, params, sigma, checks
@@ -109,13 +109,19 @@ class Prover:
         backend.init_ntt_domain(max(2 * n, 4 * m_i) * 2 * s_max)
         self.mixer = mixer or Mixer.random()
         # witness polynomials (gen_bXY, read_R1CS_gen_uvwXY)
-        u_ev, v_ev, w_ev = qap.uvw_evals(p, placements, r1cs_list)
-        self.t.add("init.build.witness.uvw_evals_host", time.perf_counter() - t0)
-        self.uXY = backend.from_rou_evals(u_ev, n, s_max)
-        self.vXY = backend.from_rou_evals(v_ev, n, s_max)
-        self.wXY = backend.from_rou_evals(w_ev, n, s_max)
-        self.bXY = backend.from_rou_evals(qap.interface_evals(p, placements, infos), m_i, s_max)
+        wt = qap.WitnessTable(p, placements, infos)
+        self.t.add("init.witness_table", time.perf_counter() - t0)
+        t1 = time.perf_counter()
+        csr = library_csr or qap.LibraryCSR(r1cs_list)
+        self.t.add("init.library_csr", time.perf_counter() - t1)
+        t1 = time.perf_counter()
+        self.uXY, self.vXY, self.wXY = backend.uvw_polys(p, csr, wt)
+        self.t.add("init.build.witness.uvwXY", time.perf_counter() - t1)
+        t1 = time.perf_counter()
+        self.bXY = backend.from_rou_evals(qap.interface_evals_from_table(p, wt), m_i, s_max)
+        self.t.add("init.build.witness.bXY", time.perf_counter() - t1)
         self.rXY = None
+        t1 = time.perf_counter()
         # instance polynomials
         public_instance = list(instance.a_pub_user[:p.l_user]) + list(instance.a_pub_block[:l_free - p.l_user])
         if len(public_instance) != l_free:
@@ -130,9 +136,10 @@ class Prover:
         self.s1XY = backend.from_rou_evals(s1_ev, m_i, s_max)
         self.q = [None] * 4  # q0 (Q_AX part), q1, q2 (Q_CX part), q3
         self.cache = {}
+        self.t.add("init.build.instance", time.perf_counter() - t1)
         self.t.add("init.build", time.perf_counter() - t0)
         t1 = time.perf_counter()
-        self.binding = self._binding(placements, infos)
+        self.binding = self._binding(placements, infos, wt)
         self.t.add("init.binding", time.perf_counter() - t1)
         self.t.add("init", time.perf_counter() - t0)
 
@@ -179,7 +186,7 @@ class Prover:
         return pt
 
     # ---- binding (prove/src/lib.rs:1092-1176; sparse MSMs: group_structures/mod.rs:145-300)
-    def _binding(self, placements, infos):
+    def _binding(self, placements, infos, wt):
         be, p, sg, mx = self.be, self.p, self.sigma, self.mixer
         A_free = self.encode(self.a_free_X, "A_free")
         # O_pub_free: public sides of bufferPubOut (outputs), bufferPubIn / bufferBlockIn (inputs); bufferEVMIn is O_pub_fix
@@ -196,32 +203,24 @@ class Prover:
                 idx.append(info.flattenMap[j])
                 sc.append(pl.variables[j])
         O_pub_free = be.msm_indexed(sg.gamma_inv_o_inst, np.array(idx, dtype=np.uint32), frs_from_ints(sc))
-        O_mid_core = self._encode_statement(placements, infos, p.l, p.l_D, sg.eta_inv_li_o_inter_alpha4_kj)
-        O_prv_core = self._encode_statement(placements, infos, p.l_D, p.m_D, sg.delta_inv_li_o_prv)
-        O_mid = be.g1_add(O_mid_core, be.g1_mul(sg.delta, mx.rO_mid))
-        O_prv = be.g1_sub(O_prv_core, be.g1_mul(sg.eta, mx.rO_mid))
-        terms = [(sg.delta_inv_alphak_xh_tx[0][0], mx.rU_X), (sg.delta_inv_alphak_xh_tx[1][0], mx.rV_X)]
+        O_mid_core = self._encode_statement(wt, p.l, p.l_D, sg.eta_inv_li_o_inter_alpha4_kj)
+        O_prv_core = self._encode_statement(wt, p.l_D, p.m_D, sg.delta_inv_li_o_prv)
+        # zero-knowledge terms (prove/src/lib.rs:1131-1160): the 17 scalar multiples as two small MSMs
+        O_mid = be.g1_add(O_mid_core, be.msm_points([sg.delta], [mx.rO_mid]))
+        terms = [(sg.eta, (-mx.rO_mid) % R_MOD), (sg.delta_inv_alphak_xh_tx[0][0], mx.rU_X), (sg.delta_inv_alphak_xh_tx[1][0], mx.rV_X)]
         terms += [(sg.delta_inv_alphak_xh_tx[2][h], mx.rW_X[h]) for h in range(3)]
         terms += [(sg.delta_inv_alpha4_xj_tx[j], mx.rB_X[j]) for j in range(2)]
         terms += [(sg.delta_inv_alphak_yi_ty[0][0], mx.rU_Y), (sg.delta_inv_alphak_yi_ty[1][0], mx.rV_Y)]
         terms += [(sg.delta_inv_alphak_yi_ty[2][i], mx.rW_Y[i]) for i in range(3)]
         terms += [(sg.delta_inv_alphak_yi_ty[3][i], mx.rB_Y[i]) for i in range(2)]
-        for pt, k in terms:
-            O_prv = be.g1_add(O_prv, be.g1_mul(pt, k))
+        O_prv = be.g1_add(O_prv_core, be.msm_points([t[0] for t in terms], [t[1] for t in terms]))
         return {"A_free": A_free, "O_pub_free": O_pub_free, "O_mid": O_mid, "O_prv": O_prv}
 
-    def _encode_statement(self, placements, infos, lo, hi, table):
+    def _encode_statement(self, wt, lo, hi, table):
         """encode_statement_common (group_structures/mod.rs:266-300): every wire of every placement whose global index
         lies in [lo, hi), against table[global - lo][placement]."""
-        s_max = self.p.s_max
-        idx, sc = [], []
-        for col, pl in enumerate(placements):
-            fmap = infos[pl.subcircuitId].flattenMap
-            for g, v in zip(fmap, pl.variables):
-                if lo <= g < hi:
-                    idx.append((g - lo) * s_max + col)
-                    sc.append(v)
-        return self.be.msm_indexed(table, np.array(idx, dtype=np.uint32), frs_from_ints(sc))
+        idx, vals = wt.gather(lo, hi, self.p.s_max)
+        return self.be.msm_indexed(table, idx, vals)
 
     # ---- prove0 (prove/src/lib.rs:1446-1782)
     def prove0(self):

@@ -26,6 +26,65 @@ def o_evaled(params, infos, r1cs_list, tau):
     return o
 
 
+class LibraryCSR:
+    """The library's constraints as one concatenated CSR (per subcircuit and matrix), the layout tkm_r1cs_uvw_polys takes.
+    Built once per library (the reference re-parses the .r1cs binaries on every prove, iotools/mod.rs:1322-1340)."""
+
+    def __init__(self, r1cs_list):
+        s_d = len(r1cs_list)
+        self.n_rows = np.array([r.n_constraints for r in r1cs_list], dtype=np.uint32)
+        self.rp_base = np.zeros(s_d * 3, dtype=np.uint64)
+        row_ptr, wire, coeff = [], [], bytearray()
+        for s, r in enumerate(r1cs_list):
+            for m in range(3):
+                self.rp_base[3 * s + m] = len(row_ptr)
+                row_ptr.append(len(wire))
+                for abc in r.constraints:
+                    for wi, cf in abc[m]:
+                        wire.append(wi)
+                        coeff += cf.to_bytes(32, "little")
+                    row_ptr.append(len(wire))
+        self.row_ptr = np.array(row_ptr, dtype=np.uint32)
+        self.wire = np.array(wire, dtype=np.uint32)
+        self.coeff = np.frombuffer(bytes(coeff), dtype=np.uint64).reshape(-1, 4).copy()
+        self.r1cs_list = r1cs_list
+
+
+class WitnessTable:
+    """All placement variables as one (total, 4) uint64 array of canonical limbs + per-column offsets: the in-memory form
+    of placementVariables.json the vectorised host code and the device kernels work on."""
+
+    def __init__(self, params, placements, infos):
+        if len(placements) > params.s_max:
+            raise ValueError("placement_variables length exceeds s_max.")
+        self.placements = placements
+        self.sub_of_col = np.full(params.s_max, 0xFFFFFFFF, dtype=np.uint32)
+        self.var_off = np.zeros(params.s_max, dtype=np.uint64)
+        off = 0
+        chunks = []
+        for col, pl in enumerate(placements):
+            if len(pl.variables) != infos[pl.subcircuitId].Nwires:
+                raise ValueError("Corrupted placement variables.")
+            self.sub_of_col[col] = pl.subcircuitId
+            self.var_off[col] = off
+            off += len(pl.variables)
+            chunks.append(b"".join([v.to_bytes(32, "little") for v in pl.variables]))
+        self.values = np.frombuffer(b"".join(chunks), dtype=np.uint64).reshape(-1, 4)
+        self.fmap = [np.array(s.flattenMap, dtype=np.int64) for s in infos]
+
+    def gather(self, lo, hi, s_max):
+        """Every (placement, wire) whose global wire index lies in [lo, hi): -> (table index (g - lo) * s_max + col, values)."""
+        idx, rows = [], []
+        for col, pl in enumerate(self.placements):
+            fm = self.fmap[pl.subcircuitId]
+            sel = np.nonzero((fm >= lo) & (fm < hi))[0]
+            idx.append((fm[sel] - lo) * s_max + col)
+            rows.append(sel + int(self.var_off[col]))
+        idx = np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
+        rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+        return idx.astype(np.uint32), np.ascontiguousarray(self.values[rows])
+
+
 def uvw_evals(params, placements, r1cs_list):
     """Evaluation tables of u, v, w on the n x s_max grid, row-major [row][placement] (read_R1CS_gen_uvwXY +
     eval_uvwxy_sparse_rows, iotools/mod.rs:1287-1420; the transpose at :1363-1365 is folded into the indexing).
@@ -48,6 +107,15 @@ def uvw_evals(params, placements, r1cs_list):
                 acc %= R_MOD
                 if acc:
                     out[m][row * s_max + col] = (acc & mask, (acc >> 64) & mask, (acc >> 128) & mask, acc >> 192)
+    return out
+
+
+def interface_evals_from_table(params, wt: WitnessTable):
+    """gen_bXY over a WitnessTable (vectorised)."""
+    s_max = params.s_max
+    out = np.zeros(((params.l_D - params.l) * s_max, 4), dtype=np.uint64)
+    idx, vals = wt.gather(params.l, params.l_D, s_max)
+    out[idx] = vals
     return out
 
 
