@@ -388,12 +388,12 @@ def main():
         for p_ in (d_bases, d_scalars):
             ctx.dev_free(p_)
         gpu_be = GpuBackend(ctx)
-        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync)
+        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync, warmup=3)
         full["reference"] = {"cpu_prove_s": 45.7, "icicle_cuda_prove_s": 21.08, "stage_split_cpu_s": [5.21, 10.09, 2.13, 13.37, 1.56, 13.33],
                              "stage_split_icicle_cuda_s": [0.72, 4.03, 0.78, 7.27, 0.90, 7.37],
                              "source": "BASELINE.md (reference's own artifacts, unnamed hosts, real template tx, 166 placements)"}
         line["prove"] = {"metric": "prove s/tx", "value": full["prove_s"], "unit": "s", "higher_is_better": False, **full}
-        small = prove_full.run(gpu_be, prove_full.reduced_shape(), repeats=3, verify=False, sync=ctx.sync, keep_sigma=True)
+        small = prove_full.run(gpu_be, prove_full.reduced_shape(), repeats=3, verify=False, sync=ctx.sync, keep_sigma=True, warmup=1)
         from oracle_backend import OracleBackend, OracleTable
 
         sg = copy.copy(small.pop("_sigma"))
