@@ -60,7 +60,7 @@ class ClockSampler:
     loop beside the benchmark was seen to stall kernel launches for tens of ms); started before the warm-up so that samples
     exist for short timed regions, summarised over the [t0, t1] window of the timed region."""
 
-    PERIOD_S = 0.1
+    PERIOD_S = float(os.environ.get("TKM_BENCH_SAMPLER_PERIOD_S", "0.1"))  # developer knob; <= 0 disables sampling
 
     def __init__(self, index):
         self.index = index
@@ -69,6 +69,8 @@ class ClockSampler:
         self._stop = threading.Event()
 
     def start(self):
+        if self.PERIOD_S <= 0:
+            return
         try:
             import pynvml as nv
 
@@ -110,7 +112,8 @@ class ClockSampler:
             sel = [min(self.samples, key=lambda x: abs(x[0] - t1))]
         reasons = sorted({nm for x in sel for nm, b in bits.items() if x[4] & b})
         return {"sm_mhz": float(np.median([x[1] for x in sel])) if sel else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(sel), "power_w_max": max(x[3] for x in sel) if sel else None, "source": "NVML, in-process thread, 100 ms period"}
+                "samples": len(sel), "power_w_max": max(x[3] for x in sel) if sel else None,
+                "source": f"NVML, in-process thread, {int(self.PERIOD_S * 1000)} ms period"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm

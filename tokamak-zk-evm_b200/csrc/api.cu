@@ -198,6 +198,7 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->twiddles) cudaFree(ctx->twiddles);
+  if (ctx->fb_table) cudaFree(ctx->fb_table);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->kev0) cudaEventDestroy(ctx->kev0);
@@ -441,7 +442,7 @@ int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bas
   }
   TKM_REQUIRE(scalars && bases, "null argument");
   // Large inputs: overlap the host->device copies with the bucket accumulation, one point range at a time.
-  uint32_t pieces = n >= ((size_t)1 << 21) ? 4 : (n >= ((size_t)1 << 19) ? 2 : 1);
+  uint32_t pieces = n >= ((size_t)1 << 21) ? 3 : (n >= ((size_t)1 << 19) ? 2 : 1);
   if (const char *e = getenv("TKM_MSM_HOST_PIECES")) pieces = (uint32_t)atoi(e);  // developer knob
   return msm_host_pipelined(ctx, scalars, bases, n, pieces, out96);
 }
@@ -451,13 +452,19 @@ int32_t tkm_g1_fixed_base_mul(tkm_ctx *ctx, const uint8_t base96[96], const void
   TKM_REQUIRE(base96 && out, "null argument");
   if (n == 0) return TKM_OK;
   TKM_REQUIRE(scalars, "null scalars");
-  Scratch<G1Affine> table;
-  TKM_TRY(table.alloc(ctx, FB_WINDOWS * 16));
-  G1Affine b;
-  memcpy(&b, base96, 96);
-  k_fixed_base_table<<<1, 32, 0, ctx->stream>>>(b, table.p);
-  TKM_TRY(launch_check(ctx, "k_fixed_base_table"));
-  k_fixed_base_mul<<<grid_for(n, 128, ctx->sm_count), 128, 0, ctx->stream>>>(table.p, (const Fr *)scalars, scalars_mont, n,
+  // the 64 x 16 window table of the most recent base stays on the context: setup multiplies one generator millions of
+  // times across dozens of calls (Sigma1::gen), and building the table is a serial 20 ms job
+  if (!ctx->fb_table) TKM_CUDA(cudaMalloc((void **)&ctx->fb_table, FB_WINDOWS * 16 * sizeof(G1Affine)));
+  if (!ctx->fb_valid || memcmp(ctx->fb_base, base96, 96) != 0) {
+    G1Affine b;
+    memcpy(&b, base96, 96);
+    ctx->fb_valid = false;
+    k_fixed_base_table<<<1, 32, 0, ctx->stream>>>(b, ctx->fb_table);
+    TKM_TRY(launch_check(ctx, "k_fixed_base_table"));
+    memcpy(ctx->fb_base, base96, 96);
+    ctx->fb_valid = true;
+  }
+  k_fixed_base_mul<<<grid_for(n, 128, ctx->sm_count), 128, 0, ctx->stream>>>(ctx->fb_table, (const Fr *)scalars, scalars_mont, n,
                                                                             (G1Affine *)out);
   return launch_check(ctx, "k_fixed_base_mul");
 }

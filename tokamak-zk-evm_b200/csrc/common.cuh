@@ -53,6 +53,10 @@ struct tkm_ctx {
   // bench.py's roofline divides the kernel's algorithmic work by this duration (tkm_kernel_time_last)
   cudaEvent_t kev0 = nullptr, kev1 = nullptr;
   bool kernel_timed = false;
+  // window table (64 x 16 affine multiples) of the most recent tkm_g1_fixed_base_mul base
+  tkm::G1Affine *fb_table = nullptr;
+  uint8_t fb_base[96] = {};
+  bool fb_valid = false;
   // copy engine side of the pipelined host-buffer MSM (created on first use)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[17] = {};

@@ -612,9 +612,25 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
   if (pieces < 1) pieces = 1;
   if (pieces > 16) pieces = 16;
+  if (pieces > n) pieces = (uint32_t)n;
   if (!ctx->copy_stream) {
     TKM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 17; i++) TKM_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+  }
+  // Piece boundaries.  The copy engine outruns the accumulation (~2.4 ms vs ~7 ms per 2^20 points), so only the first
+  // piece's copy is exposed: cut the range in growing pieces (weights 1, 3, 4, 4, ..) -- a small first piece starts the
+  // compute early, few large later pieces keep the per-piece overhead (sort, chunk tails, bucket merge) low.
+  size_t bound[17];
+  {
+    uint32_t wsum = 0, acc = 0;
+    for (uint32_t k = 0; k < pieces; k++) wsum += k == 0 ? 1 : (k == 1 ? 3 : 4);
+    bound[0] = 0;
+    for (uint32_t k = 0; k < pieces; k++) {
+      acc += k == 0 ? 1 : (k == 1 ? 3 : 4);
+      bound[k + 1] = k + 1 == pieces ? n : (size_t)((unsigned __int128)n * acc / wsum);
+      if (bound[k + 1] <= bound[k]) bound[k + 1] = bound[k] + 1;  // n >= pieces keeps every piece non-empty
+      if (bound[k + 1] > n) bound[k + 1] = n;
+    }
   }
   const MsmGeom m = pick_geom(n);
   Scratch<Fr> ds;
@@ -623,25 +639,24 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   TKM_TRY(ds.alloc(ctx, n));
   TKM_TRY(db.alloc(ctx, n));
   const size_t set_stride = (size_t)m.nbuckets + 1;
-  const size_t per = (n + pieces - 1) / pieces;
-  pieces = (uint32_t)((n + per - 1) / per);
   TKM_TRY(buckets.alloc(ctx, set_stride * pieces));
   // the staging buffers come from the compute stream's pool: the copy stream may touch them only after this point
   TKM_CUDA(cudaEventRecord(ctx->copy_ev[16], ctx->stream));
   TKM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[16], 0));
-  uint32_t used = 0;
-  for (size_t off = 0; off < n; off += per, used++) {
-    const size_t cnt = (off + per <= n) ? per : n - off;
-    TKM_CUDA(cudaMemcpyAsync(ds.p + off, scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    TKM_CUDA(cudaMemcpyAsync(db.p + off, bases + off * 96, cnt * 96, cudaMemcpyHostToDevice, ctx->copy_stream));
-    TKM_CUDA(cudaEventRecord(ctx->copy_ev[used], ctx->copy_stream));
-  }
-  k_fill_identity<<<grid_for(set_stride * pieces, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, set_stride * pieces);
-  TKM_TRY(launch_check(ctx, "k_fill_identity"));
-  uint32_t k = 0;
   int32_t st = TKM_OK;
-  for (size_t off = 0; off < n && st == TKM_OK; off += per, k++) {
-    const size_t cnt = (off + per <= n) ? per : n - off;
+  for (uint32_t k = 0; k < pieces && st == TKM_OK; k++) {
+    const size_t off = bound[k], cnt = bound[k + 1] - bound[k];
+    cudaError_t e = cudaMemcpyAsync(ds.p + off, scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db.p + off, bases + off * 96, cnt * 96, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream);
+    if (e != cudaSuccess) st = fail(TKM_ERR_CUDA, "host-to-device copy of MSM piece %u failed: %s", k, cudaGetErrorString(e));
+  }
+  if (st == TKM_OK) {
+    k_fill_identity<<<grid_for(set_stride * pieces, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, set_stride * pieces);
+    st = launch_check(ctx, "k_fill_identity");
+  }
+  for (uint32_t k = 0; k < pieces && st == TKM_OK; k++) {
+    const size_t off = bound[k], cnt = bound[k + 1] - bound[k];
     cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0);
     if (e != cudaSuccess) {
       st = fail(TKM_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
