@@ -71,7 +71,7 @@ def test_product_does_not_reference_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".rs", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
-                if re.search(r"(import\s+(pyref|oracle_ffi)|from\s+(pyref|oracle_ffi)|liboracle|oracle/)", txt):
+                if re.search(r"(import\s+(pyref|oracle_ffi|oracle_backend)|from\s+(pyref|oracle_ffi|oracle_backend)|liboracle|oracle/)", txt):
                     # comments that merely state the rule are allowed only in ffi.py's docstring
                     if not (f == "ffi.py" and "nothing here imports oracle/" in txt and txt.count("oracle") == 1):
                         bad.append(os.path.join(dirpath, f))

@@ -1,8 +1,8 @@
 """The product backend of the protocol driver: every polynomial, commitment and sparse MSM runs on the B200 through the
 C-ABI of libtokamak_b200 (no CPU fallback: constructing it without a GPU fails in tkm_ctx_create).
 
-The driver talks to a backend through this small surface (the oracle-backed twin used by the tests lives in
-oracle/oracle_backend.py and implements the same methods):
+The driver talks to a backend through this small surface (the CPU twin used by the tests lives with the test oracle,
+outside this package, and implements the same methods):
   from_coeffs / from_rou_evals -> polynomial with  + - * (poly | int), mul_monomial, scale_coeffs_x/y, eval,
                                    div_by_vanishing_opt, div_by_ruffini, to_rou_evals, clone
   make_table(col, row, base)    -> G1 table  T[j][i] = col[j] * row[i] * base   (Sigma1 components)
