@@ -121,6 +121,15 @@ int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bas
  * bases = device table in Montgomery form (from tkm_g1_bases_to_mont or a tkm_crs). */
 int32_t tkm_msm_g1(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, const void *dev_bases_mont, size_t n,
                    uint8_t out96[96]);
+/* tkm_ntt_batch fused with the multi-GPU re-sharding exchange: the last pass stores straight into the
+ * peers' buffers over NVLink instead of writing a local result, so the X<->Y transpose of a row-sharded bivariate NTT
+ * needs no separate transpose kernel and no separate all-to-all.  The element at axis position a of batch lane b is
+ * written to peer_out[a / (n / n_peers)] + ((a mod (n / n_peers)) * stride_a + (b + b0) * stride_b) elements.
+ * peer_out[] (host array) holds n_peers peer-mapped device pointers (a power of two <= 16); the caller orders the
+ * launch against the peers with its own barriers. */
+int32_t tkm_ntt_batch_scatter(tkm_ctx *ctx, const void *dev_in, size_t n, size_t batch, int32_t columns_batch, int32_t dir,
+                              const uint8_t *coset32, void *const *peer_out, uint32_t n_peers, uint64_t stride_a, uint64_t stride_b,
+                              uint64_t b0);
 /* Canonical affine bytes on the device -> Montgomery-form base table (in place allowed). */
 int32_t tkm_g1_bases_to_mont(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n);
 /* The inverse conversion (device Montgomery affine -> canonical), e.g. to write a generated CRS table out. */

@@ -49,6 +49,25 @@ for (x, y, cx, cy) in ((64, 32, None, None), (2048, 64, 12345, 678910), (4096, 2
     back = D.bintt_sharded_inverse(ops, ev.contiguous(), x, y, cx, cy)
     assert np.array_equal(from_dev_mont(back).reshape(hi - lo, y, 4), full.reshape(x, y, 4)[lo:hi]), "round trip"
 
+# fused exchange: the last NTT pass stores into the peers' buffers over NVLink (no transpose copy, no all-to-all)
+if world & (world - 1) == 0:
+    for (x, y, cx, cy) in ((64, 32, None, None), (2048, 64, 12345, 678910), (4096, 256, None, None), (16384, 512, 7, None)):
+        if x % world or y % world:
+            continue
+        ctx.init_ntt_domain_for_size(max(1 << 20, x * y))
+        ex = D.PeerExchange(x, y, dev)
+        full = O.random_fr(31 + x, x * y)
+        lo, hi = D.shard_range(x, world, rank)
+        t = to_dev_mont(full.reshape(x, y, 4)[lo:hi].copy()).view(hi - lo, y, 4)
+        exp = O.bintt(full, x, y, False, None if cx is None else O.fr_from_int(cx), None if cy is None else O.fr_from_int(cy)).reshape(x, y, 4)
+        yb = y // world
+        for rep in range(2):  # twice: the barriers must also protect buffer reuse
+            ev = D.bintt_sharded_forward_fused(ops, ex, t, cx, cy)
+            assert np.array_equal(from_dev_mont(ev).reshape(x, yb, 4), exp[:, rank * yb:(rank + 1) * yb]), f"fused forward {x}x{y}"
+            back = D.bintt_sharded_inverse_fused(ops, ex, ev, cx, cy)
+            assert np.array_equal(from_dev_mont(back).reshape(hi - lo, y, 4), full.reshape(x, y, 4)[lo:hi]), f"fused round trip {x}x{y}"
+        del ex
+
 n = 50001  # ragged shards
 G = np.frombuffer(P.g1_to_bytes(P.G1_GEN), dtype=np.uint64).copy()
 pts = O.g1_fixed_base_mul_batch(G, O.random_fr(21, n))

@@ -143,6 +143,37 @@ def test_ntt_batch_rows_vs_columns(ctx, T):
     ctx.dev_free(o)
 
 
+@pytest.mark.parametrize("x,y,world", [(64, 32, 4), (2048, 64, 2), (4096, 256, 8)])
+def test_ntt_batch_scatter_single_gpu_emulation(ctx, T, x, y, world):
+    """tkm_ntt_batch_scatter (fused multi-GPU re-sharding store) with all 'peers' on this GPU: after every emulated rank has
+    run its row pass, peer p's buffer must hold the column shard [x][y/G] of the Y-transformed matrix; the inverse X pass
+    scatters column shards back into row shards."""
+    full = O.random_fr(300 + x, x * y)
+    xl, yb = x // world, y // world
+    exp_y = O.ntt(full, y, x, False, False).reshape(x, y, 4)  # transform along Y of every row
+    peers = [ctx.dev_alloc(x * yb * 32) for _ in range(world)]
+    for r in range(world):
+        d = ctx.upload_fr(full.reshape(x, y, 4)[r * xl:(r + 1) * xl].reshape(-1, 4).copy())
+        ctx.ntt_batch_scatter(d, y, xl, False, T.FORWARD, None, peers, 1, yb, r * xl)
+        ctx.dev_free(d)
+    for p in range(world):
+        got = ctx.download_fr(peers[p], x * yb).reshape(x, yb, 4)
+        assert np.array_equal(got, exp_y[:, p * yb:(p + 1) * yb]), (p, "row pass scatter")
+    # inverse X pass over each column shard, scattered into row shards [x/G][y]; with a coset generator on the axis
+    g = 0x1234567
+    rows = [ctx.dev_alloc(xl * y * 32) for _ in range(world)]
+    exp_x = O.ntt(np.ascontiguousarray(exp_y).reshape(-1, 4), x, y, True, True, O.fr_from_int(g)).reshape(x, y, 4)  # inverse along X of every column
+    for r in range(world):
+        ctx.ntt_batch_scatter(peers[r], x, yb, True, T.INVERSE, g, rows, y, 1, r * yb)
+    for q in range(world):
+        got = ctx.download_fr(rows[q], xl * y).reshape(xl, y, 4)
+        assert np.array_equal(got, exp_x[q * xl:(q + 1) * xl]), (q, "column pass scatter")
+    for p in peers + rows:
+        ctx.dev_free(p)
+    with pytest.raises(T.TkmError):
+        ctx.ntt_batch_scatter(1, y, xl, False, T.FORWARD, None, [1, 2, 3], 1, yb, 0)  # peer count must be a power of two
+
+
 def test_ntt_domain_errors(T):
     c = T.Context(0)
     a = O.random_fr(1, 16)

@@ -388,6 +388,18 @@ int32_t tkm_ntt_batch(tkm_ctx *ctx, const void *in, void *out, size_t n, size_t 
   return ntt_axis(ctx, (const Fr *)in, (Fr *)out, batch, n, 1, dir, coset32 ? &g : nullptr);
 }
 
+int32_t tkm_ntt_batch_scatter(tkm_ctx *ctx, const void *in, size_t n, size_t batch, int32_t columns_batch, int32_t dir, const uint8_t *coset32,
+                              void *const *peer_out, uint32_t n_peers, uint64_t stride_a, uint64_t stride_b, uint64_t b0) {
+  API_BEGIN
+  TKM_REQUIRE(in && peer_out, "null argument");
+  TKM_REQUIRE(dir == TKM_FORWARD || dir == TKM_INVERSE, "bad direction");
+  for (uint32_t i = 0; i < n_peers; i++) TKM_REQUIRE(peer_out[i], "null peer buffer");
+  Fr g;
+  if (coset32) g = fr_from_bytes_host(coset32);
+  if (columns_batch) return ntt_axis_scatter(ctx, (const Fr *)in, 1, n, batch, dir, coset32 ? &g : nullptr, peer_out, n_peers, stride_a, stride_b, b0);
+  return ntt_axis_scatter(ctx, (const Fr *)in, batch, n, 1, dir, coset32 ? &g : nullptr, peer_out, n_peers, stride_a, stride_b, b0);
+}
+
 int32_t tkm_g1_bases_to_mont(tkm_ctx *ctx, const void *in, void *out, size_t n) {
   API_BEGIN
   return g1_to_mont_dev(ctx, (const G1Affine *)in, (G1Affine *)out, n);

@@ -142,6 +142,8 @@ int32_t vec_transpose(tkm_ctx *ctx, const Fr *in, Fr *out, size_t rows, size_t c
 int32_t bintt_dev(tkm_ctx *ctx, const Fr *in, Fr *out, size_t x, size_t y, int dir, const Fr *coset_x,
                   const Fr *coset_y);
 int32_t ntt_axis(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, size_t n, size_t inner, int dir, const Fr *coset);
+int32_t ntt_axis_scatter(tkm_ctx *ctx, const Fr *in, size_t outer, size_t n, size_t inner, int dir, const Fr *coset, void *const *peers,
+                         uint32_t n_peers, uint64_t stride_a, uint64_t stride_b, uint64_t b0);
 int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n);
 int32_t g1_from_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n);
 struct MsmInput {

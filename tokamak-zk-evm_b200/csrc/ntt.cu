@@ -62,6 +62,7 @@ int32_t fill_powers_public(tkm_ctx *ctx, Fr *out, const Fr &base, const Fr &scal
   return fill_powers(ctx, out, base, scale, count);
 }
 
+constexpr int NTT_MAX_PEERS = 16;
 struct NttPass {
   const Fr *in;
   Fr *out;
@@ -74,6 +75,12 @@ struct NttPass {
   uint32_t pass;         // 1 = first pass of a split, 2 = last (or only) pass
   uint32_t batch_inner;  // 1: batch lanes walk `inner`; 0: batch lanes walk `outer` (inner == 1)
   uint32_t has_post_scalar;
+  // Fused exchange (multi-GPU row<->column re-sharding): when sc_on, the last pass does not write `out`;
+  // the element at axis position a of batch lane b goes to sc_peer[a >> sc_logblk] + (a & (blk-1))*sc_sA + (b + sc_b0)*sc_sB,
+  // where sc_peer[] are peer-mapped device buffers (NVLink P2P stores): the all-to-all transpose happens in the store.
+  uint32_t sc_on, sc_logblk;
+  uint64_t sc_sA, sc_sB, sc_b0;
+  Fr *sc_peer[NTT_MAX_PEERS];
 };
 
 constexpr uint32_t NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of tile data
@@ -231,8 +238,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(NttPass p) {
         l = (p.logL == 0) ? 0 : (__brev(k) >> (32 - p.logL));
         pos = (uint64_t)k * n1 + brev_g;
       }
-      uint64_t addr = base + pos * pos_stride + (uint64_t)c * c_stride;
-      gout[2 * addr + half] = (half ? d_hi : d_lo)[l * C + c];
+      const uint4 v = (half ? d_hi : d_lo)[l * C + c];
+      if (p.sc_on) {
+        const uint64_t a_loc = pos & ((1ull << p.sc_logblk) - 1);
+        uint4 *gp = reinterpret_cast<uint4 *>(p.sc_peer[pos >> p.sc_logblk]);
+        const uint64_t dst = a_loc * p.sc_sA + (cb * C + c + p.sc_b0) * p.sc_sB;
+        gp[2 * dst + half] = v;
+      } else {
+        uint64_t addr = base + pos * pos_stride + (uint64_t)c * c_stride;
+        gout[2 * addr + half] = v;
+      }
     }
   }
 }
@@ -263,8 +278,13 @@ static int32_t launch_pass(tkm_ctx *ctx, const NttPass &p, bool inverse) {
 // Transform along the middle axis of [outer][n][inner].  coset: Montgomery scalar or null.
 // extra_scalar (inverse only): folded into the output scaling of this axis (used for the 1/N of the
 // other axis so a 2-D inverse multiplies each element by 1/(x*y) once).
+struct NttScatter {
+  void *const *peers;  // n_peers peer-mapped device buffers
+  uint32_t n_peers;
+  uint64_t stride_a, stride_b, b0;
+};
 static int32_t ntt_axis_impl(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, size_t n, size_t inner, int dir,
-                             const Fr *coset, const Fr *extra_scalar, bool defer_scale = false) {
+                             const Fr *coset, const Fr *extra_scalar, bool defer_scale = false, const NttScatter *scatter = nullptr) {
   if (!is_pow2(n) || !is_pow2(outer) || !is_pow2(inner)) return fail(TKM_ERR_INVALID_ARGUMENT, "NTT sizes must be powers of two");
   const bool inverse = dir == TKM_INVERSE;
   const size_t total = outer * n * inner;
@@ -322,9 +342,24 @@ static int32_t ntt_axis_impl(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, 
     return lc < lb ? lc : lb;
   };
 
+  auto arm_scatter = [&]() {
+    if (!scatter) return;
+    p.sc_on = 1;
+    p.sc_logblk = logn - log2_exact(scatter->n_peers);
+    p.sc_sA = scatter->stride_a;
+    p.sc_sB = scatter->stride_b;
+    p.sc_b0 = scatter->b0;
+    for (uint32_t i = 0; i < scatter->n_peers; i++) p.sc_peer[i] = (Fr *)scatter->peers[i];
+  };
+  if (scatter) {
+    if (scatter->n_peers == 0 || scatter->n_peers > NTT_MAX_PEERS || !is_pow2(scatter->n_peers) || scatter->n_peers > n)
+      return fail(TKM_ERR_INVALID_ARGUMENT, "fused exchange needs a power-of-two peer count <= min(%d, axis length)", NTT_MAX_PEERS);
+    if (p.batch_inner && outer != 1) return fail(TKM_ERR_INVALID_ARGUMENT, "fused exchange over a strided axis needs outer == 1");
+  }
   if (logn <= NTT_MAX_LOGL) {
     p.in = in;
     p.out = out;
+    arm_scatter();
     p.logn1 = 0;
     p.logn2 = logn;
     p.logL = logn;
@@ -352,6 +387,7 @@ static int32_t ntt_axis_impl(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, 
   TKM_TRY(launch_pass(ctx, p, inverse));
   p.in = mid.p;
   p.out = out;
+  arm_scatter();
   p.logL = p.logn2;
   p.logC = pick_logC(p.logL);
   p.pass = 2;
@@ -364,6 +400,14 @@ static int32_t ntt_axis_impl(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, 
 
 int32_t ntt_axis(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, size_t n, size_t inner, int dir, const Fr *coset) {
   return ntt_axis_impl(ctx, in, out, outer, n, inner, dir, coset, nullptr);
+}
+
+// Batched 1-D transform whose output is re-sharded across peers in the store of its last pass (no separate transpose,
+// no separate all-to-all).  The 1/n of an inverse transform is applied here.
+int32_t ntt_axis_scatter(tkm_ctx *ctx, const Fr *in, size_t outer, size_t n, size_t inner, int dir, const Fr *coset, void *const *peers,
+                         uint32_t n_peers, uint64_t stride_a, uint64_t stride_b, uint64_t b0) {
+  NttScatter sc{peers, n_peers, stride_a, stride_b, b0};
+  return ntt_axis_impl(ctx, in, nullptr, outer, n, inner, dir, coset, nullptr, false, &sc);
 }
 
 // DensePolynomialExt::_biNTT (bivariate_polynomial/mod.rs:1422-1478).

@@ -189,6 +189,13 @@ class Context:
         k, p = fr_bytes(coset)
         check(self.lib.tkm_ntt_batch(self.h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), n, batch, int(columns_batch), direction, p))
 
+    def ntt_batch_scatter(self, d_in, n, batch, columns_batch, direction, coset, peer_ptrs, stride_a, stride_b, b0):
+        """tkm_ntt_batch_scatter: batched 1-D transform whose last pass stores into the peers' buffers (fused exchange)."""
+        k, pc = fr_bytes(coset)
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+        check(self.lib.tkm_ntt_batch_scatter(self.h, d_in, n, batch, 1 if columns_batch else 0, direction, pc, arr, len(peer_ptrs),
+                                             stride_a, stride_b, b0))
+
     def msm_g1_host(self, scalars, bases):
         """msm::msm(HostSlice scalars, HostSlice bases, MSMConfig::default()) -> affine point (12 x u64)."""
         scalars = _as_fr_array(scalars)

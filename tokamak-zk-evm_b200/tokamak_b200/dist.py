@@ -9,6 +9,12 @@ this is new work scoped by SURVEY.md §8(e).
   up with all x rows of column block g.  The result stays column-sharded (pointwise work is
   layout-agnostic); the inverse transform starts from that layout and returns to row shards.
 
+* Fused exchange (`PeerExchange`, `bintt_sharded_*_fused`): the same re-sharding without NCCL on the data path.  The last
+  pass of the local transform stores every output element straight into the destination rank's buffer over NVLink
+  (peer-mapped symmetric memory; `tkm_ntt_batch_scatter`), so the transpose copy and the all-to-all disappear; ranks only
+  meet at two stream-ordered barriers (before the stores: the peers have finished reading their buffers; after: all stores
+  have landed).
+
 The local compute steps are injected (`LocalOps`) so the exchange logic can be exercised on CPU with the
 gloo backend in tests; the default implementation calls the CUDA library through the C-ABI.
 """
@@ -32,6 +38,12 @@ class CudaLocalOps:
 
     def ntt_cols(self, t, n, batch, direction, coset=None):
         self.ctx.ntt_batch_dev(t.data_ptr(), t.data_ptr(), n, batch, True, direction, coset)
+
+    def ntt_rows_scatter(self, t, n, batch, direction, coset, peer_ptrs, stride_a, stride_b, b0):
+        self.ctx.ntt_batch_scatter(t.data_ptr(), n, batch, False, direction, coset, peer_ptrs, stride_a, stride_b, b0)
+
+    def ntt_cols_scatter(self, t, n, batch, direction, coset, peer_ptrs, stride_a, stride_b, b0):
+        self.ctx.ntt_batch_scatter(t.data_ptr(), n, batch, True, direction, coset, peer_ptrs, stride_a, stride_b, b0)
 
     def msm(self, scalars_t, bases_t, n):
         return self.ctx.msm_g1_dev(scalars_t.data_ptr(), False, bases_t.data_ptr(), n)
@@ -114,3 +126,56 @@ def bintt_sharded_inverse(ops, t, x, y, coset_x=None, coset_y=None, group=None):
         t = _exchange_cols_to_rows(t, x, y_local, world, group)
     ops.ntt_rows(t, y, x // world, INVERSE, coset_y)
     return t
+
+
+class PeerExchange:
+    """Peer-mapped staging buffers for the fused re-sharding of an x-by-y bivariate transform: every rank owns one
+    column-shard buffer [x][y/G] and one row-shard buffer [x/G][y]; all ranks hold device pointers to all of them
+    (torch symmetric memory: CUDA VMM allocations exchanged once at rendezvous)."""
+
+    def __init__(self, x, y, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world & (self.world - 1) or x % self.world or y % self.world:
+            raise ValueError("fused exchange needs a power-of-two number of ranks dividing both extents")
+        self.x, self.y = x, y
+        n_local = x * y // self.world
+        if hasattr(symm_mem, "enable_symm_mem_for_group"):
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+        self.cols = symm_mem.empty((n_local, 4), dtype=torch.int64, device=device)
+        self.rows = symm_mem.empty((n_local, 4), dtype=torch.int64, device=device)
+        self.h_cols = symm_mem.rendezvous(self.cols, group)
+        self.h_rows = symm_mem.rendezvous(self.rows, group)
+        self.cols_ptrs = [int(p) for p in self.h_cols.buffer_ptrs]
+        self.rows_ptrs = [int(p) for p in self.h_rows.buffer_ptrs]
+
+
+def bintt_sharded_forward_fused(ops, ex, t, coset_x=None, coset_y=None):
+    """bintt_sharded_forward with the exchange fused into the Y pass: rows [x/G][y] in `t` -> evaluations as the column
+    shard [x][y/G] in ex.cols (returned as a view)."""
+    x, y, world, rank = ex.x, ex.y, ex.world, ex.rank
+    x_local, yb = x // world, y // world
+    ex.h_cols.barrier()  # nobody is still reading a column buffer from an earlier transform
+    # output (row r, column l) of this rank -> peer l // yb, element (rank*x_local + r) * yb + l % yb
+    ops.ntt_rows_scatter(t, y, x_local, FORWARD, coset_y, ex.cols_ptrs, 1, yb, rank * x_local)
+    ex.h_cols.barrier()  # every rank's stores have landed
+    ops.ntt_cols(ex.cols, x, yb, FORWARD, coset_x)
+    return ex.cols.view(x, yb, 4)
+
+
+def bintt_sharded_inverse_fused(ops, ex, t, coset_x=None, coset_y=None):
+    """Inverse of the above: column shard [x][y/G] in `t` (may be ex.cols) -> coefficients as the row shard [x/G][y] in
+    ex.rows."""
+    x, y, world, rank = ex.x, ex.y, ex.world, ex.rank
+    xb, yb = x // world, y // world
+    ex.h_rows.barrier()
+    # output (row k, column c) of this rank -> peer k // xb, element (k % xb) * y + rank*yb + c
+    ops.ntt_cols_scatter(t, x, yb, INVERSE, coset_x, ex.rows_ptrs, y, 1, rank * yb)
+    ex.h_rows.barrier()
+    ops.ntt_rows(ex.rows, y, xb, INVERSE, coset_y)
+    return ex.rows.view(xb, y, 4)

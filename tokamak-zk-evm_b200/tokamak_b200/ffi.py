@@ -44,6 +44,7 @@ SIGNATURES = {
     "tkm_ntt_batch": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_int32, c_void_p],
     "tkm_msm_g1_host": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_msm_g1": [c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p],
+    "tkm_ntt_batch_scatter": [c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_int32, c_void_p, c_void_p, c_uint32, c_uint64, c_uint64, c_uint64],
     "tkm_g1_bases_to_mont": [c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_g1_bases_from_mont": [c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_msm_g1_rect": [c_void_p, c_void_p, c_int32, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p],
