@@ -142,11 +142,6 @@ class PeerExchange:
             raise ValueError("fused exchange needs a power-of-two number of ranks dividing both extents")
         self.x, self.y = x, y
         n_local = x * y // self.world
-        if hasattr(symm_mem, "enable_symm_mem_for_group"):
-            try:
-                symm_mem.enable_symm_mem_for_group(group.group_name)
-            except Exception:
-                pass
         self.cols = symm_mem.empty((n_local, 4), dtype=torch.int64, device=device)
         self.rows = symm_mem.empty((n_local, 4), dtype=torch.int64, device=device)
         self.h_cols = symm_mem.rendezvous(self.cols, group)
