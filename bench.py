@@ -149,6 +149,20 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "published_reference_cpu": {"value": 1.01, "unit": UNIT, "note": "ICICLE CPU backend, 8192x511 pts, unnamed macOS host (BASELINE.md)"},
     }
+    if not args.skip_prove:
+        # "prove s/tx" on the CPU path: the protocol driver on the oracle backend, bounded sample (every extent of the
+        # reference shape / 4 = 1/16 of the MSM and NTT work); CRS generated on the CPU first (not timed)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
+        import prove_full
+        from oracle_backend import OracleBackend
+
+        cpu = prove_full.run(OracleBackend(), prove_full.reduced_shape(), repeats=1, verify=False)
+        line["prove_sample"] = {"metric": "prove s/tx", "value": cpu["prove_s"], "unit": "s", "higher_is_better": False, "cores": cores, "kind": "port",
+                                "sample": "reference shape with every extent / 4 (n=1024, s_max=64, m_I=1024)", "setup_s_not_timed": cpu["setup_s"],
+                                "stage_s": {k: cpu["median_run"][k] for k in ("init_s", "prove0_s", "prove1_s", "prove2_s", "prove3_s", "prove4_s", "encode_s")},
+                                "proof_sha256": cpu["proof_sha256"],
+                                "published_reference_cpu": {"value": 45.7, "unit": "s", "note": "full shape, real template tx, ICICLE CPU backend (BASELINE.md)"}}
     print(json.dumps(line), flush=True)
 
 

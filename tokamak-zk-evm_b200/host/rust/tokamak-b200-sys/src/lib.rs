@@ -96,6 +96,14 @@ extern "C" {
     pub fn tkm_poly_div_by_ruffini(ctx: *mut tkm_ctx, p: *const tkm_poly, x32: *const u8, y32: *const u8, out_qx: *mut *mut tkm_poly,
                                    out_qy: *mut *mut tkm_poly, out_r32: *mut u8) -> i32;
     pub fn tkm_poly_commit(ctx: *mut tkm_ctx, p: *mut tkm_poly, crs: *const tkm_crs, out96: *mut u8) -> i32;
+    pub fn tkm_r1cs_uvw_polys(ctx: *mut tkm_ctx, s_d: u32, n_rows: *const u32, rp_base: *const u64, row_ptr: *const u32, row_ptr_len: usize,
+                              wire: *const u32, coeff32: *const u8, nnz: usize, sub_of_col: *const u32, var_off: *const u64,
+                              witness32: *const u8, n_vars: usize, n: usize, s_max: usize, out_u: *mut *mut tkm_poly,
+                              out_v: *mut *mut tkm_poly, out_w: *mut *mut tkm_poly) -> i32;
+    pub fn tkm_ntt_batch_scatter(ctx: *mut tkm_ctx, dev_in: *const c_void, n: usize, batch: usize, columns_batch: i32, dir: i32,
+                                 coset32: *const u8, peer_out: *const *mut c_void, n_peers: u32, stride_a: u64, stride_b: u64, b0: u64) -> i32;
+    pub fn tkm_g1_bases_from_mont(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, n: usize) -> i32;
+    pub fn tkm_kernel_time_last(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_event_time_begin(ctx: *mut tkm_ctx) -> i32;
     pub fn tkm_event_time_end(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_launch_count(ctx: *mut tkm_ctx, out: *mut u64) -> i32;
