@@ -156,3 +156,17 @@ def test_proof_is_deterministic_under_fixed_blinding(tiny):
     pts2, sc2, fmt2, _ = PV.prove(pv2)
     assert fmt2 != t["fmt"]
     assert VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], pts2, sc2)
+
+
+@pytest.mark.parametrize("n_placements,small", [(6, 0.0), (7, 1.0)])
+def test_fewer_placements_than_columns_and_random_blinding(tiny, n_placements, small):
+    """Placement lists shorter than s_max leave empty columns (placement_variables.len() <= s_max, iotools/mod.rs:1308);
+    random blinding scalars (Mixer.random) must verify like the fixed ones."""
+    t = tiny
+    pl, perm, inst = S.synthesize(t["params"], t["infos"], t["r1cs"], n_placements=n_placements, seed=9, small_value_fraction=small)
+    pv = PV.Prover(t["be"], t["params"], t["infos"], t["r1cs"], t["sigma"], pl, perm, inst, mixer=PV.Mixer.random(), checks=True)
+    points, scalars, _, _ = PV.prove(pv)
+    pre = PP.preprocess(t["be"], t["params"], t["sigma"], perm, inst)
+    assert VF.verify_snark(t["params"], t["sigma"], pre, inst, points, scalars)
+    with pytest.raises(ValueError):
+        PV.Prover(t["be"], t["params"], t["infos"], t["r1cs"], t["sigma"], pl * 2, perm, inst)  # more placements than s_max
