@@ -232,6 +232,12 @@ int32_t tkm_poly_div_by_ruffini(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x
 /* encode_poly (iotools/mod.rs:2041-2113; group_structures/mod.rs:59-119): optimize_size, bounds
  * check against the CRS grid, commit the trimmed rectangle.  Zero polynomial -> identity. */
 int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t out96[96]);
+/* The same commitment as a begin/end pair: begin queues the MSM and returns a ticket at once; its serial recombination
+ * tail (one warp, 1-2 ms) runs on a side stream, so a caller that queues the next commitment before calling end overlaps
+ * that tail with the next accumulation (prove0..4 produce up to six commitments before the transcript needs any of them).
+ * The polynomial may be freed or modified after begin returns.  At most 32 tickets in flight. */
+int32_t tkm_poly_commit_begin(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, int32_t *out_ticket);
+int32_t tkm_commit_end(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]);
 
 /* ---- instrumentation used by bench.py (not part of the reference API) ---------------------- */
 /* Times one device-resident launch sequence with CUDA events on the context stream; ms out. */

@@ -530,6 +530,32 @@ def test_encode_poly_fixed_tau(ctx, T):
     assert "Insufficient length" in str(e.value)
 
 
+def test_commit_begin_end_tickets(ctx, T):
+    """tkm_poly_commit_begin / tkm_commit_end: queued commitments resolved out of order equal the synchronous ones; the
+    polynomial may be dropped right after begin; the zero polynomial and ticket exhaustion behave."""
+    G = g1s([P.G1_GEN])[0]
+    rs_x, rs_y = 64, 32
+    sigma = T.Sigma1(ctx, O.g1_fixed_base_mul_batch(G, O.random_fr(401, rs_x * rs_y)), rs_x, rs_y)
+    shapes = [(64, 32), (32, 32), (8, 4), (1, 1), (64, 1)]
+    polys = [T.DensePolynomialExt.from_coeffs(ctx, O.random_fr(410 + i, x * y), x, y) for i, (x, y) in enumerate(shapes)]
+    exp = [sigma.encode_poly(p) for p in polys]
+    tickets = [sigma.encode_poly_begin(p) for p in polys]
+    polys = None  # dropped (freed on the stream) while the commitments are in flight
+    zt = sigma.encode_poly_begin(T.DensePolynomialExt.zero(ctx, 4, 4))
+    for i in reversed(range(len(tickets))):
+        assert np.array_equal(sigma.encode_poly_end(tickets[i]), exp[i]), i
+    assert g1_tuple(sigma.encode_poly_end(zt)) is None
+    with pytest.raises(T.TkmError):
+        sigma.encode_poly_end(tickets[0])  # already consumed
+    one = T.DensePolynomialExt.from_coeffs(ctx, frs([5]), 1, 1)
+    held = [sigma.encode_poly_begin(one) for _ in range(32)]
+    with pytest.raises(T.TkmError):
+        sigma.encode_poly_begin(one)  # 33rd ticket
+    for t in held:
+        sigma.encode_poly_end(t)
+    sigma.close()
+
+
 def test_poly_expr_fused_matches_coefficients(ctx, T):
     """test_poly_expr_fused_matches_coefficients (tests.rs:1240-1276), plus a larger instance checked against the oracle."""
     for sx, sy, seed in ((2, 2, 400), (16, 8, 410)):

@@ -203,6 +203,16 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->kev0) cudaEventDestroy(ctx->kev0);
   if (ctx->kev1) cudaEventDestroy(ctx->kev1);
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+  }
+  for (tkm_ctx::Ticket &k : ctx->tickets) {
+    if (k.parts) cudaFree(k.parts);
+    if (k.host) cudaFreeHost(k.host);
+    if (k.ready) cudaEventDestroy(k.ready);
+    if (k.done) cudaEventDestroy(k.done);
+  }
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
     for (cudaEvent_t e : ctx->copy_ev)

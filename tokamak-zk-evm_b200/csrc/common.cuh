@@ -38,6 +38,7 @@ int32_t fail(int32_t code, const char *fmt, ...);
 
 }  // namespace tkm
 
+constexpr int TKM_MAX_TICKETS = 32;
 struct tkm_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -57,6 +58,15 @@ struct tkm_ctx {
   tkm::G1Affine *fb_table = nullptr;
   uint8_t fb_base[96] = {};
   bool fb_valid = false;
+  // asynchronous commitments: the serial recombination tail (k_final) of MSM k runs on side_stream while MSM k+1 accumulates
+  struct Ticket {
+    tkm::G1Xyzz *parts = nullptr;  // per-ticket device buffers read by the tail (parts | window sums | result)
+    uint8_t *host = nullptr;       // pinned 96-byte result slot
+    cudaEvent_t ready = nullptr, done = nullptr;
+    bool busy = false, zero = false;
+  };
+  cudaStream_t side_stream = nullptr;
+  Ticket tickets[TKM_MAX_TICKETS];
   // copy engine side of the pipelined host-buffer MSM (created on first use)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[17] = {};
@@ -159,6 +169,8 @@ struct MsmInput {
 };
 int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c, G1Affine **out_table, uint32_t *out_W);
 int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]);
+int32_t msm_run_async(tkm_ctx *ctx, const MsmInput &in, int32_t *out_ticket);
+int32_t msm_wait(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]);
 int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t pieces, uint8_t out96[96]);
 
 }  // namespace tkm

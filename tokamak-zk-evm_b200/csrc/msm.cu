@@ -544,16 +544,15 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   return TKM_OK;
 }
 
-// Window reduction + recombination of a filled bucket set; reads back the 96-byte canonical affine result.
-static int32_t msm_reduce(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets, uint8_t out96[96]) {
+// Window reduction of a filled bucket set into `parts` on the context stream, then the recombination kernel (one warp,
+// latency-bound: ~1-2 ms) on `final_stream`.  When that is a side stream the caller can already queue the next MSM: the
+// serial tail overlaps the next accumulation instead of idling 147 SMs.
+static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets, G1Xyzz *parts, G1Xyzz *wsum, uint32_t *res_dev,
+                             cudaStream_t final_stream, cudaEvent_t ready) {
   const size_t nsegs = (size_t)m.W * m.nseg;
-  Scratch<G1Xyzz> seg_acc, seg_run, parts, wsum;
-  Scratch<uint32_t> res;
+  Scratch<G1Xyzz> seg_acc, seg_run;
   TKM_TRY(seg_acc.alloc(ctx, nsegs));
   TKM_TRY(seg_run.alloc(ctx, nsegs));
-  TKM_TRY(parts.alloc(ctx, (size_t)m.W * (m.nbits + 1)));
-  TKM_TRY(wsum.alloc(ctx, m.W));
-  TKM_TRY(res.alloc(ctx, 24));
   k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets, m, seg_acc.p, seg_run.p);
   TKM_TRY(launch_check(ctx, "k_bucket_seg"));
   {
@@ -563,21 +562,109 @@ static int32_t msm_reduce(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets,
     if (splits > 64) splits = 64;
     const uint32_t groups = m.W * (m.nbits + 1);
     if (splits == 1) {
-      k_bucket_bits<<<groups, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, 1, parts.p);
+      k_bucket_bits<<<groups, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, 1, parts);
       TKM_TRY(launch_check(ctx, "k_bucket_bits"));
     } else {
       Scratch<G1Xyzz> sliced;
       TKM_TRY(sliced.alloc(ctx, (size_t)groups * splits));
       k_bucket_bits<<<groups * splits, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, splits, sliced.p);
       TKM_TRY(launch_check(ctx, "k_bucket_bits"));
-      k_sum_groups<<<groups, 32, 0, ctx->stream>>>(sliced.p, splits, parts.p);
+      k_sum_groups<<<groups, 32, 0, ctx->stream>>>(sliced.p, splits, parts);
       TKM_TRY(launch_check(ctx, "k_sum_groups"));
     }
   }
-  k_final<<<1, 32, 0, ctx->stream>>>(parts.p, m, wsum.p, nullptr, res.p);
-  TKM_TRY(launch_check(ctx, "k_final"));
+  if (final_stream != ctx->stream) {
+    TKM_CUDA(cudaEventRecord(ready, ctx->stream));
+    TKM_CUDA(cudaStreamWaitEvent(final_stream, ready, 0));
+  }
+  k_final<<<1, 32, 0, final_stream>>>(parts, m, wsum, nullptr, res_dev);
+  return launch_check(ctx, "k_final");
+}
+
+// Synchronous form: reads back the 96-byte canonical affine result.
+static int32_t msm_reduce(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets, uint8_t out96[96]) {
+  Scratch<G1Xyzz> parts, wsum;
+  Scratch<uint32_t> res;
+  TKM_TRY(parts.alloc(ctx, (size_t)m.W * (m.nbits + 1)));
+  TKM_TRY(wsum.alloc(ctx, m.W));
+  TKM_TRY(res.alloc(ctx, 24));
+  TKM_TRY(msm_reduce_to(ctx, m, buckets, parts.p, wsum.p, res.p, ctx->stream, nullptr));
   TKM_CUDA(cudaMemcpyAsync(out96, res.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
   TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TKM_OK;
+}
+
+// ---- asynchronous MSMs: tickets own the small buffers the side-stream tail reads
+constexpr size_t TICKET_PARTS = 2048;  // >= W * (nbits + 1) for every geometry (W <= 64, nbits <= 21)
+static int32_t ticket_acquire(tkm_ctx *ctx, int32_t *out) {
+  if (!ctx->side_stream) TKM_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  for (int t = 0; t < TKM_MAX_TICKETS; t++) {
+    tkm_ctx::Ticket &k = ctx->tickets[t];
+    if (k.busy) continue;
+    if (!k.parts) {
+      TKM_CUDA(cudaMalloc((void **)&k.parts, (TICKET_PARTS + 64) * sizeof(G1Xyzz) + 128));
+      TKM_CUDA(cudaMallocHost((void **)&k.host, 96));
+      TKM_CUDA(cudaEventCreateWithFlags(&k.ready, cudaEventDisableTiming));
+      TKM_CUDA(cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+    }
+    k.busy = true;
+    k.zero = false;
+    *out = t;
+    return TKM_OK;
+  }
+  return fail(TKM_ERR_INVALID_ARGUMENT, "too many commitments in flight (%d): call tkm_commit_end first", TKM_MAX_TICKETS);
+}
+
+int32_t msm_run_async(tkm_ctx *ctx, const MsmInput &in, int32_t *out_ticket) {
+  const size_t n = in.rows * in.cols;
+  int32_t t;
+  TKM_TRY(ticket_acquire(ctx, &t));
+  tkm_ctx::Ticket &k = ctx->tickets[t];
+  *out_ticket = t;
+  if (n == 0) {
+    k.zero = true;
+    return TKM_OK;
+  }
+  int32_t st = TKM_OK;
+  if (n > 0x7fffffffull / 32) st = fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
+  if (st == TKM_OK && in.idx && in.rows != 1) st = fail(TKM_ERR_INVALID_ARGUMENT, "indexed MSM must be one row");
+  if (st == TKM_OK) {
+    const MsmGeom m = pick_geom(n, in.pre_c, in.pre_stride);
+    if ((size_t)m.W * (m.nbits + 1) > TICKET_PARTS || m.W > 64) st = fail(TKM_ERR_INTERNAL, "ticket buffers too small for this geometry");
+    Scratch<G1Xyzz> buckets;
+    if (st == TKM_OK) st = buckets.alloc(ctx, (size_t)m.nbuckets + 1);
+    if (st == TKM_OK) {
+      k_fill_identity<<<grid_for((size_t)m.nbuckets + 1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, (size_t)m.nbuckets + 1);
+      st = launch_check(ctx, "k_fill_identity");
+    }
+    if (st == TKM_OK) st = msm_accumulate_pass(ctx, in, m, buckets.p);
+    G1Xyzz *wsum = k.parts + TICKET_PARTS;
+    uint32_t *res = reinterpret_cast<uint32_t *>(k.parts + TICKET_PARTS + 64);
+    if (st == TKM_OK) st = msm_reduce_to(ctx, m, buckets.p, k.parts, wsum, res, ctx->side_stream, k.ready);
+    if (st == TKM_OK) {
+      cudaError_t e = cudaMemcpyAsync(k.host, res, 96, cudaMemcpyDeviceToHost, ctx->side_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(k.done, ctx->side_stream);
+      if (e != cudaSuccess) st = fail(TKM_ERR_CUDA, "queuing the MSM tail failed: %s", cudaGetErrorString(e));
+    }
+  }
+  if (st != TKM_OK) k.busy = false;
+  return st;
+}
+
+int32_t msm_wait(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]) {
+  if (ticket < 0 || ticket >= TKM_MAX_TICKETS || !ctx->tickets[ticket].busy) return fail(TKM_ERR_INVALID_ARGUMENT, "invalid commitment ticket %d", ticket);
+  tkm_ctx::Ticket &k = ctx->tickets[ticket];
+  if (k.zero) {
+    memset(out96, 0, 96);
+  } else {
+    cudaError_t e = cudaEventSynchronize(k.done);
+    if (e != cudaSuccess) {
+      k.busy = false;
+      return fail(TKM_ERR_CUDA, "MSM tail failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(out96, k.host, 96);
+  }
+  k.busy = false;
   return TKM_OK;
 }
 

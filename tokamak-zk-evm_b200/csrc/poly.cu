@@ -827,31 +827,55 @@ int32_t tkm_poly_div_by_ruffini(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x
   return TKM_OK;
 }
 
+static int32_t commit_input(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, MsmInput *in, bool *zero) {
+  int64_t xd, yd;
+  TKM_TRY(poly_find_degree(ctx, p, &xd, &yd));
+  *zero = xd < 0 || yd < 0;  // the zero polynomial commits to the identity (iotools/mod.rs:2057-2059)
+  if (*zero) return TKM_OK;
+  const size_t tx = (size_t)xd + 1, ty = (size_t)yd + 1;
+  if (tx > crs->rows || ty > crs->cols) return fail(TKM_ERR_INVALID_ARGUMENT, "Insufficient length of sigma.sigma_1.xy_powers");
+  in->scalars = p->d;
+  in->scalars_mont = true;
+  in->scalar_row_stride = p->y_size;
+  in->bases = crs->pre ? crs->pre : crs->d;
+  in->base_row_stride = crs->cols;
+  in->rows = tx;
+  in->cols = ty;
+  in->idx = nullptr;
+  if (crs->pre) {  // fixed-base tables (tkm_crs_precompute): one shared bucket set, no Horner tail
+    in->pre_c = crs->pre_c;
+    in->pre_stride = (uint32_t)(crs->rows * crs->cols);
+  }
+  return TKM_OK;
+}
+
 int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t out96[96]) {
   API_BEGIN
   TKM_REQUIRE(p && crs && out96, "null argument");
-  int64_t xd, yd;
-  TKM_TRY(poly_find_degree(ctx, p, &xd, &yd));
-  if (xd < 0 || yd < 0) {  // zero polynomial commits to the identity (iotools/mod.rs:2057-2059)
+  MsmInput in;
+  bool zero;
+  TKM_TRY(commit_input(ctx, p, crs, &in, &zero));
+  if (zero) {
     memset(out96, 0, 96);
     return TKM_OK;
   }
-  const size_t tx = (size_t)xd + 1, ty = (size_t)yd + 1;
-  if (tx > crs->rows || ty > crs->cols) return fail(TKM_ERR_INVALID_ARGUMENT, "Insufficient length of sigma.sigma_1.xy_powers");
-  MsmInput in;
-  in.scalars = p->d;
-  in.scalars_mont = true;
-  in.scalar_row_stride = p->y_size;
-  in.bases = crs->pre ? crs->pre : crs->d;
-  in.base_row_stride = crs->cols;
-  in.rows = tx;
-  in.cols = ty;
-  in.idx = nullptr;
-  if (crs->pre) {  // fixed-base tables (tkm_crs_precompute): one shared bucket set, no Horner tail
-    in.pre_c = crs->pre_c;
-    in.pre_stride = (uint32_t)(crs->rows * crs->cols);
-  }
   return msm_run(ctx, in, out96);
+}
+
+int32_t tkm_poly_commit_begin(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, int32_t *out_ticket) {
+  API_BEGIN
+  TKM_REQUIRE(p && crs && out_ticket, "null argument");
+  MsmInput in;
+  bool zero;
+  TKM_TRY(commit_input(ctx, p, crs, &in, &zero));
+  if (zero) in.rows = in.cols = 0;
+  return msm_run_async(ctx, in, out_ticket);
+}
+
+int32_t tkm_commit_end(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]) {
+  API_BEGIN
+  TKM_REQUIRE(out96, "null out pointer");
+  return msm_wait(ctx, ticket, out96);
 }
 
 }  // extern "C"

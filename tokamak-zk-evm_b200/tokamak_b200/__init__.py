@@ -293,6 +293,17 @@ class Sigma1:
         check(self.ctx.lib.tkm_poly_commit(self.ctx.h, poly.h, self.h, _vp(out)))
         return out
 
+    def encode_poly_begin(self, poly):
+        """Queue a commitment (tkm_poly_commit_begin); returns a ticket for encode_poly_end."""
+        t = ctypes.c_int32()
+        check(self.ctx.lib.tkm_poly_commit_begin(self.ctx.h, poly.h, self.h, ctypes.byref(t)))
+        return t.value
+
+    def encode_poly_end(self, ticket):
+        out = np.zeros(12, dtype=np.uint64)
+        check(self.ctx.lib.tkm_commit_end(self.ctx.h, ticket, _vp(out)))
+        return out
+
     def device_ptr(self):
         p = ctypes.c_void_p()
         check(self.ctx.lib.tkm_crs_device_ptr(self.h, ctypes.byref(p), None, None))

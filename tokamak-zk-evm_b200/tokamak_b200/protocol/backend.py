@@ -65,6 +65,18 @@ class GpuTable:
             pass
 
 
+class _PendingCommit:
+    def __init__(self, ctx, ticket):
+        self.ctx, self.ticket, self.value, self.done = ctx, ticket, None, False
+
+    def get(self):
+        if not self.done:
+            out = np.zeros(12, dtype=np.uint64)
+            check(self.ctx.lib.tkm_commit_end(self.ctx.h, self.ticket, _vp(out)))
+            self.value, self.done = g1_to_tuple(out), True
+        return self.value
+
+
 class GpuBackend:
     name = "b200"
 
@@ -118,6 +130,13 @@ class GpuBackend:
         out = np.zeros(12, dtype=np.uint64)
         check(self.ctx.lib.tkm_poly_commit(self.ctx.h, poly.h, table.h, _vp(out)))
         return g1_to_tuple(out)
+
+    def commit_async(self, table, poly):
+        """tkm_poly_commit_begin: queue the commitment and return at once; .get() (tkm_commit_end) waits for its tail.
+        The recombination tail of this MSM overlaps whatever is queued next on the context stream."""
+        t = ctypes.c_int32()
+        check(self.ctx.lib.tkm_poly_commit_begin(self.ctx.h, poly.h, table.h, ctypes.byref(t)))
+        return _PendingCommit(self.ctx, t.value)
 
     def msm_indexed(self, table, idx, scalars):
         idx = np.ascontiguousarray(idx, dtype=np.uint32)

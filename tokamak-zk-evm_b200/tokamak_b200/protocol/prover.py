@@ -179,11 +179,24 @@ class Prover:
         return self.be.from_rou_evals(frs_from_ints(ev), size, 1) if along_x else self.be.from_rou_evals(frs_from_ints(ev), 1, size)
 
     def encode(self, poly, name):
+        """Sigma1::encode_poly.  With a backend that can queue commitments (commit_async) this returns a pending handle:
+        the stage collects its commitments and resolves them together (`_resolve`), so the serial tail of one MSM overlaps
+        the next polynomial combination and accumulation instead of stalling the device."""
         t0 = time.perf_counter()
-        pt = self.be.commit(self.sigma.xy_powers, poly)
+        if hasattr(self.be, "commit_async"):
+            pt = self.be.commit_async(self.sigma.xy_powers, poly)
+        else:
+            pt = self.be.commit(self.sigma.xy_powers, poly)
         self.t.add("encode", time.perf_counter() - t0)
         self.t.add("encode." + name, time.perf_counter() - t0)
         return pt
+
+    def _resolve(self, d):
+        t0 = time.perf_counter()
+        out = {k: (v.get() if hasattr(v, "get") else v) for k, v in d.items()}
+        self.t.add("encode", time.perf_counter() - t0)
+        self.t.add("encode.wait", time.perf_counter() - t0)
+        return out
 
     # ---- binding (prove/src/lib.rs:1092-1176; sparse MSMs: group_structures/mod.rs:145-300)
     def _binding(self, placements, infos, wt):
@@ -214,7 +227,7 @@ class Prover:
         terms += [(sg.delta_inv_alphak_yi_ty[2][i], mx.rW_Y[i]) for i in range(3)]
         terms += [(sg.delta_inv_alphak_yi_ty[3][i], mx.rB_Y[i]) for i in range(2)]
         O_prv = be.g1_add(O_prv_core, be.msm_points([t[0] for t in terms], [t[1] for t in terms]))
-        return {"A_free": A_free, "O_pub_free": O_pub_free, "O_mid": O_mid, "O_prv": O_prv}
+        return self._resolve({"A_free": A_free, "O_pub_free": O_pub_free, "O_mid": O_mid, "O_prv": O_prv})
 
     def _encode_statement(self, wt, lo, hi, table):
         """encode_statement_common (group_structures/mod.rs:266-300): every wire of every placement whose global index
@@ -244,8 +257,9 @@ class Prover:
         term_B_zk = self.low_degree_x_times_vanishing(mx.rB_X, self.m_i) + self.low_degree_y_times_vanishing(mx.rB_Y, p.s_max)
         self.cache["term_b_zk"] = term_B_zk
         B = self.encode(self.bXY + term_B_zk, "B")
+        out = self._resolve({"U": U, "V": V, "W": W, "Q_AX": Q_AX, "Q_AY": Q_AY, "B": B})
         self.t.add("prove0", time.perf_counter() - t0)
-        return {"U": U, "V": V, "W": W, "Q_AX": Q_AX, "Q_AY": Q_AY, "B": B}
+        return out
 
     def _check_quotient(self, pXY, qx, qy, c, d):
         xe, ye = secrets.randbelow(R_MOD), secrets.randbelow(R_MOD)
@@ -267,9 +281,9 @@ class Prover:
         r_evals = self.be.recursion_evals(f.to_rou_evals(), g.to_rou_evals(), self.m_i, p.s_max)
         self.rXY = self.be.from_rou_evals(r_evals, self.m_i, p.s_max)
         RXY = self.rXY + (self.t_mi * mx.rR_X + self.t_smax * mx.rR_Y)
-        R = self.encode(RXY, "R")
+        out = self._resolve({"R": self.encode(RXY, "R")})
         self.t.add("prove1", time.perf_counter() - t0)
-        return {"R": R}
+        return out
 
     # ---- prove2 (:1958-2270)
     def prove2(self, thetas, kappa0):
@@ -300,6 +314,7 @@ class Prover:
             d1 = lin(r_D1, rB) + g_D * rR
             d2 = lin(r_D2, rB) + g_D * rR
             out[name] = self.encode(comb((ONE, q), (rR, KL), (kappa0, mul_by_x_minus_one(d1)), (k0sq, K0 * d2)), name)
+        out = self._resolve(out)
         self.t.add("prove2", time.perf_counter() - t0)
         return out
 
@@ -379,7 +394,10 @@ class Prover:
         # Pi_B: opening of a_free
         A_eval = self.a_free_X.eval(chi, zeta)
         pi_B_XY, _piBy, _ = (self.a_free_X - A_eval).div_by_ruffini(chi, zeta)
-        Pi_B = be.g1_mul(self.encode(pi_B_XY, "Pi_B"), pow(kappa1, 4, R_MOD))
+        r = self._resolve({"Pi_AX": Pi_AX, "Pi_AY": Pi_AY, "M_X": M_X, "M_Y": M_Y, "N_X": N_X, "N_Y": N_Y, "Pi_CX": Pi_CX, "Pi_CY": Pi_CY,
+                           "Pi_B": self.encode(pi_B_XY, "Pi_B")})
+        Pi_AX, Pi_AY, M_X, M_Y, N_X, N_Y, Pi_CX, Pi_CY = (r[k] for k in ("Pi_AX", "Pi_AY", "M_X", "M_Y", "N_X", "N_Y", "Pi_CX", "Pi_CY"))
+        Pi_B = be.g1_mul(r["Pi_B"], pow(kappa1, 4, R_MOD))
         Pi_X = be.g1_add(be.g1_add(Pi_AX, Pi_CX), Pi_B)
         Pi_Y = be.g1_add(Pi_AY, Pi_CY)
         self.t.add("prove4", time.perf_counter() - t0)
