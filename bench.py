@@ -36,7 +36,7 @@ G1_GEN = (
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ncu_k_accumulate_summary.csv: 2^22-point MSM; profiles/r01_ncu_k_ntt_pass_summary.csv: 16384 x 512 forward)
-NCU_TRAFFIC = {"k_accumulate": 11.829, "k_ntt_pass_x3": 1.459}
+NCU_TRAFFIC = {"k_accumulate": 11.913, "k_ntt_pass_x3": 1.464}
 
 
 def measured_peaks():
