@@ -174,7 +174,39 @@ class GpuBackend:
     def g1_mul(self, a, k):
         return g1_to_tuple(self.ctx.g1_mul(g1_from_tuple(a), k % R_MOD))
 
+    # ---- prove2's combined copy-constraint polynomial
+    def p_comb(self, r, g, f, r_wX, r_wXwY, KL, K0, kappa0, x_size, y_size):
+        """(r - 1) KL + kappa0 (X - 1)(r g - r(X/w,Y) f) + kappa0^2 K0 (r g - r(X/w,Y/w) f) as one fused expression in the
+        evaluation domain x_size x y_size: one NTT per distinct leaf, pointwise passes, one inverse NTT
+        (PolyExpr::evaluate_fused_with_domain, prove/src/lib.rs:2110-2146)."""
+        from .. import PolyExpr as E
+
+        rg = E.mul(E.poly(r), E.poly(g))
+        p1 = E.mul(E.sub(E.poly(r), E.scalar(1)), E.poly(KL))
+        p2 = E.mul_x_minus_one(E.sub(rg, E.mul(E.poly(r_wX), E.poly(f))))
+        p3 = E.mul(E.poly(K0), E.sub(rg, E.mul(E.poly(r_wXwY), E.poly(f))))
+        expr = E.weighted_sum([(1, p1), (kappa0 % R_MOD, p2), (kappa0 * kappa0 % R_MOD, p3)])
+        return expr.evaluate_fused_with_domain(x_size, y_size, self.ctx)
+
     # ---- prove1's recursion polynomial
+    def recursion_poly(self, f, g, m_i, s_max):
+        """r(X,Y) from the polynomials f, g without leaving the device (prove/src/lib.rs:1835-1880): evaluate both on the
+        grid, scalers = g/f, transpose to placement-major order, exclusive suffix product, transpose back, interpolate."""
+        ctx = self.ctx
+        n = m_i * s_max
+        if f.shape != (m_i, s_max) or g.shape != (m_i, s_max):
+            return None
+        fe, ge = f.clone(), g.clone()
+        check(ctx.lib.tkm_poly_ntt_inplace(ctx.h, fe.h, 0, None, None))
+        check(ctx.lib.tkm_poly_ntt_inplace(ctx.h, ge.h, 0, None, None))
+        pf, pg = fe.device_ptr(), ge.device_ptr()
+        check(ctx.lib.tkm_fr_vec_op(ctx.h, 3, pg, pf, pg, n))  # OP_DIV
+        check(ctx.lib.tkm_fr_transpose(ctx.h, pg, pf, m_i, s_max))
+        check(ctx.lib.tkm_fr_suffix_product(ctx.h, pf, pf, n))
+        check(ctx.lib.tkm_fr_transpose(ctx.h, pf, pg, s_max, m_i))
+        check(ctx.lib.tkm_poly_ntt_inplace(ctx.h, ge.h, 1, None, None))
+        return ge
+
     def recursion_evals(self, f_evals, g_evals, m_i, s_max):
         """r(X,Y) on the grid (prove/src/lib.rs:1853-1870): scalers = g/f, transposed to placement-major order,
         r[last] = 1, r[k] = r[k+1] * scalers[k+1], transposed back.  All on the device."""

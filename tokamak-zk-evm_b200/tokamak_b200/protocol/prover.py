@@ -278,8 +278,10 @@ class Prover:
         t0 = time.perf_counter()
         p, mx = self.p, self.mixer
         f, g = self._fg(thetas)
-        r_evals = self.be.recursion_evals(f.to_rou_evals(), g.to_rou_evals(), self.m_i, p.s_max)
-        self.rXY = self.be.from_rou_evals(r_evals, self.m_i, p.s_max)
+        self.rXY = self.be.recursion_poly(f, g, self.m_i, p.s_max) if hasattr(self.be, "recursion_poly") else None
+        if self.rXY is None:
+            r_evals = self.be.recursion_evals(f.to_rou_evals(), g.to_rou_evals(), self.m_i, p.s_max)
+            self.rXY = self.be.from_rou_evals(r_evals, self.m_i, p.s_max)
         RXY = self.rXY + (self.t_mi * mx.rR_X + self.t_smax * mx.rR_Y)
         out = self._resolve({"R": self.encode(RXY, "R")})
         self.t.add("prove1", time.perf_counter() - t0)
