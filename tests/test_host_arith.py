@@ -53,6 +53,30 @@ def test_field_ops(L, name):
         assert toint(o) == pow(a, mod - 2, mod)
 
 
+@pytest.mark.parametrize("name", ["fr", "fq"])
+def test_dedicated_squaring(L, name):
+    """Fp::sqr (N(N+1)/2 products + interleaved reduction) against big integers: canonical inputs and raw Montgomery
+    inputs up to the container limit used inside the point formulas."""
+    mod, n, fn = (P.R_MOD, 8, L.h_fr_op) if name == "fr" else (P.Q_MOD, 12, L.h_fq_op)
+    rng = random.Random(7)
+    R = 1 << (32 * n)
+    rinv = pow(R, -1, mod)
+    top = (1 << 31) - 1
+    edge = [0, 1, 2, 3, mod - 1, mod - 2, R % mod, (1 << 32) - 1, 1 << 32, (1 << 31), mod >> 1, (mod >> 1) + 1,
+            int("ffffffff" * (n - 1), 16), int("80000000" * (n - 1), 16) % mod, int("7fffffff" + "ffffffff" * (n - 1), 16) % mod]
+    vals = edge + [rng.randrange(mod) for _ in range(600)] + [(rng.randrange(1 << 31) << (32 * (n - 1))) % mod for _ in range(50)]
+    for a in vals:
+        o = np.zeros(n, dtype=np.uint32)
+        fn(5, pp(u32(a, n)), pp(u32(a, n)), pp(o))
+        assert toint(o) == a * a % mod, (name, hex(a))
+        o2 = np.zeros(n, dtype=np.uint32)
+        fn(6, pp(u32(a, n)), pp(u32(a, n)), pp(o2))  # raw Montgomery square: a*a/R mod p
+        assert toint(o2) == a * a * rinv % mod, (name, "raw", hex(a))
+        o3 = np.zeros(n, dtype=np.uint32)
+        fn(4, pp(u32(a, n)), pp(u32(a, n)), pp(o3))
+        assert np.array_equal(o2, o3)
+
+
 def g1b(pt):
     return np.frombuffer(P.g1_to_bytes(pt), dtype=np.uint32).copy()
 
