@@ -187,8 +187,13 @@ def write_synthesizer_output(path, placements, permutation, instance: Instance):
 
 
 def read_synthesizer_output(path):
-    placements = [PlacementVariables(d["subcircuitId"], [from_hex(v) for v in d["variables"]])
-                  for d in json.load(open(os.path.join(path, "placementVariables.json")))]
+    # int(v, 16) accepts the 0x prefix; values above r (never produced by the synthesizer) are reduced like from_hex does
+    placements = []
+    for d in json.load(open(os.path.join(path, "placementVariables.json"))):
+        vals = [int(v, 16) for v in d["variables"]]
+        if vals and max(vals) >= R_MOD:
+            vals = [v % R_MOD for v in vals]
+        placements.append(PlacementVariables(d["subcircuitId"], vals))
     permutation = [Permutation(d["row"], d["col"], d["X"], d["Y"]) for d in json.load(open(os.path.join(path, "permutation.json")))]
     d = json.load(open(os.path.join(path, "instance.json")))
     inst = Instance(*[[from_hex(v) for v in d[k]] for k in ("a_pub_user", "a_pub_block", "a_pub_function")])
