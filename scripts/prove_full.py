@@ -32,6 +32,8 @@ def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: 
         sync()
     t_setup = time.perf_counter() - t
     log("setup done", t_setup)
+    if hasattr(be, "reserve"):
+        be.reserve(min(24 << 30, 48 * params.n * params.s_max * 32 * 16))  # one-time pool growth, like the CRS upload
     t = time.perf_counter()
     csr = qap.LibraryCSR(r1cs)  # once per library, like the resident CRS
     t_csr = time.perf_counter() - t

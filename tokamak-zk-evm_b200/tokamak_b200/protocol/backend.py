@@ -93,6 +93,14 @@ class GpuBackend:
     def init_ntt_domain(self, size):
         self.ctx.init_ntt_domain_for_size(size)
 
+    def reserve(self, nbytes):
+        """Grow the stream-ordered memory pool once (the pool never returns memory to the driver): later polynomial and
+        MSM scratch allocations are then served without driver calls.  A prove at the reference shape peaks at a few GB; when
+        the pool has to grow inside a stage that stage stalls for ~0.7 s."""
+        p = self.ctx.dev_alloc(nbytes)
+        self.ctx.dev_free(p)
+        self.ctx.sync()
+
     def uvw_polys(self, params, csr, wt):
         """read_R1CS_gen_uvwXY on the device (tkm_r1cs_uvw_polys): sparse R1CS x witness + three inverse biNTTs."""
         u, v, w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
