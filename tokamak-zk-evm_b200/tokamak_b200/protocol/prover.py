@@ -4,7 +4,7 @@ integers mod r.  `prove()` runs the reference's main (prove/src/main.rs:39-62): 
 kappa0 -> prove2 -> (chi, zeta) -> prove3 -> kappa1 -> prove4, and returns the proof in the reference's layout."""
 import secrets
 import time
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List
 
 import numpy as np
