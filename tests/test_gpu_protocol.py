@@ -74,3 +74,34 @@ def test_reference_shape_prove_verifies_and_matches_golden_hash(backends):
     assert VF.verify_snark(params, sigma, pre, inst, points, scalars)
     golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prove_reference_shape.json")))
     assert hashlib.sha256(json.dumps(fmt, sort_keys=True).encode()).hexdigest() == golden["proof_sha256"]
+
+
+def test_r1cs_uvw_polys_against_host_products(backends):
+    """tkm_r1cs_uvw_polys (device sparse R1CS x witness + inverse biNTT) against the literal per-placement dot products of
+    read_R1CS_gen_uvwXY on Python integers, with empty columns; invalid metadata is rejected before any launch."""
+    import ctypes
+
+    import oracle_ffi as O
+    import tokamak_b200 as T
+    from tokamak_b200.protocol import qap
+
+    gpu, orc = backends
+    params, infos, r1cs = S.make_library(_small_shape(), seed=5)
+    pl, _, _ = S.synthesize(params, infos, r1cs, n_placements=9, seed=6, small_value_fraction=0.2)  # columns 9..15 stay empty
+    gpu.init_ntt_domain(params.n * params.s_max)
+    csr, wt = qap.LibraryCSR(r1cs), qap.WitnessTable(params, pl, infos)
+    got = gpu.uvw_polys(params, csr, wt)
+    exp = qap.uvw_evals(params, pl, r1cs)
+    for g, e in zip(got, exp):
+        assert g.shape == (params.n, params.s_max)
+        assert np.array_equal(g.to_rou_evals(), e)
+        assert np.array_equal(g.copy_coeffs(), O.bintt(e, params.n, params.s_max, True))
+    bad = np.array(wt.sub_of_col, copy=True)
+    bad[0] = len(infos)  # subcircuit id out of range
+    u, v, w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    vals = np.ascontiguousarray(wt.values)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = gpu.ctx.lib.tkm_r1cs_uvw_polys(gpu.ctx.h, len(csr.n_rows), vp(csr.n_rows), vp(csr.rp_base), vp(csr.row_ptr), csr.row_ptr.shape[0], vp(csr.wire),
+                                        vp(csr.coeff), csr.wire.shape[0], vp(bad), vp(wt.var_off), vp(vals), vals.shape[0], params.n, params.s_max,
+                                        ctypes.byref(u), ctypes.byref(v), ctypes.byref(w))
+    assert rc == T.ffi.TKM_ERR_INVALID_ARGUMENT if hasattr(T.ffi, "TKM_ERR_INVALID_ARGUMENT") else rc != 0
