@@ -1,0 +1,239 @@
+// The reference's own library tests (packages/backend/libs/src/tests.rs) restated against the C++ host mirror of the
+// `libs` API: same test names, same identities, run on the GPU through the C-ABI.  Usage:
+//   test_libs            run every test on cuda:0, print "ALL PASSED"
+//   test_libs --scalar   host-only: print ScalarField arithmetic results for a seeded stream (checked by the CPU suite)
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <iostream>
+
+#include "tokamak_b200.hpp"
+
+using namespace tokamak_b200;
+
+#define EXPECT(cond)                                                                       \
+  do {                                                                                     \
+    if (!(cond)) throw std::runtime_error(std::string("expectation failed: ") + #cond + " (line " + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+static const uint8_t G1_GEN_LE[96] = {
+    0xbb, 0xc6, 0x22, 0xdb, 0x0a, 0xf0, 0x3a, 0xfb, 0xef, 0x1a, 0x7a, 0xf9, 0x3f, 0xe8, 0x55, 0x6c, 0x58, 0xac, 0x1b, 0x17, 0x3f, 0x3a, 0x4e, 0xa1,
+    0x05, 0xb9, 0x74, 0x97, 0x4f, 0x8c, 0x68, 0xc3, 0x0f, 0xac, 0xa9, 0x4f, 0x8c, 0x63, 0x95, 0x26, 0x94, 0xd7, 0x97, 0x31, 0xa7, 0xd3, 0xf1, 0x17,
+    0xe1, 0xe7, 0xc5, 0x46, 0x29, 0x23, 0xaa, 0x0c, 0xe4, 0x8a, 0x88, 0xa2, 0x44, 0xc7, 0x3c, 0xd0, 0xed, 0xb3, 0x04, 0x2c, 0xcb, 0x18, 0xdb, 0x00,
+    0xf6, 0x0a, 0xd0, 0xd5, 0x95, 0xe0, 0xf5, 0xfc, 0xe4, 0x8a, 0x1d, 0x74, 0xed, 0x30, 0x9e, 0xa0, 0xf1, 0xa0, 0xaa, 0xe3, 0x81, 0xf4, 0xb3, 0x08};
+
+static G1Affine generator() {
+  G1Affine g;
+  std::memcpy(g.b, G1_GEN_LE, 96);
+  return g;
+}
+
+// Simple 2x2 polynomial 1 + 3y + 2x + 4xy (tests.rs:63-72)
+static DensePolynomialExt create_simple_polynomial(const Context &c) {
+  return DensePolynomialExt::from_coeffs(c, {ScalarField::from_u32(1), ScalarField::from_u32(3), ScalarField::from_u32(2), ScalarField::from_u32(4)}, 2, 2);
+}
+static ScalarField host_eval(const std::vector<ScalarField> &co, size_t xs, size_t ys, const ScalarField &x, const ScalarField &y) {
+  ScalarField acc = ScalarField::zero();
+  for (size_t i = xs; i-- > 0;) {
+    ScalarField row = ScalarField::zero();
+    for (size_t j = ys; j-- > 0;) row = row * y + co[i * ys + j];
+    acc = acc * x + row;
+  }
+  return acc;
+}
+
+static int run_gpu_tests() {
+  Context ctx(0);
+  ScalarCfg rng(2026);
+  int passed = 0;
+  auto T = [&](const char *name, const std::function<void()> &f) {
+    f();
+    std::printf("ok   %s\n", name);
+    passed++;
+  };
+
+  T("test_domain_errors", [&] {  // "NTT domain size too small" panics (bivariate_polynomial/mod.rs:1437-1445)
+    Context fresh(0);
+    auto co = rng.generate_random(16);
+    auto p = DensePolynomialExt::from_coeffs(fresh, co, 4, 4);
+    bool threw = false;
+    try {
+      p.to_rou_evals();
+    } catch (const std::runtime_error &e) {
+      threw = std::string(e.what()).find("NTT domain") != std::string::npos;
+    }
+    EXPECT(threw);
+  });
+  ctx.init_ntt_domain_for_size(1 << 16);
+
+  T("test_from_coeffs", [&] {
+    auto poly = create_simple_polynomial(ctx);
+    EXPECT(poly.x_size() == 2 && poly.y_size() == 2);
+    EXPECT(poly.find_degree() == std::make_pair((int64_t)1, (int64_t)1));
+    EXPECT(poly.get_coeff(0, 0) == ScalarField::from_u32(1) && poly.get_coeff(0, 1) == ScalarField::from_u32(3));
+    EXPECT(poly.get_coeff(1, 0) == ScalarField::from_u32(2) && poly.get_coeff(1, 1) == ScalarField::from_u32(4));
+    bool threw = false;
+    try {
+      DensePolynomialExt::from_coeffs(ctx, rng.generate_random(5), 2, 2);
+    } catch (const std::runtime_error &) {
+      threw = true;
+    }
+    EXPECT(threw);
+  });
+  T("test_from_evals", [&] {  // tests.rs:107-131
+    const size_t x = 2048, y = 1;
+    auto evals = rng.generate_random(x * y);
+    auto poly = DensePolynomialExt::from_rou_evals(ctx, evals, x, y);
+    EXPECT(poly.to_rou_evals() == evals);
+  });
+  T("test_coset_ntt_matches_manual_scaling", [&] {  // tests.rs:134-180
+    const size_t x = 16, y = 8;
+    auto poly = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(x * y), x, y);
+    auto cx = rng.generate_random(1)[0], cy = rng.generate_random(1)[0];
+    auto evals_coset = poly.to_rou_evals(&cx, &cy);
+    auto evals_legacy = poly.scale_coeffs_x(cx).scale_coeffs_y(cy).to_rou_evals();
+    EXPECT(evals_coset == evals_legacy);
+    auto poly_coset = DensePolynomialExt::from_rou_evals(ctx, evals_coset, x, y, &cx, &cy);
+    auto poly_legacy = DensePolynomialExt::from_rou_evals(ctx, evals_coset, x, y).scale_coeffs_x(cx.inv()).scale_coeffs_y(cy.inv());
+    EXPECT(poly_coset.copy_coeffs() == poly_legacy.copy_coeffs());
+    EXPECT(poly_coset.copy_coeffs() == poly.copy_coeffs());
+  });
+  T("test_add / test_sub / mismatched sizes", [&] {  // tests.rs:183-420
+    auto p1 = create_simple_polynomial(ctx), p2 = create_simple_polynomial(ctx);
+    auto sum = p1 + p2, diff = p1 - p2;
+    EXPECT(sum.get_coeff(1, 1) == ScalarField::from_u32(8) && sum.get_coeff(0, 1) == ScalarField::from_u32(6));
+    EXPECT(diff.find_degree() == std::make_pair((int64_t)-1, (int64_t)-1));
+    auto big = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(8 * 4), 8, 4);
+    auto s2 = p1 + big;
+    EXPECT(s2.x_size() == 8 && s2.y_size() == 4);
+    EXPECT(s2.get_coeff(1, 1) == big.get_coeff(1, 1) + ScalarField::from_u32(4));
+    EXPECT(s2.get_coeff(7, 3) == big.get_coeff(7, 3));
+    EXPECT(p1.get_coeff(1, 1) == ScalarField::from_u32(4));  // operators never mutate their inputs
+  });
+  T("test_mul_scalar / test_add_scalar / test_sub_scalar / test_neg", [&] {  // tests.rs:711-798
+    auto p = create_simple_polynomial(ctx);
+    auto s = ScalarField::from_u32(7);
+    EXPECT((p * s).get_coeff(1, 1) == ScalarField::from_u32(28) && (s * p).get_coeff(0, 1) == ScalarField::from_u32(21));
+    EXPECT((p + s).get_coeff(0, 0) == ScalarField::from_u32(8) && (p + s).get_coeff(1, 0) == ScalarField::from_u32(2));
+    EXPECT((p - s).get_coeff(0, 0) == ScalarField::from_u32(1) - s);
+    EXPECT((-p).get_coeff(1, 0) == ScalarField::zero() - ScalarField::from_u32(2));
+  });
+  T("test_eval", [&] {  // tests.rs:838-884
+    const size_t x = 32, y = 16;
+    auto co = rng.generate_random(x * y);
+    auto p = DensePolynomialExt::from_coeffs(ctx, co, x, y);
+    auto pt = rng.generate_random(2);
+    EXPECT(p.eval(pt[0], pt[1]) == host_eval(co, x, y, pt[0], pt[1]));
+  });
+  T("test_resize / test_optimize_size / test_mul_monomial", [&] {  // tests.rs:886-933,1011-1040
+    auto p = create_simple_polynomial(ctx);
+    p.resize(8, 4);
+    EXPECT(p.x_size() == 8 && p.y_size() == 4 && p.get_coeff(1, 1) == ScalarField::from_u32(4) && p.get_coeff(7, 3) == ScalarField::zero());
+    p.optimize_size();
+    EXPECT(p.x_size() == 2 && p.y_size() == 2);
+    auto m = p.mul_monomial(3, 2);
+    EXPECT(m.get_coeff(4, 3) == ScalarField::from_u32(4) && m.get_coeff(3, 2) == ScalarField::from_u32(1) && m.get_coeff(0, 0) == ScalarField::zero());
+  });
+  T("test_mul_polynomial", [&] {  // tests.rs:1042-1088: the product is correct at a random point
+    auto p = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(64 * 16), 64, 16);
+    auto q = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(32 * 32), 32, 32);
+    auto pq = p * q;
+    auto pt = rng.generate_random(2);
+    EXPECT(pq.eval(pt[0], pt[1]) == p.eval(pt[0], pt[1]) * q.eval(pt[0], pt[1]));
+  });
+  T("test_div_by_ruffini", [&] {  // tests.rs:935-953
+    auto p = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(64 * 32), 64, 32);
+    auto a = rng.generate_random(2), pt = rng.generate_random(2);
+    auto r = p.div_by_ruffini(a[0], a[1]);
+    EXPECT(r.remainder == p.eval(a[0], a[1]));
+    EXPECT(p.eval(pt[0], pt[1]) == r.q_x.eval(pt[0], pt[1]) * (pt[0] - a[0]) + r.q_y.eval(pt[0], pt[1]) * (pt[1] - a[1]) + r.remainder);
+  });
+  T("test_div_by_vanishing_opt_basic", [&] {  // tests.rs:1225-1238
+    const size_t c = 16, d = 8;
+    auto qx = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(c * d), c, d);
+    auto qy = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(c * d), c, d);
+    std::vector<ScalarField> tx(2 * c, ScalarField::zero()), ty(2 * d, ScalarField::zero());
+    tx[0] = ty[0] = ScalarField::zero() - ScalarField::one();
+    tx[c] = ty[d] = ScalarField::one();
+    auto t_x = DensePolynomialExt::from_coeffs(ctx, tx, 2 * c, 1), t_y = DensePolynomialExt::from_coeffs(ctx, ty, 1, 2 * d);
+    auto p = qx * t_x + qy * t_y;
+    auto quot = p.div_by_vanishing_opt(c, d);
+    auto pt = rng.generate_random(2);
+    auto lhs = p.eval(pt[0], pt[1]);
+    auto rhs = quot.first.eval(pt[0], pt[1]) * (pt[0].pow(c) - ScalarField::one()) + quot.second.eval(pt[0], pt[1]) * (pt[1].pow(d) - ScalarField::one());
+    EXPECT(lhs == rhs);
+  });
+  T("test_msm_equals_scalar_mul", [&] {  // tests.rs:12-45: MSM over multiples of G equals one scalar multiplication
+    const size_t n = 300;
+    auto ks = rng.generate_random(n), ss = rng.generate_random(n);
+    std::vector<G1Affine> bases(n);
+    ScalarField dot = ScalarField::zero();
+    for (size_t i = 0; i < n; i++) {
+      bases[i] = ctx.g1_mul(generator(), ks[i]);
+      dot = dot + ks[i] * ss[i];
+    }
+    EXPECT(ctx.msm_g1_bases(ss, bases) == ctx.g1_mul(generator(), dot));
+    EXPECT(ctx.msm_g1_bases({}, {}) == G1Affine::zero());
+    bool threw = false;
+    try {
+      ctx.msm_g1_bases(ss, std::vector<G1Affine>(n - 1));
+    } catch (const std::runtime_error &) {
+      threw = true;
+    }
+    EXPECT(threw);
+  });
+  T("test_encode_poly (setup/trusted-setup/src/main.rs:222-246)", [&] {
+    const size_t rs_x = 16, rs_y = 8;
+    auto tau = rng.generate_random(2);
+    std::vector<G1Affine> xy(rs_x * rs_y);
+    ScalarField xh = ScalarField::one();
+    for (size_t h = 0; h < rs_x; h++) {
+      ScalarField yi = ScalarField::one();
+      for (size_t i = 0; i < rs_y; i++) {
+        xy[h * rs_y + i] = ctx.g1_mul(generator(), xh * yi);
+        yi = yi * tau[1];
+      }
+      xh = xh * tau[0];
+    }
+    Sigma1 sigma(ctx, xy, rs_x, rs_y);
+    EXPECT(xy[rs_y] == ctx.g1_mul(generator(), tau[0]) && xy[1] == ctx.g1_mul(generator(), tau[1]));
+    auto co = rng.generate_random(8 * 8);
+    auto poly = DensePolynomialExt::from_coeffs(ctx, co, 8, 8);
+    EXPECT(sigma.encode_poly(poly) == ctx.g1_mul(generator(), poly.eval(tau[0], tau[1])));
+    auto too_big = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(32 * 8), 32, 8);
+    bool threw = false;
+    try {
+      sigma.encode_poly(too_big);
+    } catch (const std::runtime_error &e) {
+      threw = std::string(e.what()).find("Insufficient length") != std::string::npos;
+    }
+    EXPECT(threw);
+  });
+  std::printf("ALL PASSED (%d tests)\n", passed);
+  return 0;
+}
+
+static void print_scalar(const ScalarField &s) { std::printf("%016llx%016llx%016llx%016llx\n", (unsigned long long)s.l[3], (unsigned long long)s.l[2], (unsigned long long)s.l[1], (unsigned long long)s.l[0]); }
+
+int main(int argc, char **argv) {
+  try {
+    if (argc > 1 && std::string(argv[1]) == "--scalar") {
+      ScalarCfg rng(7);
+      auto v = rng.generate_random(8);
+      for (int i = 0; i < 8; i += 2) {
+        print_scalar(v[i]);
+        print_scalar(v[i + 1]);
+        print_scalar(v[i] + v[i + 1]);
+        print_scalar(v[i] - v[i + 1]);
+        print_scalar(v[i] * v[i + 1]);
+        print_scalar(v[i].inv());
+        print_scalar(v[i].pow(65537));
+      }
+      return 0;
+    }
+    return run_gpu_tests();
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "FAILED: %s\n", e.what());
+    return 1;
+  }
+}
