@@ -76,3 +76,13 @@ def test_product_does_not_reference_oracle():
                     if not (f == "ffi.py" and "nothing here imports oracle/" in txt and txt.count("oracle") == 1):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """The -sys crate sources (host/rust/tokamak-b200-sys) are not compiled here (no Rust toolchain), so at least keep
+    them in step with the header: one `pub fn` per exported prototype."""
+    hdr = open(os.path.join(ROOT, "include", "tokamak_b200.h")).read()
+    rs = open(os.path.join(PKG, "host", "rust", "tokamak-b200-sys", "src", "lib.rs")).read()
+    syms = set(re.findall(r"\b(tkm_[a-z0-9_]+)\s*\(", hdr))
+    have = set(re.findall(r"pub fn (tkm_[a-z0-9_]+)", rs))
+    assert not (syms - have), sorted(syms - have)
