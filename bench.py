@@ -464,31 +464,36 @@ def main():
         # the same transform with the exchange fused into the last NTT pass (P2P stores over NVLink, no NCCL on the data path)
         fused = None
         if world & (world - 1) == 0:
-            ex = D.PeerExchange(NTT_X, NTT_Y, torch.device("cuda", local_rank))
-            fres = {}
-            for key in ("forward", "roundtrip"):
-                def one_fused():
-                    ev = D.bintt_sharded_forward_fused(ops, ex, src)
+            try:
+                ex = D.PeerExchange(NTT_X, NTT_Y, torch.device("cuda", local_rank))
+                fres = {}
+                for key in ("forward", "roundtrip"):
+                    def one_fused():
+                        ev = D.bintt_sharded_forward_fused(ops, ex, src)
+                        if key == "roundtrip":
+                            return D.bintt_sharded_inverse_fused(ops, ex, ev)
+                        return ev
+                    for i in range(warm):
+                        out = one_fused()
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for i in range(args.steps):
+                        out = one_fused()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    fres[key] = float(tt.item())
                     if key == "roundtrip":
-                        return D.bintt_sharded_inverse_fused(ops, ex, ev)
-                    return ev
-                for i in range(warm):
-                    out = one_fused()
-                barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for i in range(args.steps):
-                    out = one_fused()
-                e1.record()
-                torch.cuda.synchronize()
-                tt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                fres[key] = float(tt.item())
-                if key == "roundtrip":
-                    assert torch.equal(out.reshape(-1), src.reshape(-1)), "fused sharded biNTT round trip is not the identity"
-            fused = {"forward_ms": fres["forward"], "forward_gelem_s": nn / fres["forward"] / 1e6, "roundtrip_ms": fres["roundtrip"],
-                     "exchange": "fused into the last k_ntt_pass: 128-bit P2P stores into peer-mapped symmetric memory + 2 stream-ordered barriers",
-                     "p2p_bytes_per_rank": (world - 1) * (nn // world // world) * 32}
+                        assert torch.equal(out.reshape(-1), src.reshape(-1)), "fused sharded biNTT round trip is not the identity"
+                fused = {"forward_ms": fres["forward"], "forward_gelem_s": nn / fres["forward"] / 1e6, "roundtrip_ms": fres["roundtrip"],
+                         "exchange": "fused into the last k_ntt_pass: 128-bit P2P stores into peer-mapped symmetric memory + 2 stream-ordered barriers",
+                         "p2p_bytes_per_rank": (world - 1) * (nn // world // world) * 32}
+            except AssertionError:
+                raise  # a wrong result is never reported as "unavailable"
+            except Exception as exc:  # symmetric memory not available on this box: keep the NCCL numbers, say why
+                fused = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         if rank == 0:
             line["bintt_sharded"] = {"shape": [NTT_X, NTT_Y], "ranks": world, "forward_ms": res["forward"], "forward_gelem_s": nn / res["forward"] / 1e6,
                                      "roundtrip_ms": res["roundtrip"], "scaling": "strong", "exchange": "all_to_all_single (NCCL), one per direction",
