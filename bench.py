@@ -26,6 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
 
 LOG_N = 22
 NTT_X, NTT_Y = 16384, 512
+NTT_BUTTERFLIES = NTT_X * NTT_Y * ((14 - 2) / 2 + (9 - 2) / 2 + 0.5)  # 83.9 M products per transform
 METRIC = "BLS12-381 G1 MSM throughput at 2^22 points"
 UNIT = "Mpts/s"
 G1_GEN = (
@@ -311,8 +312,9 @@ def main():
             fq_mul = ctx.microbench(3)
             madd = ctx.microbench(4)
             W = 16 if args.log_n == 22 else None
+            bfly = ctx.microbench(6)
             line["microbench"] = {"imad_wide_u32_per_s": imad_wide, "imad_wide_x_u32_per_s": imad_wide_x, "imad_u32_per_s": ctx.microbench(0),
-                                  "fr_mul_per_s": ctx.microbench(2), "fq_mul_per_s": fq_mul, "xyzz_madd_per_s": madd}
+                                  "fr_mul_per_s": ctx.microbench(2), "fq_mul_per_s": fq_mul, "xyzz_madd_per_s": madd, "fr_butterfly_per_s": bfly}
             if W:
                 # k_accumulate alone, timed live with CUDA events on the launching stream (tkm_kernel_time_last), averaged
                 acc_ms = []
@@ -356,7 +358,13 @@ def main():
                     "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": NCU_TRAFFIC["k_ntt_pass_x3"],
                                  "traffic_unit": "GB per transform (dram read+write summed over the 3 launches, ncu --set full capture in profiles/)",
                                  "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_element": 128,
-                                 "kernel": "k_ntt_pass x3", "kernel_ms": kms}}
+                                 "kernel": "k_ntt_pass x3", "kernel_ms": kms},
+                    # the bound that actually binds: 256-bit modular butterflies on the INT32 pipes
+                    "roofline_int32": {"bound": "int32", "unit": "G butterflies/s", "achieved": NTT_BUTTERFLIES / (kms * 1e-3) / 1e9, "peak": bfly / 1e9,
+                                       "frac": NTT_BUTTERFLIES / (kms * 1e-3) / bfly,
+                                       "note": "product-carrying butterflies of a 16384x512 transform: N*((log2 x - 2)/2 + (log2 y - 2)/2 + 1/2) = 83.9 M "
+                                               "(the radix-4 tail of each axis needs one product per four elements); peak = measured Fr "
+                                               "product+add+sub stream on this GPU"}}
             # e2e biNTT through the host-buffer entry point (pinned buffers)
             h_poly = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)
             h_out = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)

@@ -105,3 +105,78 @@ def test_r1cs_uvw_polys_against_host_products(backends):
                                         vp(csr.coeff), csr.wire.shape[0], vp(bad), vp(wt.var_off), vp(vals), vals.shape[0], params.n, params.s_max,
                                         ctypes.byref(u), ctypes.byref(v), ctypes.byref(w))
     assert rc == T.ffi.TKM_ERR_INVALID_ARGUMENT if hasattr(T.ffi, "TKM_ERR_INVALID_ARGUMENT") else rc != 0
+
+
+def test_random_polynomial_programs_gpu_vs_oracle(backends):
+    """Differential fuzz: random sequences of DensePolynomialExt operations (mismatched shapes, zero polynomials, scalar
+    forms, monomial shifts, coefficient scalings, divisions, evaluations) on the GPU engine and on its CPU twin; the padded
+    coefficient matrices must agree after every step."""
+    import random
+
+    import oracle_ffi as O
+
+    gpu, orc = backends
+    gpu.init_ntt_domain(1 << 16)
+    rng = random.Random(20261018)
+
+    def same(a, b):
+        tx, ty = max(a.shape[0], b.shape[0]), max(a.shape[1], b.shape[1])
+
+        def padded(coeffs, shape):
+            m = np.zeros((tx, ty, 4), dtype=np.uint64)
+            m[:shape[0], :shape[1]] = np.asarray(coeffs, dtype=np.uint64).reshape(shape[0], shape[1], 4)
+            return m
+
+        return np.array_equal(padded(a.copy_coeffs(), a.shape), padded(b.copy_coeffs(), b.shape))
+
+    for prog in range(12):
+        pool = []
+        for k in range(3):
+            x, y = 1 << rng.randrange(0, 6), 1 << rng.randrange(0, 5)
+            co = O.random_fr(9000 + 10 * prog + k, x * y)
+            if rng.random() < 0.2:
+                co[rng.randrange(x * y):] = 0  # low-degree / partly zero
+            if rng.random() < 0.1:
+                co[:] = 0
+            pool.append((gpu.from_coeffs(co, x, y), orc.from_coeffs(co, x, y)))
+        for step in range(10):
+            op = rng.choice(["add", "sub", "mul", "scale", "adds", "mono", "scx", "scy", "eval", "neg", "ruffini"])
+            (ga, oa), (gb, ob) = rng.choice(pool), rng.choice(pool)
+            s = rng.randrange(VF.R_MOD) if rng.random() < 0.8 else rng.choice([0, 1, VF.R_MOD - 1])
+            if op == "add":
+                r = (ga + gb, oa + ob)
+            elif op == "sub":
+                r = (ga - gb, oa - ob)
+            elif op == "mul":
+                if ga.shape[0] * gb.shape[0] > 256 or ga.shape[1] * gb.shape[1] > 256:
+                    continue
+                r = (ga * gb, oa * ob)
+            elif op == "scale":
+                r = (ga * s, oa * s)
+            elif op == "adds":
+                r = (ga + s, oa + s)
+            elif op == "neg":
+                r = (-ga, -oa)
+            elif op == "mono":
+                ex, ey = rng.randrange(0, 3), rng.randrange(0, 3)
+                if (ga.shape[0] + ex) > 128 or (ga.shape[1] + ey) > 64:
+                    continue
+                r = (ga.mul_monomial(ex, ey), oa.mul_monomial(ex, ey))
+            elif op == "scx":
+                r = (ga.scale_coeffs_x(s), oa.scale_coeffs_x(s))
+            elif op == "scy":
+                r = (ga.scale_coeffs_y(s), oa.scale_coeffs_y(s))
+            elif op == "eval":
+                px, py = rng.randrange(VF.R_MOD), rng.randrange(VF.R_MOD)
+                assert ga.eval(px, py) == oa.eval(px, py), (prog, step, op)
+                continue
+            else:  # ruffini
+                if ga.shape[0] < 2 or ga.shape[1] < 2:
+                    continue
+                px, py = rng.randrange(VF.R_MOD), rng.randrange(VF.R_MOD)
+                gq, oq = ga.div_by_ruffini(px, py), oa.div_by_ruffini(px, py)
+                assert gq[2] == oq[2] and same(gq[0], oq[0]) and same(gq[1], oq[1]), (prog, step, op)
+                continue
+            assert same(r[0], r[1]), (prog, step, op, r[0].shape, r[1].shape)
+            if r[0].shape[0] * r[0].shape[1] <= 4096:
+                pool[rng.randrange(len(pool))] = r

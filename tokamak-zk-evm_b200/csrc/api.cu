@@ -125,6 +125,17 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
     uint32_t r = 0;
     for (int i = 0; i < 16; i++) r ^= E[i] ^ O[i];
     if (r == 0x12345678u) sink[0] = r;
+  } else if (KIND == 6) {  // the NTT butterfly: one Fr product, one addition, one subtraction
+    Fr x = Fr::one(), y = Fr::r2(), w = Fr::r2();
+    x.v[0] ^= t;
+    w.v[1] ^= t;
+    for (int it = 0; it < iters; it++) {
+      Fr s = x + y;
+      Fr d = (x - y) * w;
+      x = s;
+      y = d;
+    }
+    if (x.v[0] == 0x12345678u && y.v[1] == 1) sink[0] = x.v[1];
   } else if (KIND == 2) {
     Fr x = Fr::one(), y = Fr::r2();
     x.v[0] ^= t;
@@ -647,6 +658,7 @@ int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
       case 3: iters = 256; ops_per_iter = 2; k_microbench<3><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 4: iters = 64; ops_per_iter = 1; k_microbench<4><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 5: iters = 4096; ops_per_iter = 16; k_microbench<5><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 6: iters = 512; ops_per_iter = 1; k_microbench<6><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown microbench kind %d", kind);
     }
     TKM_TRY(launch_check(ctx, "k_microbench"));
