@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
   // one radix-4 register butterfly with a single multiplication per four elements.
   const bool radix4_tail = (p.pass == 2 && p.logL >= 2);
   const uint32_t r2_stages = radix4_tail ? p.logL - 2 : p.logL;
-  for (uint32_t u = 0; u < r2_stages; u++) {
-    const uint32_t logh = p.logL - 1 - u, h = 1u << logh;
-    const uint32_t toff = L - (L >> u);
+  // Stages are taken two at a time as radix-4 register butterflies (4 elements, 4 products, 3 twiddles): half the
+  // shared-memory round trips and half the barriers of a radix-2 sweep; an odd stage count starts with one radix-2 stage.
+  uint32_t u = 0;
+  if (r2_stages & 1) {
+    const uint32_t logh = p.logL - 1, h = 1u << logh;
     for (uint32_t w = tid; w < (TILE >> 1); w += NTT_THREADS) {
       uint32_t c = w & (C - 1), bidx = w >> p.logC;
       uint32_t j = bidx & (h - 1);
@@ -187,11 +189,34 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
       uint32_t i0 = l0 * C + c, i1 = i0 + h * C;
       Fr a = lds_fr(d_lo, d_hi, i0);
       Fr b = lds_fr(d_lo, d_hi, i1);
-      Fr tw = lds_fr(t_lo, t_hi, toff + j);
-      Fr s = a + b;
-      Fr d = INVERSE ? (b - a) : (a - b);
-      sts_fr(d_lo, d_hi, i0, s);
-      sts_fr(d_lo, d_hi, i1, d * tw);
+      Fr tw = lds_fr(t_lo, t_hi, j);  // stage 0 twiddles start at offset 0
+      Fr sm = a + b;
+      Fr df = INVERSE ? (b - a) : (a - b);
+      sts_fr(d_lo, d_hi, i0, sm);
+      sts_fr(d_lo, d_hi, i1, df * tw);
+    }
+    __syncthreads();
+    u = 1;
+  }
+  for (; u + 1 < r2_stages; u += 2) {
+    const uint32_t logh = p.logL - 1 - u, h = 1u << logh, logh2 = logh - 1, h2 = h >> 1;
+    const uint32_t toff0 = L - (L >> u), toff1 = L - (L >> (u + 1));
+    for (uint32_t w = tid; w < (TILE >> 2); w += NTT_THREADS) {
+      const uint32_t c = w & (C - 1), q = w >> p.logC;
+      const uint32_t j = q & (h2 - 1);
+      const uint32_t l0 = ((q >> logh2) << (logh + 1)) + j;
+      const uint32_t i0 = l0 * C + c, i1 = i0 + h2 * C, i2 = i0 + h * C, i3 = i2 + h2 * C;
+      Fr x0 = lds_fr(d_lo, d_hi, i0), x2 = lds_fr(d_lo, d_hi, i2);
+      Fr a0 = x0 + x2;
+      Fr a2 = (INVERSE ? (x2 - x0) : (x0 - x2)) * lds_fr(t_lo, t_hi, toff0 + j);
+      Fr x1 = lds_fr(d_lo, d_hi, i1), x3 = lds_fr(d_lo, d_hi, i3);
+      Fr a1 = x1 + x3;
+      Fr a3 = (INVERSE ? (x3 - x1) : (x1 - x3)) * lds_fr(t_lo, t_hi, toff0 + j + h2);
+      const Fr tw1 = lds_fr(t_lo, t_hi, toff1 + j);
+      sts_fr(d_lo, d_hi, i0, a0 + a1);
+      sts_fr(d_lo, d_hi, i1, (INVERSE ? (a1 - a0) : (a0 - a1)) * tw1);
+      sts_fr(d_lo, d_hi, i2, a2 + a3);
+      sts_fr(d_lo, d_hi, i3, (INVERSE ? (a3 - a2) : (a2 - a3)) * tw1);
     }
     __syncthreads();
   }
