@@ -143,7 +143,7 @@ def test_ntt_batch_rows_vs_columns(ctx, T):
     ctx.dev_free(o)
 
 
-@pytest.mark.parametrize("x,y,world", [(64, 32, 4), (2048, 64, 2), (4096, 256, 8)])
+@pytest.mark.parametrize("x,y,world", [(64, 32, 4), (2048, 64, 2), (4096, 256, 8), (32, 16, 1), (16, 16, 16)])
 def test_ntt_batch_scatter_single_gpu_emulation(ctx, T, x, y, world):
     """tkm_ntt_batch_scatter (fused multi-GPU re-sharding store) with all 'peers' on this GPU: after every emulated rank has
     run its row pass, peer p's buffer must hold the column shard [x][y/G] of the Y-transformed matrix; the inverse X pass
