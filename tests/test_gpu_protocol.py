@@ -180,3 +180,29 @@ def test_random_polynomial_programs_gpu_vs_oracle(backends):
             assert same(r[0], r[1]), (prog, step, op, r[0].shape, r[1].shape)
             if r[0].shape[0] * r[0].shape[1] <= 4096:
                 pool[rng.randrange(len(pool))] = r
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("TKM_RUN_SLOW"), reason="minutes of CPU time: set TKM_RUN_SLOW=1")
+def test_reference_shape_oracle_proof_matches_golden_hash(backends):
+    """The CPU oracle proves the full-size circuit (CRS tables downloaded from the GPU setup, which the small-shape test
+    checks point by point against the oracle's own setup) and must reproduce the golden proof hash: this is the
+    cross-check that makes tests/golden/prove_reference_shape.json an oracle-verified value, not only a self-consistent one."""
+    import copy
+    import hashlib
+    import json
+    import os
+
+    from oracle_backend import OracleTable
+
+    gpu, orc = backends
+    params, infos, r1cs = S.make_library(S.reference_shape())
+    pl, perm, inst = S.synthesize(params, infos, r1cs, small_value_fraction=0.5)
+    sg = copy.copy(ST.generate(gpu, params, infos, r1cs, ST.Tau.gen_fixed()))
+    for name in ("xy_powers", "gamma_inv_o_inst", "eta_inv_li_o_inter_alpha4_kj", "delta_inv_li_o_prv"):
+        t = getattr(sg, name)
+        setattr(sg, name, OracleTable(t.points_host(), t.rows, t.cols))
+    pv = PV.Prover(orc, params, infos, r1cs, sg, pl, perm, inst, mixer=PV.Mixer.fixed())
+    _, _, fmt, _ = PV.prove(pv)
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prove_reference_shape.json")))
+    assert hashlib.sha256(json.dumps(fmt, sort_keys=True).encode()).hexdigest() == golden["proof_sha256"]
+    print("oracle prove spans:", {k: round(v, 2) for k, v in pv.t.spans.items() if "." not in k})
