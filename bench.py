@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--log-n", type=int, default=LOG_N, help="developer override of the MSM size (the graded config is 22)")
     ap.add_argument("--skip-aux", action="store_true", help="skip the biNTT / cpu-baseline / e2e legs (profiling runs)")
     ap.add_argument("--skip-prove", action="store_true", help="skip the full-prove leg (setup + prove0..4 + verify at the reference shape)")
+    ap.add_argument("--no-cpu-prove-full", dest="cpu_prove_full", action="store_false",
+                    help="skip the CPU oracle's FULL reference-shape prove (about 35 s on 16 cores); the shape / 4 sample always runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -418,7 +420,9 @@ def main():
         for p_ in (d_bases, d_scalars):
             ctx.dev_free(p_)
         gpu_be = GpuBackend(ctx)
-        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync, warmup=3)
+        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync, warmup=3,
+                              keep_sigma=args.cpu_prove_full)
+        full_sigma = full.pop("_sigma", None)
         full["reference"] = {"cpu_prove_s": 45.7, "icicle_cuda_prove_s": 21.08, "stage_split_cpu_s": [5.21, 10.09, 2.13, 13.37, 1.56, 13.33],
                              "stage_split_icicle_cuda_s": [0.72, 4.03, 0.78, 7.27, 0.90, 7.37],
                              "source": "BASELINE.md (reference's own artifacts, unnamed hosts, real template tx, 166 placements)"}
@@ -432,6 +436,17 @@ def main():
             setattr(sg, name, OracleTable(t_.points_host(), t_.rows, t_.cols))
         cpu = prove_full.run(OracleBackend(), prove_full.reduced_shape(), repeats=1, verify=False, sigma=sg)
         assert cpu["proof_sha256"] == small["proof_sha256"], "GPU proof and CPU-oracle proof differ on the reduced shape"
+        if args.cpu_prove_full:
+            sgf = copy.copy(full_sigma)
+            for name in ("xy_powers", "gamma_inv_o_inst", "eta_inv_li_o_inter_alpha4_kj", "delta_inv_li_o_prv"):
+                t_ = getattr(sgf, name)
+                setattr(sgf, name, OracleTable(t_.points_host(), t_.rows, t_.cols))
+            cpu_full = prove_full.run(OracleBackend(), S.reference_shape(), repeats=1, verify=False, sigma=sgf)
+            assert cpu_full["proof_sha256"] == full["proof_sha256"], "GPU proof and CPU-oracle proof differ at the full reference shape"
+            line.setdefault("cpu_baseline", {})["prove_full_shape"] = {
+                "value": cpu_full["prove_s"], "unit": "s", "cores": O.num_threads(), "kind": "port", "gpu_same_input_s": full["prove_s"],
+                "cpu_stage_s": {k: cpu_full["median_run"][k] for k in ("init_s", "prove0_s", "prove1_s", "prove2_s", "prove3_s", "prove4_s", "encode_s")},
+                "sample": "the full reference-shape circuit (no reduction); proof byte-identical to the GPU proof"}
         line.setdefault("cpu_baseline", {})["prove"] = {
             "value": cpu["prove_s"], "unit": "s", "cores": O.num_threads(), "kind": "port",
             "sample": "reference shape with every extent / 4 (n=1024, s_max=64, m_I=1024; 1/16 of the MSM and NTT work): protocol driver on "
