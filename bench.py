@@ -337,6 +337,9 @@ def main():
                                             "N*W mixed additions x 2748 issued wide IMADs (8 products x 288 + 2 squarings x 222) per launch / k_accumulate's event-timed duration; "
                                             "peak = best measured IMAD.WIDE.U32 stream on this GPU (64-bit-addend or carry-chain form)",
                                     "whole_msm_frac": adds * wide_per_add / (ms_res * 1e-3) / peak,
+                                    # the schema's HBM view of the same kernel, for completeness: 104 algorithmic bytes per addition
+                                    "hbm_view": {"bound": "hbm", "achieved": adds * 104 / (acc_ms * 1e-3) / 1e9, "peak": measured_peaks()[0], "unit": "GB/s",
+                                                 "frac": adds * 104 / (acc_ms * 1e-3) / 1e9 / measured_peaks()[0]},
                                     "madd_frac": adds / (acc_ms * 1e-3) / madd}
 
             # ---- bivariate NTT 16384 x 512 (device-resident) with its HBM roofline
