@@ -611,13 +611,30 @@ def test_transpose_fill_x_minus_one(ctx, T):
         ctx.dev_free(p)
 
 
-def test_div_by_vanishing_legacy_name(ctx, T):
-    """div_by_vanishing (legacy entry, tests.rs:1216-1222): unique decomposition => same output as _opt."""
-    x, y, c, d = 64, 32, 16, 8
-    a = O.random_fr(430, x * y)
-    qx, qy = poly_from(T, ctx, a, x, y).div_by_vanishing(c, d)
-    eqx, eqy = O.div_by_vanishing_opt(a, x, y, c, d)
-    assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy)
+def test_div_by_vanishing_legacy_coset_formulation(ctx, T):
+    """div_by_vanishing (the coset-NTT formulation, tests.rs:1216-1222) on a numerator in the ideal: same quotients as
+    div_by_vanishing_opt and as the oracle; the denominator cache is reused on the second call; the reference's panics."""
+    c, d = 16, 8
+    for qx_rows in (c, 2 * c):  # numerator x-size 2c (m = 2) and 4c (m = 4)
+        qx0 = T.DensePolynomialExt.from_coeffs(ctx, O.random_fr(430 + qx_rows, qx_rows * d), qx_rows, d)
+        qy0 = T.DensePolynomialExt.from_coeffs(ctx, O.random_fr(431, c * d), c, d)
+        tx = T.DensePolynomialExt.from_coeffs(ctx, frs([P.R_MOD - 1] + [0] * (c - 1) + [1] + [0] * (c - 1)), 2 * c, 1)
+        ty = T.DensePolynomialExt.from_coeffs(ctx, frs([P.R_MOD - 1] + [0] * (d - 1) + [1] + [0] * (d - 1)), 1, 2 * d)
+        p = qx0 * tx + qy0 * ty
+        cache = T.DivByVanishingCache(seed=5)
+        for _ in range(2):
+            gx, gy = p.clone().div_by_vanishing(c, d, cache)
+            ox, oy = p.clone().div_by_vanishing_opt(c, d)
+            xs, ys = p.shape
+            ex, ey = O.div_by_vanishing_opt(p.copy_coeffs(), xs, ys, c, d)
+            assert np.array_equal(gx.copy_coeffs(), ox.copy_coeffs()) and np.array_equal(gx.copy_coeffs(), ex)
+            assert np.array_equal(gy.copy_coeffs(), oy.copy_coeffs()) and np.array_equal(gy.copy_coeffs(), ey)
+        assert len(cache.denom_x_eval_inv) == 1 and len(cache.denom_y_eval_inv) == 1
+    small = T.DensePolynomialExt.from_coeffs(ctx, O.random_fr(432, 8 * 4), 8, 4)
+    with pytest.raises(ValueError):
+        small.div_by_vanishing(16, 8)  # "The numerator must have grater degrees than denominators."
+    with pytest.raises(ValueError):
+        small.div_by_vanishing(3, 4)   # "The denominators must have degress as powers of two."
 
 
 @pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 4096, 100003, 1 << 20])

@@ -499,11 +499,58 @@ class DensePolynomialExt:
         check(self.ctx.lib.tkm_poly_div_by_vanishing(self.ctx.h, self.h, x_degree, y_degree, ctypes.byref(qx), ctypes.byref(qy)))
         return DensePolynomialExt(self.ctx, qx), DensePolynomialExt(self.ctx, qy)
 
-    def div_by_vanishing(self, x_degree, y_degree, cache=None):
-        """div_by_vanishing (:2096-2282), the legacy coset-NTT formulation.  With deg_X(Q_Y) < c the decomposition
-        P = Q_X (X^c - 1) + Q_Y (Y^d - 1) is unique (X^c - 1 and Y^d - 1 are coprime), so it returns exactly the
-        polynomials of div_by_vanishing_opt; the denominator cache of the reference is not needed."""
-        return self.div_by_vanishing_opt(x_degree, y_degree)
+    def div_by_vanishing(self, denom_x_degree, denom_y_degree, cache=None):
+        """div_by_vanishing (:2096-2282), the legacy formulation, literally: fold the X-blocks of the numerator, divide by
+        Y^d - 1 on a Y-coset of the c x (n d) grid to get Q_Y, subtract Q_Y (Y^d - 1), divide by X^c - 1 on an X-coset to
+        get Q_X.  `cache` (DivByVanishingCache) keeps the coset generators and the inverted denominator tables per shape
+        like the reference's.  For a numerator in the ideal it returns the polynomials of div_by_vanishing_opt (the
+        decomposition with deg_X Q_Y < c is unique); the prover only calls the _opt form."""
+        c, d = int(denom_x_degree), int(denom_y_degree)
+        if c <= 0 or d <= 0 or c & (c - 1) or d & (d - 1):
+            raise ValueError("The denominators must have degress as powers of two.")
+        self.optimize_size()
+        xs, ys = self.shape
+        xd, yd = self.find_degree()
+        if xd < c or yd < d:
+            raise ValueError("The numerator must have grater degrees than denominators.")
+        m, n = xs // c, ys // d
+        cache = cache if cache is not None else DivByVanishingCache()
+        ctx = self.ctx
+        hit_x = cache.find(cache.denom_x_eval_inv, m * c, n * d, c)
+        zeta = hit_x["coset"] if hit_x else cache.fresh_coset()
+        hit_y = cache.find(cache.denom_y_eval_inv, c, n * d, d)
+        xi = hit_y["coset"] if hit_y else zeta
+
+        def build_denom_inv(target_x, target_y, base, coset, along_y):
+            axis = target_y if along_y else target_x
+            root = ctx.get_root_of_unity(axis // base)
+            cp = pow(coset, base, R_MOD)
+            vals, w = [], 1
+            for _ in range(axis):
+                vals.append((cp * w - 1) % R_MOD)
+                w = w * root % R_MOD
+            ax = frs_from_ints(vals)
+            mat = np.tile(ax, (target_x, 1)) if along_y else np.repeat(ax, target_y, axis=0)
+            return ctx.vec_op_host(OP_DIV, frs_from_ints([1] * (target_x * target_y)), mat)
+
+        blocks = self.copy_coeffs().reshape(m, c * ys, 4)
+        acc = np.ascontiguousarray(blocks[0])
+        for i in range(1, m):
+            acc = ctx.vec_op_host(OP_ADD, acc, np.ascontiguousarray(blocks[i]))
+        r_tilde = DensePolynomialExt.from_coeffs(ctx, acc, c, n * d).to_rou_evals(None, xi)
+        if not hit_y:
+            hit_y = {"coset": xi, "x_size": c, "y_size": n * d, "base": d, "evals": build_denom_inv(c, n * d, d, xi, True)}
+            cache.denom_y_eval_inv.append(hit_y)
+        quo_y = DensePolynomialExt.from_rou_evals(ctx, ctx.vec_op_host(OP_MUL, r_tilde, hit_y["evals"]), c, n * d, None, xi)
+        r = quo_y.mul_monomial(0, d) - quo_y
+        b = self - r
+        b.resize(m * c, n * d)
+        b_tilde = b.to_rou_evals(zeta, None)
+        if not hit_x:
+            hit_x = {"coset": zeta, "x_size": m * c, "y_size": n * d, "base": c, "evals": build_denom_inv(m * c, n * d, c, zeta, False)}
+            cache.denom_x_eval_inv.append(hit_x)
+        quo_x = DensePolynomialExt.from_rou_evals(ctx, ctx.vec_op_host(OP_MUL, b_tilde, hit_x["evals"]), m * c, n * d, zeta, None)
+        return quo_x, quo_y
 
     def div_by_ruffini(self, x, y):
         kx, px = fr_bytes(x)
@@ -512,6 +559,25 @@ class DensePolynomialExt:
         r = np.zeros(4, dtype=np.uint64)
         check(self.ctx.lib.tkm_poly_div_by_ruffini(self.ctx.h, self.h, px, py, ctypes.byref(qx), ctypes.byref(qy), _vp(r)))
         return DensePolynomialExt(self.ctx, qx), DensePolynomialExt(self.ctx, qy), fr_to_int(r)
+
+
+class DivByVanishingCache:
+    """DivByVanishingCache / DenomCache (bivariate_polynomial/mod.rs:88-110): inverted denominator evaluations and the coset
+    generator they were built for, keyed by (x_size, y_size, base)."""
+
+    def __init__(self, seed=None):
+        self.denom_x_eval_inv, self.denom_y_eval_inv = [], []
+        self._rng = __import__("random").Random(seed)
+
+    @staticmethod
+    def find(entries, x_size, y_size, base):
+        for e in entries:
+            if (e["x_size"], e["y_size"], e["base"]) == (x_size, y_size, base):
+                return e
+        return None
+
+    def fresh_coset(self):
+        return self._rng.randrange(2, R_MOD)
 
 
 def _domain_size_for_degree(degree):
