@@ -229,6 +229,11 @@ int32_t tkm_poly_div_by_vanishing(tkm_ctx *ctx, tkm_poly *p, size_t c, size_t d,
 /* div_by_ruffini (:2412-2477): P = Qx (X - x) + Qy (Y - y) + r.  Qx shape = p shape, Qy = 1 x y_size. */
 int32_t tkm_poly_div_by_ruffini(tkm_ctx *ctx, const tkm_poly *p, const uint8_t x32[32], const uint8_t y32[32],
                                 tkm_poly **out_qx, tkm_poly **out_qy, uint8_t out_r32[32]);
+/* divide_x / divide_y (:1998-2094): univariate long division of every line along X (y_dir = 0) or Y (y_dir = 1) by an
+ * X- (Y-) univariate denominator; P = Q * D + R with deg R < deg D along that axis.  Q and R have the shape of p (a constant
+ * denominator gives Q = p / c and the 1 x 1 zero remainder).  The reference's panics become TKM_ERR_INVALID_ARGUMENT with the
+ * same texts ("Denominator for divide_x must be X-univariate", "Numer.degree < Denom.degree for divide_x", "Divide by zero"). */
+int32_t tkm_poly_divide_uni(tkm_ctx *ctx, const tkm_poly *p, const tkm_poly *denom, int32_t y_dir, tkm_poly **out_q, tkm_poly **out_r);
 /* encode_poly (iotools/mod.rs:2041-2113; group_structures/mod.rs:59-119): optimize_size, bounds
  * check against the CRS grid, commit the trimmed rectangle.  Zero polynomial -> identity. */
 int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t out96[96]);

@@ -504,6 +504,61 @@ def test_div_by_ruffini(ctx, T, x, y):
     assert r == p.eval(px, py)
 
 
+def _long_division(num, den):
+    """Schoolbook polynomial long division on Python integers (coefficients low to high)."""
+    num, dd = list(num), max(i for i, c in enumerate(den) if c)
+    linv = pow(den[dd], P.R_MOD - 2, P.R_MOD)
+    quo = [0] * len(num)
+    for i in range(len(num) - dd - 1, -1, -1):
+        f = num[i + dd] * linv % P.R_MOD
+        quo[i] = f
+        for k in range(dd + 1):
+            num[i + k] = (num[i + k] - f * den[k]) % P.R_MOD
+    return quo, num
+
+
+@pytest.mark.parametrize("y_dir", [False, True])
+def test_divide_x_and_divide_y(ctx, T, y_dir):
+    """divide_x / divide_y (tests.rs:955-1008): P = Q D + R at a random point, every line equal to integer long division,
+    the constant-denominator path and the reference's panics."""
+    x, y = (32, 256) if y_dir else (256, 32)
+    pc = O.random_fr(440 + y_dir, x * y)
+    p = poly_from(T, ctx, pc, x, y)
+    dlen = 16
+    dc = O.random_fr(442 + y_dir, dlen)
+    dc[dlen - 3:] = 0  # degree 12 inside a 16-slot buffer
+    den = poly_from(T, ctx, dc, 1, dlen) if y_dir else poly_from(T, ctx, dc, dlen, 1)
+    q, r = p.divide_y(den) if y_dir else p.divide_x(den)
+    assert q.shape == (x, y) and r.shape == (x, y)
+    a, b = 0x1234567890ABCDEF % P.R_MOD, 0xFEDCBA0987654321 % P.R_MOD
+    assert p.eval(a, b) == (q.eval(a, b) * den.eval(a, b) + r.eval(a, b)) % P.R_MOD
+    pm, qm, rm = (np.array(to_ints(z), dtype=object).reshape(x, y) for z in (pc, q.copy_coeffs(), r.copy_coeffs()))
+    dints = to_ints(dc)
+    for line in (0, 1, (x if y_dir else y) - 1):
+        num = list(pm[line, :]) if y_dir else list(pm[:, line])
+        eq, er = _long_division(num, dints)
+        assert (list(qm[line, :]) if y_dir else list(qm[:, line])) == eq
+        assert (list(rm[line, :]) if y_dir else list(rm[:, line])) == er
+    rd = r.find_degree()
+    assert (rd[1] if y_dir else rd[0]) < 12
+    # constant denominator: quotient = p / c, remainder = 0 (1 x 1)
+    cden = poly_from(T, ctx, frs([7]), 1, 1)
+    q2, r2 = p.divide_y(cden) if y_dir else p.divide_x(cden)
+    assert np.array_equal(q2.copy_coeffs(), (p * pow(7, P.R_MOD - 2, P.R_MOD)).copy_coeffs()) and r2.shape == (1, 1) and r2.is_zero()
+    wrong = poly_from(T, ctx, O.random_fr(444, 4 * 4), 4, 4)  # bivariate denominator
+    with pytest.raises(T.TkmError, match="univariate"):
+        p.divide_y(wrong) if y_dir else p.divide_x(wrong)
+    with pytest.raises(T.TkmError, match="Numer.degree < Denom.degree"):
+        (den.divide_y(p.get_univariate_polynomial_y(0)) if y_dir else den.divide_x(p.get_univariate_polynomial_x(0)))
+    with pytest.raises(T.TkmError, match="Divide by zero"):
+        p.divide_y(T.DensePolynomialExt.zero(ctx)) if y_dir else p.divide_x(T.DensePolynomialExt.zero(ctx))
+    # get_univariate_polynomial_x / _y (tests.rs:800-836)
+    col = p.get_univariate_polynomial_x(3)
+    row = p.get_univariate_polynomial_y(5)
+    assert col.shape == (x, 1) and row.shape == (1, y)
+    assert to_ints(col.copy_coeffs()) == list(pm[:, 3]) and to_ints(row.copy_coeffs()) == list(pm[5, :])
+
+
 def test_encode_poly_fixed_tau(ctx, T):
     """encode_poly(P) == P(tau_x, tau_y) * G (setup/trusted-setup/src/main.rs:222-246) on a 64 x 32 grid built
     on the device with the fixed-tau generator; trimmed-rectangle, zero-polynomial and too-small-CRS paths."""

@@ -298,6 +298,28 @@ __global__ void __launch_bounds__(128) k_r1cs_uvw(R1csView v, size_t n, size_t s
   w[t] = acc[2];
 }
 
+
+// ---------------------------------------------------------------- univariate long division along one axis (divide_x / divide_y)
+// One thread per line of the sweep direction: schoolbook division of the line (length len, stride es) by the univariate
+// denominator den[0..dd] (lead_inv = 1 / den[dd]).  rem holds a copy of the numerator on entry and the remainder on exit.
+// (_divide_uni, libs/src/bivariate_polynomial/mod.rs:2052-2094: the reference slices every line into a DensePolynomial
+// and calls ICICLE's divide on it; tests only, so clarity over speed.)
+__global__ void __launch_bounds__(128) k_divide_uni(Fr *__restrict__ rem, Fr *__restrict__ quo, const Fr *__restrict__ den, size_t den_stride,
+                                                    uint32_t dd, Fr lead_inv, size_t len, size_t lines, size_t es, size_t ls) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= lines) return;
+  Fr *r = rem + t * ls;
+  Fr *q = quo + t * ls;
+  for (size_t i = len - dd; i-- > 0;) {
+    const Fr c = r[(i + dd) * es];
+    if (c.is_zero()) continue;
+    const Fr f = c * lead_inv;
+    q[i * es] = f;
+    for (uint32_t k = 0; k < dd; k++) r[(i + k) * es] = r[(i + k) * es] - f * den[k * den_stride];
+    r[(i + dd) * es] = Fr::zero();
+  }
+}
+
 // ---------------------------------------------------------------- host orchestration
 static int32_t poly_alloc(tkm_ctx *ctx, size_t x, size_t y, tkm_poly **out) {
   if (!is_pow2(x) || !is_pow2(y)) return fail(TKM_ERR_INVALID_ARGUMENT, "The input sizes must be powers of two (got %zu x %zu).", x, y);
@@ -846,6 +868,54 @@ static int32_t commit_input(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, MsmIn
     in->pre_c = crs->pre_c;
     in->pre_stride = (uint32_t)(crs->rows * crs->cols);
   }
+  return TKM_OK;
+}
+
+int32_t tkm_poly_divide_uni(tkm_ctx *ctx, const tkm_poly *p, const tkm_poly *denom, int32_t y_dir, tkm_poly **out_q, tkm_poly **out_r) {
+  API_BEGIN
+  TKM_REQUIRE(p && denom && out_q && out_r, "null argument");
+  int64_t nx, ny, dx, dy;
+  TKM_TRY(poly_find_degree(ctx, p, &nx, &ny));
+  TKM_TRY(poly_find_degree(ctx, denom, &dx, &dy));
+  const char *axis = y_dir ? "divide_y" : "divide_x";
+  if (dx < 0) return fail(TKM_ERR_INVALID_ARGUMENT, "Divide by zero");
+  if (y_dir ? dx != 0 : dy != 0) return fail(TKM_ERR_INVALID_ARGUMENT, "Denominator for %s must be %s-univariate", axis, y_dir ? "Y" : "X");
+  const int64_t nd = y_dir ? ny : nx, dd = y_dir ? dy : dx;
+  if (nd < dd) return fail(TKM_ERR_INVALID_ARGUMENT, "Numer.degree < Denom.degree for %s", axis);
+  // leading coefficient of the denominator and its inverse (host side, one element)
+  const size_t den_stride = y_dir ? 1 : denom->y_size;
+  Fr lead;
+  TKM_CUDA(cudaMemcpyAsync(&lead, denom->d + (size_t)dd * den_stride, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const Fr lead_inv = lead.inv();
+  tkm_poly *q = nullptr, *r = nullptr;
+  if (dd == 0) {  // constant denominator: quotient = p / c, remainder = the zero constant (:2010-2020)
+    TKM_TRY(poly_alloc(ctx, p->x_size, p->y_size, &q));
+    int32_t st = vec_scale(ctx, lead_inv, p->d, q->d, p->x_size * p->y_size);
+    if (st == TKM_OK) st = tkm_poly_zero(ctx, 1, 1, &r);
+    if (st != TKM_OK) {
+      poly_release(ctx, q);
+      return st;
+    }
+    *out_q = q;
+    *out_r = r;
+    return TKM_OK;
+  }
+  int32_t st = tkm_poly_zero(ctx, p->x_size, p->y_size, &q);
+  if (st == TKM_OK) st = tkm_poly_clone(ctx, p, &r);
+  if (st == TKM_OK) {
+    const size_t len = y_dir ? p->y_size : p->x_size, lines = y_dir ? p->x_size : p->y_size;
+    const size_t es = y_dir ? 1 : p->y_size, ls = y_dir ? p->y_size : 1;
+    k_divide_uni<<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(r->d, q->d, denom->d, den_stride, (uint32_t)dd, lead_inv, len, lines, es, ls);
+    st = launch_check(ctx, "k_divide_uni");
+  }
+  if (st != TKM_OK) {
+    poly_release(ctx, q);
+    poly_release(ctx, r);
+    return st;
+  }
+  *out_q = q;
+  *out_r = r;
   return TKM_OK;
 }
 

@@ -96,6 +96,8 @@ extern "C" {
     pub fn tkm_poly_div_by_ruffini(ctx: *mut tkm_ctx, p: *const tkm_poly, x32: *const u8, y32: *const u8, out_qx: *mut *mut tkm_poly,
                                    out_qy: *mut *mut tkm_poly, out_r32: *mut u8) -> i32;
     pub fn tkm_poly_commit(ctx: *mut tkm_ctx, p: *mut tkm_poly, crs: *const tkm_crs, out96: *mut u8) -> i32;
+    pub fn tkm_poly_divide_uni(ctx: *mut tkm_ctx, p: *const tkm_poly, denom: *const tkm_poly, y_dir: i32, out_q: *mut *mut tkm_poly,
+                               out_r: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_commit_begin(ctx: *mut tkm_ctx, p: *mut tkm_poly, crs: *const tkm_crs, out_ticket: *mut i32) -> i32;
     pub fn tkm_commit_end(ctx: *mut tkm_ctx, ticket: i32, out96: *mut u8) -> i32;
     pub fn tkm_r1cs_uvw_polys(ctx: *mut tkm_ctx, s_d: u32, n_rows: *const u32, rp_base: *const u64, row_ptr: *const u32, row_ptr_len: usize,

@@ -552,6 +552,32 @@ class DensePolynomialExt:
         quo_x = DensePolynomialExt.from_rou_evals(ctx, ctx.vec_op_host(OP_MUL, b_tilde, hit_x["evals"]), m * c, n * d, zeta, None)
         return quo_x, quo_y
 
+    def _divide_uni(self, denominator, y_dir):
+        q, r = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.ctx.lib.tkm_poly_divide_uni(self.ctx.h, self.h, denominator.h, 1 if y_dir else 0, ctypes.byref(q), ctypes.byref(r)))
+        return DensePolynomialExt(self.ctx, q), DensePolynomialExt(self.ctx, r)
+
+    def divide_x(self, denominator):
+        """divide_x (:1998-2023): long division of every Y-column along X by an X-univariate denominator -> (quotient, remainder)."""
+        return self._divide_uni(denominator, False)
+
+    def divide_y(self, denominator):
+        """divide_y (:2025-2050)."""
+        return self._divide_uni(denominator, True)
+
+    def get_univariate_polynomial_x(self, idx_y):
+        """The X-univariate polynomial of the idx_y-th power of Y (:1760-1770), shape x_size x 1."""
+        x, y = self.shape
+        return DensePolynomialExt.from_coeffs(self.ctx, np.ascontiguousarray(self.copy_coeffs().reshape(x, y, 4)[:, idx_y]), x, 1)
+
+    def get_univariate_polynomial_y(self, idx_x):
+        """The Y-univariate polynomial of the idx_x-th power of X (:1772-1782), shape 1 x y_size."""
+        x, y = self.shape
+        return DensePolynomialExt.from_coeffs(self.ctx, np.ascontiguousarray(self.copy_coeffs().reshape(x, y, 4)[idx_x]), 1, y)
+
+    def degree(self):
+        return self.find_degree()
+
     def div_by_ruffini(self, x, y):
         kx, px = fr_bytes(x)
         ky, py = fr_bytes(y)

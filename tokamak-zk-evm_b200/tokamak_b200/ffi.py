@@ -84,6 +84,7 @@ SIGNATURES = {
     "tkm_poly_eval_y": [c_void_p, c_void_p, c_void_p, P(c_void_p)],
     "tkm_poly_div_by_vanishing": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p), P(c_void_p)],
     "tkm_poly_div_by_ruffini": [c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p), P(c_void_p), c_void_p],
+    "tkm_poly_divide_uni": [c_void_p, c_void_p, c_void_p, c_int32, P(c_void_p), P(c_void_p)],
     "tkm_poly_commit": [c_void_p, c_void_p, c_void_p, c_void_p],
     "tkm_poly_commit_begin": [c_void_p, c_void_p, c_void_p, P(c_int32)],
     "tkm_commit_end": [c_void_p, c_int32, c_void_p],
