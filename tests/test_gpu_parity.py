@@ -798,3 +798,13 @@ def test_commit_with_fixed_base_tables(ctx, T, c):
     exp = O.msm_g1_rect(frs(sparse), 32, grid, rs_y, 64, 32)
     assert np.array_equal(sigma.encode_poly(poly_from(T, ctx, frs(sparse), 64, 32)), exp)
     assert g1_tuple(sigma.encode_poly(T.DensePolynomialExt.zero(ctx, 8, 8))) is None
+
+
+def test_reflected_scalar_operators(ctx, T):
+    """&s + &p and &s - &p (bivariate_polynomial/mod.rs:1100-1281): the scalar only touches c00."""
+    a = O.random_fr(450, 8 * 4)
+    p = poly_from(T, ctx, a, 8, 4)
+    s = 0x123456789
+    ai = to_ints(a)
+    assert to_ints((s + p).copy_coeffs()) == [(ai[0] + s) % P.R_MOD] + ai[1:]
+    assert to_ints((s - p).copy_coeffs()) == [(s - ai[0]) % P.R_MOD] + [(-v) % P.R_MOD for v in ai[1:]]

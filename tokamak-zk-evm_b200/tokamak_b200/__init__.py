@@ -453,6 +453,12 @@ class DensePolynomialExt:
     def __neg__(self):
         return self._axpby(R_MOD - 1, None, None)
 
+    def __radd__(self, other):  # &s + &p (:1100-1140)
+        return self + other
+
+    def __rsub__(self, other):  # &s - &p: negate, then add the scalar to c00
+        return (-self) + int(other)
+
     def __mul__(self, other):
         if isinstance(other, DensePolynomialExt):
             h = ctypes.c_void_p()

@@ -7,7 +7,6 @@ import time
 from dataclasses import dataclass
 from typing import List
 
-import numpy as np
 
 from .. import frs_from_ints
 from ..transcript import TranscriptManager
@@ -202,22 +201,9 @@ class Prover:
     def _binding(self, placements, infos, wt):
         be, p, sg, mx = self.be, self.p, self.sigma, self.mixer
         A_free = self.encode(self.a_free_X, "A_free")
-        # O_pub_free: public sides of bufferPubOut (outputs), bufferPubIn / bufferBlockIn (inputs); bufferEVMIn is O_pub_fix
-        idx, sc = [], []
-        for pl in placements:
-            info = infos[pl.subcircuitId]
-            if info.name == "bufferPubOut":
-                s0, cnt = info.Out_idx
-            elif info.name in ("bufferPubIn", "bufferBlockIn"):
-                s0, cnt = info.In_idx
-            else:
-                continue
-            for j in range(s0, s0 + cnt):
-                idx.append(info.flattenMap[j])
-                sc.append(pl.variables[j])
-        O_pub_free = be.msm_indexed(sg.gamma_inv_o_inst, np.array(idx, dtype=np.uint32), frs_from_ints(sc))
-        O_mid_core = self._encode_statement(wt, p.l, p.l_D, sg.eta_inv_li_o_inter_alpha4_kj)
-        O_prv_core = self._encode_statement(wt, p.l_D, p.m_D, sg.delta_inv_li_o_prv)
+        O_pub_free = sg.encode_O_pub_free(be, placements, infos, p)
+        O_mid_core = sg.encode_O_mid_no_zk(be, wt, p)
+        O_prv_core = sg.encode_O_prv_no_zk(be, wt, p)
         # zero-knowledge terms (prove/src/lib.rs:1131-1160): the 17 scalar multiples as two small MSMs
         O_mid = be.g1_add(O_mid_core, be.msm_points([sg.delta], [mx.rO_mid]))
         terms = [(sg.eta, (-mx.rO_mid) % R_MOD), (sg.delta_inv_alphak_xh_tx[0][0], mx.rU_X), (sg.delta_inv_alphak_xh_tx[1][0], mx.rV_X)]
@@ -228,12 +214,6 @@ class Prover:
         terms += [(sg.delta_inv_alphak_yi_ty[3][i], mx.rB_Y[i]) for i in range(2)]
         O_prv = be.g1_add(O_prv_core, be.msm_points([t[0] for t in terms], [t[1] for t in terms]))
         return self._resolve({"A_free": A_free, "O_pub_free": O_pub_free, "O_mid": O_mid, "O_prv": O_prv})
-
-    def _encode_statement(self, wt, lo, hi, table):
-        """encode_statement_common (group_structures/mod.rs:266-300): every wire of every placement whose global index
-        lies in [lo, hi), against table[global - lo][placement]."""
-        idx, vals = wt.gather(lo, hi, self.p.s_max)
-        return self.be.msm_indexed(table, idx, vals)
 
     # ---- prove0 (prove/src/lib.rs:1446-1782)
     def prove0(self):

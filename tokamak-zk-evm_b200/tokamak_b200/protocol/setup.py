@@ -75,6 +75,56 @@ class Sigma:
         self.delta_inv_alpha4_xj_tx = None          # [2] points
         self.delta_inv_alphak_yi_ty = None          # [4][3] points, k in 1..4, i in 0..2
 
+    # ---- Sigma1's encoders, with the reference's names (group_structures/mod.rs:59-119,145-300,584-700)
+    def encode_poly(self, backend, poly):
+        """[P(x, y)]_1 over xy_powers (impl_encode_poly!)."""
+        return backend.commit(self.xy_powers, poly)
+
+    def encode_O_pub_free(self, backend, placements, infos, params):
+        """encode_o_pub_free_common: the public sides of bufferPubOut (outputs), bufferPubIn and bufferBlockIn (inputs)
+        against gamma_inv_o_inst; bufferEVMIn belongs to O_pub_fix."""
+        import numpy as np
+
+        from .. import frs_from_ints
+
+        idx, sc = [], []
+        for pl in placements:
+            info = infos[pl.subcircuitId]
+            if info.name == "bufferPubOut":
+                s0, cnt = info.Out_idx
+            elif info.name in ("bufferPubIn", "bufferBlockIn"):
+                s0, cnt = info.In_idx
+            else:
+                continue
+            for j in range(s0, s0 + cnt):
+                idx.append(info.flattenMap[j])
+                sc.append(pl.variables[j])
+        return backend.msm_indexed(self.gamma_inv_o_inst, np.array(idx, dtype=np.uint32), frs_from_ints(sc))
+
+    def encode_O_pub_fix(self, backend, a_pub_function, params):
+        """encode_o_pub_fix_common: the function instance against the last m_function entries of gamma_inv_o_inst."""
+        import numpy as np
+
+        from .. import frs_from_ints
+
+        m_function = params.l - params.l_free
+        if m_function == 0:
+            return None
+        if len(a_pub_function) != m_function:
+            raise ValueError(f"a_pub_function length mismatch: expected m_function={m_function}, got a_pub_function.len()={len(a_pub_function)}")
+        start = params.l - m_function
+        return backend.msm_indexed(self.gamma_inv_o_inst, np.arange(start, start + m_function, dtype=np.uint32), frs_from_ints(a_pub_function))
+
+    def encode_O_mid_no_zk(self, backend, witness_table, params):
+        """encode_statement_common over the interface wires [l, l_D) against eta_inv_li_o_inter_alpha4_kj[wire][placement]."""
+        idx, vals = witness_table.gather(params.l, params.l_D, params.s_max)
+        return backend.msm_indexed(self.eta_inv_li_o_inter_alpha4_kj, idx, vals)
+
+    def encode_O_prv_no_zk(self, backend, witness_table, params):
+        """encode_statement_common over the private wires [l_D, m_D) against delta_inv_li_o_prv[wire][placement]."""
+        idx, vals = witness_table.gather(params.l_D, params.m_D, params.s_max)
+        return backend.msm_indexed(self.delta_inv_li_o_prv, idx, vals)
+
 
 def generate(backend, params, infos, r1cs_list, tau: Tau, g1_gen=G1_FIXED, g2_gen=G2_FIXED):
     p = params
