@@ -312,6 +312,39 @@ def test_msm_large_known_discrete_logs(ctx, logn):
         ctx.dev_free(p)
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "mostly_zero", "small_values", "extremes", "one_hot_window"])
+def test_msm_skewed_scalar_distributions_large(ctx, kind):
+    """2^17 points with the scalar shapes witness polynomials have (hot buckets spanning thousands of accumulation chunks,
+    mostly-zero digits, values near r): answer from known discrete logs, (sum s_i k_i) G."""
+    n = 1 << 17
+    G = g1s([P.G1_GEN])[0]
+    ks = O.random_fr(500, n)
+    rng = np.random.default_rng(501)
+    if kind == "all_equal":
+        vals = [0x1D2C3B4A5968778695A4B3C2D1E0F0E1D2C3B4A5968778695A4B3C2D1E0F % P.R_MOD] * n
+    elif kind == "mostly_zero":
+        vals = [0] * n
+        for i in rng.choice(n, size=n // 50, replace=False):
+            vals[int(i)] = int(rng.integers(1, 1 << 62))
+    elif kind == "small_values":
+        vals = [int(v) for v in rng.integers(0, 1 << 16, size=n)]
+    elif kind == "extremes":
+        pool = [0, 1, 2, P.R_MOD - 1, P.R_MOD - 2, (1 << 255) % P.R_MOD, (1 << 128) - 1, 1 << 128]
+        vals = [pool[int(i)] for i in rng.integers(0, len(pool), size=n)]
+    else:  # every scalar has a single non-zero 16-bit window, the same one
+        vals = [int(v) << 96 for v in rng.integers(1, 1 << 16, size=n)]
+    ss = frs(vals)
+    dk = ctx.upload_fr(ks, to_mont=False)
+    dpts = ctx.dev_alloc(n * 96)
+    ctx.lib.tkm_g1_fixed_base_mul(ctx.h, G.ctypes.data, dk, 0, n, dpts)
+    ctx.lib.tkm_g1_bases_to_mont(ctx.h, dpts, dpts, n)
+    ds = ctx.upload_fr(ss, to_mont=False)
+    got = ctx.msm_g1_dev(ds, False, dpts, n)
+    assert np.array_equal(got, O.g1_mul(G, O.fr_inner_product(ss, ks))), kind
+    for p_ in (dk, dpts, ds):
+        ctx.dev_free(p_)
+
+
 def test_msm_rect_and_indexed(ctx):
     """Strided rectangle of a CRS grid (encode_poly, iotools/mod.rs:2061-2088) and sparse gather
     (msm_g1_bases over gathered rows, group_structures/mod.rs:266-300)."""
