@@ -34,6 +34,31 @@ def _pad(a, x, y, tx, ty):
     return out.reshape(tx * ty, 4)
 
 
+def uvw_evals(params, placements, r1cs_list):
+    """Evaluation tables of u, v, w on the n x s_max grid, row-major [row][placement] (read_R1CS_gen_uvwXY +
+    eval_uvwxy_sparse_rows, iotools/mod.rs:1287-1420; the transpose at :1363-1365 is folded into the indexing).
+    Returns three (n*s_max, 4) uint64 arrays of canonical little-endian limbs."""
+    n, s_max = params.n, params.s_max
+    if len(placements) > s_max:
+        raise ValueError("placement_variables length exceeds s_max.")
+    out = [np.zeros((n * s_max, 4), dtype=np.uint64) for _ in range(3)]
+    mask = (1 << 64) - 1
+    for col, pl in enumerate(placements):
+        var = pl.variables
+        for row, abc in enumerate(r1cs_list[pl.subcircuitId].constraints):
+            for m in range(3):
+                lc = abc[m]
+                if not lc:
+                    continue
+                acc = 0
+                for wire, coeff in lc:
+                    acc += coeff * var[wire]
+                acc %= R_MOD
+                if acc:
+                    out[m][row * s_max + col] = (acc & mask, (acc >> 64) & mask, (acc >> 128) & mask, acc >> 192)
+    return out
+
+
 class OraclePoly:
     def __init__(self, data, x, y):
         self.a = np.ascontiguousarray(data, dtype=np.uint64).reshape(x * y, 4)
@@ -130,9 +155,7 @@ class OracleBackend:
 
     def uvw_polys(self, params, csr, wt):
         """read_R1CS_gen_uvwXY literally: per-placement sparse-row dot products on Python integers, then three INTTs."""
-        from tokamak_b200.protocol import qap
-
-        u, v, w = qap.uvw_evals(params, wt.placements, csr.r1cs_list)
+        u, v, w = uvw_evals(params, wt.placements, csr.r1cs_list)
         return tuple(self.from_rou_evals(e, params.n, params.s_max) for e in (u, v, w))
 
     def from_coeffs(self, coeffs, x, y):

@@ -91,7 +91,9 @@ def test_r1cs_uvw_polys_against_host_products(backends):
     gpu.init_ntt_domain(params.n * params.s_max)
     csr, wt = qap.LibraryCSR(r1cs), qap.WitnessTable(params, pl, infos)
     got = gpu.uvw_polys(params, csr, wt)
-    exp = qap.uvw_evals(params, pl, r1cs)
+    from oracle_backend import uvw_evals
+
+    exp = uvw_evals(params, pl, r1cs)
     for g, e in zip(got, exp):
         assert g.shape == (params.n, params.s_max)
         assert np.array_equal(g.to_rou_evals(), e)

@@ -1,5 +1,7 @@
-"""Sparse R1CS products: the QAP mixture o_j(tau) for setup and the u/v/w evaluation tables of a
-placement list for the prover.  Host side like the reference's (rayon loops over sparse rows, iotools/mod.rs:1380-1608)."""
+"""Sparse R1CS products: the QAP mixture o_j(tau) for setup (host side like the reference's,
+field_structures/mod.rs:73-151) and the data layouts the device kernels take for the prover's witness polynomials
+(LibraryCSR + WitnessTable -> tkm_r1cs_uvw_polys; the literal per-placement host loop of iotools/mod.rs:1380-1608 lives with
+the test oracle)."""
 import numpy as np
 
 from .fr import R_MOD, lagrange_bases_at
@@ -85,52 +87,12 @@ class WitnessTable:
         return idx.astype(np.uint32), np.ascontiguousarray(self.values[rows])
 
 
-def uvw_evals(params, placements, r1cs_list):
-    """Evaluation tables of u, v, w on the n x s_max grid, row-major [row][placement] (read_R1CS_gen_uvwXY +
-    eval_uvwxy_sparse_rows, iotools/mod.rs:1287-1420; the transpose at :1363-1365 is folded into the indexing).
-    Returns three (n*s_max, 4) uint64 arrays of canonical little-endian limbs."""
-    n, s_max = params.n, params.s_max
-    if len(placements) > s_max:
-        raise ValueError("placement_variables length exceeds s_max.")
-    out = [np.zeros((n * s_max, 4), dtype=np.uint64) for _ in range(3)]
-    mask = (1 << 64) - 1
-    for col, pl in enumerate(placements):
-        var = pl.variables
-        for row, abc in enumerate(r1cs_list[pl.subcircuitId].constraints):
-            for m in range(3):
-                lc = abc[m]
-                if not lc:
-                    continue
-                acc = 0
-                for wire, coeff in lc:
-                    acc += coeff * var[wire]
-                acc %= R_MOD
-                if acc:
-                    out[m][row * s_max + col] = (acc & mask, (acc >> 64) & mask, (acc >> 128) & mask, acc >> 192)
-    return out
-
-
 def interface_evals_from_table(params, wt: WitnessTable):
     """gen_bXY over a WitnessTable (vectorised)."""
     s_max = params.s_max
     out = np.zeros(((params.l_D - params.l) * s_max, 4), dtype=np.uint64)
     idx, vals = wt.gather(params.l, params.l_D, s_max)
     out[idx] = vals
-    return out
-
-
-def interface_evals(params, placements, infos):
-    """Evaluation table of b(X,Y) on the m_I x s_max grid (gen_bXY, libs/src/polynomial_structures/mod.rs:132-162)."""
-    l, l_d, s_max = params.l, params.l_D, params.s_max
-    out = np.zeros(((l_d - l) * s_max, 4), dtype=np.uint64)
-    mask = (1 << 64) - 1
-    for col, pl in enumerate(placements):
-        fmap = infos[pl.subcircuitId].flattenMap
-        if len(fmap) != len(pl.variables):
-            raise ValueError("Corrupted placement variables.")
-        for g, v in zip(fmap, pl.variables):
-            if l <= g < l_d and v:
-                out[(g - l) * s_max + col] = (v & mask, (v >> 64) & mask, (v >> 128) & mask, v >> 192)
     return out
 
 
