@@ -244,6 +244,17 @@ int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t o
 int32_t tkm_poly_commit_begin(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, int32_t *out_ticket);
 int32_t tkm_commit_end(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]);
 
+/* ---- host-side data loader (no device work) -------------------------------------------------------
+ * Every "0x..." string of a JSON text, in file order, as 32-byte canonical little-endian scalars reduced mod r:
+ * the HexString -> ScalarField::from_hex parsing of placementVariables.json / instance.json
+ * (libs/src/iotools/mod.rs:126-146,367-372,1582-1588).  out_count receives the number of scalars written. */
+int32_t tkm_host_parse_hex_scalars(const char *text, size_t len, uint8_t *out32, size_t capacity, size_t *out_count);
+/* iden3 .r1cs binary -> CSR (R1csBinary::read / scan_constraints, libs/src/iotools/mod.rs:505-650).  Call once with
+ * row_ptr = NULL to get n_wires, n_constraints and nnz[3] (entries of A, B, C); call again with row_ptr[3 * (n_constraints + 1)],
+ * wire[nnz total] and coeff32[32 * nnz total] to fill them (matrix-major entry order; nnz[] as returned by the first call). */
+int32_t tkm_host_parse_r1cs(const uint8_t *data, size_t len, uint32_t *n_wires, uint32_t *n_constraints, size_t nnz[3], uint32_t *row_ptr,
+                            uint32_t *wire, uint8_t *coeff32);
+
 /* ---- instrumentation used by bench.py (not part of the reference API) ---------------------- */
 /* Times one device-resident launch sequence with CUDA events on the context stream; ms out. */
 int32_t tkm_event_time_begin(tkm_ctx *ctx);

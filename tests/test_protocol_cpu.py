@@ -170,3 +170,46 @@ def test_fewer_placements_than_columns_and_random_blinding(tiny, n_placements, s
     assert VF.verify_snark(t["params"], t["sigma"], pre, inst, points, scalars)
     with pytest.raises(ValueError):
         PV.Prover(t["be"], t["params"], t["infos"], t["r1cs"], t["sigma"], pl * 2, perm, inst)  # more placements than s_max
+
+
+def test_native_loaders_match_the_python_readers(tmp_path):
+    """tkm_host_parse_r1cs / tkm_host_parse_hex_scalars (host-side data loaders of the library, no device needed) against the
+    pure-Python readers: identical CSR arrays and witness values; malformed inputs are rejected with a status, not a crash."""
+    import ctypes
+
+    import numpy as np
+
+    from tokamak_b200 import ffi
+    from tokamak_b200.protocol import qap
+
+    params, infos, r1cs = S.make_library(S.tiny_shape(), seed=11)
+    pl, perm, inst = S.synthesize(params, infos, r1cs, seed=12, small_value_fraction=0.4)
+    F.write_library(str(tmp_path / "lib"), params, infos, r1cs)
+    F.write_synthesizer_output(str(tmp_path / "syn"), pl, perm, inst)
+    p2, i2 = F.read_library_meta(str(tmp_path / "lib"))
+    assert (p2, i2) == (params, infos)
+    a, b = qap.library_csr_from_files(str(tmp_path / "lib"), p2, i2), qap.LibraryCSR(r1cs)
+    for k in ("n_rows", "rp_base", "row_ptr", "wire", "coeff"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    npl, nperm, ninst = F.read_synthesizer_output(str(tmp_path / "syn"), infos)
+    assert nperm == perm and ninst == inst and len(npl) == len(pl)
+    for x, y in zip(npl, pl):
+        assert x.subcircuitId == y.subcircuitId and list(x.variables) == y.variables and x.variables[2] == y.variables[2]
+    wt_a, wt_b = qap.WitnessTable(params, npl, infos), qap.WitnessTable(params, pl, infos)
+    assert np.array_equal(wt_a.values, wt_b.values) and np.array_equal(wt_a.var_off, wt_b.var_off)
+    lib = ffi.load()
+
+    def parse(txt, cap=8):
+        out = np.zeros((cap, 4), dtype=np.uint64)
+        c = ctypes.c_size_t()
+        rc = lib.tkm_host_parse_hex_scalars(txt, len(txt), out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(c))
+        return rc, [int.from_bytes(out[i].tobytes(), "little") for i in range(c.value)]
+
+    assert parse(b'{"k": ["0x0", "0x01", "0xFf", "0x%x", "0x%x"]}' % (fr.R_MOD - 1, fr.R_MOD + 5)) == (0, [0, 1, 255, fr.R_MOD - 1, 5])
+    assert parse(b'["0xg1"]')[0] != 0 and parse(b'["0x1')[0] != 0 and parse(b'["0x' + b"f" * 65 + b'"]')[0] != 0 and parse(b'["0x1","0x2"]', cap=1)[0] != 0
+    blob = open(tmp_path / "lib" / "r1cs" / "subcircuit5.r1cs", "rb").read()
+    nw, nc, nnz = ctypes.c_uint32(), ctypes.c_uint32(), (ctypes.c_size_t * 3)()
+    assert lib.tkm_host_parse_r1cs(blob, len(blob), ctypes.byref(nw), ctypes.byref(nc), nnz, None, None, None) == 0
+    assert (nw.value, nc.value) == (infos[5].Nwires, infos[5].Nconsts)
+    for bad in (b"xxxx" + blob[4:], blob[:-7], blob[:40]):
+        assert lib.tkm_host_parse_r1cs(bad, len(bad), ctypes.byref(nw), ctypes.byref(nc), nnz, None, None, None) != 0

@@ -613,6 +613,169 @@ int32_t tkm_crs_device_ptr(tkm_crs *crs, void **out_dev, size_t *rows, size_t *c
   return TKM_OK;
 }
 
+// Host-side data loader: every "0x..." string of a JSON text (placementVariables.json is 40 MB of them) as 32-byte
+// canonical little-endian scalars, in file order.  Pure host code, no context: the counterpart of the reference's
+// HexString -> ScalarField::from_hex parsing (libs/src/iotools/mod.rs:126-146,1582-1588), which dominates its witness load.
+int32_t tkm_host_parse_hex_scalars(const char *text, size_t len, uint8_t *out32, size_t capacity, size_t *out_count) {
+  if (!text || !out_count || (capacity && !out32)) return fail(TKM_ERR_INVALID_ARGUMENT, "null argument");
+  static const uint64_t R[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+  static const int8_t HEX[256] = {
+      -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+      -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  -1, -1, -1, -1, -1, -1,
+      -1, 10, 11, 12, 13, 14, 15, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+      -1, 10, 11, 12, 13, 14, 15, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+      -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+      -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+      -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+      -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  size_t count = 0;
+  const char *end = text + len;
+  for (const char *q = (const char *)memchr(text, '"', len); q && q + 3 < end; q = (const char *)memchr(q, '"', (size_t)(end - q))) {
+    if (q[1] != '0' || (q[2] != 'x' && q[2] != 'X')) {
+      q++;  // some other string (a key): skip to its closing quote on the next iterations
+      continue;
+    }
+    const char *first = q + 3;
+    const char *close = (const char *)memchr(first, '"', (size_t)(end - first));
+    if (!close) return fail(TKM_ERR_INVALID_ARGUMENT, "unterminated string at byte %zu", (size_t)(q - text));
+    while (first < close && *first == '0') first++;  // leading zeros carry no information
+    const size_t digits = (size_t)(close - first);
+    if (digits > 64) return fail(TKM_ERR_INVALID_ARGUMENT, "hex scalar at byte %zu exceeds 256 bits", (size_t)(q - text));
+    uint64_t v[4] = {0, 0, 0, 0};
+    for (size_t t = 0; t < digits; t++) {
+      const int d = HEX[(unsigned char)first[t]];
+      if (d < 0) return fail(TKM_ERR_INVALID_ARGUMENT, "invalid hex digit at byte %zu", (size_t)(first + t - text));
+      const size_t pos = digits - 1 - t;  // nibble index from the least significant end
+      v[pos >> 4] |= (uint64_t)d << ((pos & 15) * 4);
+    }
+    const size_t i = (size_t)(q - text);
+    (void)i;
+    // reduce into [0, r): at most two subtractions for a 256-bit value
+    for (int pass = 0; pass < 3; pass++) {
+      bool ge = true;
+      for (int k = 3; k >= 0; k--) {
+        if (v[k] != R[k]) {
+          ge = v[k] > R[k];
+          break;
+        }
+      }
+      if (!ge) break;
+      unsigned __int128 borrow = 0;
+      for (int k = 0; k < 4; k++) {
+        unsigned __int128 dd = (unsigned __int128)v[k] - R[k] - borrow;
+        v[k] = (uint64_t)dd;
+        borrow = (dd >> 64) & 1;
+      }
+    }
+    if (count >= capacity) return fail(TKM_ERR_INVALID_ARGUMENT, "more than %zu hex scalars in the text", capacity);
+    memcpy(out32 + count * 32, v, 32);
+    count++;
+    q = close + 1;
+  }
+  *out_count = count;
+  return TKM_OK;
+}
+
+// iden3 .r1cs binary -> CSR of the A, B, C matrices (R1csBinary::read + scan_constraints, libs/src/iotools/mod.rs:505-650).
+// Host only.  Pass 1 (row_ptr == NULL) reports the header and the entry counts; pass 2 fills row_ptr[3][n_constraints + 1]
+// (entry indices into wire / coeff32, matrix-major: all of A, then B, then C), wire[] and the canonical 32-byte coefficients.
+int32_t tkm_host_parse_r1cs(const uint8_t *data, size_t len, uint32_t *n_wires, uint32_t *n_constraints, size_t nnz[3], uint32_t *row_ptr,
+                            uint32_t *wire, uint8_t *coeff32) {
+  if (!data || !n_wires || !n_constraints || !nnz) return fail(TKM_ERR_INVALID_ARGUMENT, "null argument");
+  auto rd32 = [&](size_t off, uint32_t *v) {
+    if (off + 4 > len) return false;
+    memcpy(v, data + off, 4);
+    return true;
+  };
+  auto rd64 = [&](size_t off, uint64_t *v) {
+    if (off + 8 > len) return false;
+    memcpy(v, data + off, 8);
+    return true;
+  };
+  if (len < 12 || memcmp(data, "r1cs", 4) != 0) return fail(TKM_ERR_INVALID_ARGUMENT, "invalid R1CS magic");
+  uint32_t version, nsec;
+  rd32(4, &version);
+  rd32(8, &nsec);
+  if (version != 1) return fail(TKM_ERR_INVALID_ARGUMENT, "unsupported R1CS version %u", version);
+  size_t off = 12, hdr = 0, cons = 0, cons_size = 0;
+  bool have_h = false, have_c = false;
+  for (uint32_t k = 0; k < nsec; k++) {
+    uint32_t typ;
+    uint64_t size;
+    if (!rd32(off, &typ) || !rd64(off + 4, &size)) return fail(TKM_ERR_INVALID_ARGUMENT, "truncated R1CS section table");
+    off += 12;
+    if (size > len - off) return fail(TKM_ERR_INVALID_ARGUMENT, "R1CS section extends past end of file");
+    if (typ == 1 && !have_h) { hdr = off; have_h = true; }
+    if (typ == 2 && !have_c) { cons = off; cons_size = (size_t)size; have_c = true; }
+    off += (size_t)size;
+  }
+  if (!have_h || !have_c) return fail(TKM_ERR_INVALID_ARGUMENT, "missing R1CS header or constraints section");
+  uint32_t fs;
+  if (!rd32(hdr, &fs) || fs == 0 || fs % 8 || fs > 32) return fail(TKM_ERR_INVALID_ARGUMENT, "invalid R1CS field size");
+  uint32_t nw, nc;
+  if (!rd32(hdr + 4 + fs, &nw) || !rd32(hdr + 4 + fs + 4 * 4 + 8, &nc)) return fail(TKM_ERR_INVALID_ARGUMENT, "truncated R1CS header");
+  *n_wires = nw;
+  *n_constraints = nc;
+  static const uint64_t R[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+  size_t cnt[3] = {0, 0, 0};
+  size_t base[3] = {0, 0, 0};
+  if (row_ptr) {
+    base[1] = nnz[0];
+    base[2] = nnz[0] + nnz[1];
+  }
+  size_t c = cons;
+  const size_t cend = cons + cons_size;
+  for (uint32_t row = 0; row < nc; row++) {
+    for (int m = 0; m < 3; m++) {
+      uint32_t n_ent;
+      if (c + 4 > cend || !rd32(c, &n_ent)) return fail(TKM_ERR_INVALID_ARGUMENT, "truncated R1CS constraints");
+      c += 4;
+      if ((size_t)n_ent * (4 + fs) > cend - c) return fail(TKM_ERR_INVALID_ARGUMENT, "truncated R1CS constraints");
+      if (row_ptr) row_ptr[(size_t)m * (nc + 1) + row] = (uint32_t)(base[m] + cnt[m]);
+      for (uint32_t e = 0; e < n_ent; e++) {
+        uint32_t w;
+        rd32(c, &w);
+        if (w >= nw) return fail(TKM_ERR_INVALID_ARGUMENT, "R1CS wire index %u exceeds nWires %u", w, nw);
+        if (row_ptr) {
+          const size_t slot = base[m] + cnt[m];
+          if (cnt[m] >= nnz[m]) return fail(TKM_ERR_INVALID_ARGUMENT, "R1CS entry counts changed between passes");
+          wire[slot] = w;
+          uint64_t v[4] = {0, 0, 0, 0};
+          memcpy(v, data + c + 4, fs);
+          for (int pass = 0; pass < 3; pass++) {
+            bool ge = true;
+            for (int k = 3; k >= 0; k--)
+              if (v[k] != R[k]) {
+                ge = v[k] > R[k];
+                break;
+              }
+            if (!ge) break;
+            unsigned __int128 borrow = 0;
+            for (int k = 0; k < 4; k++) {
+              unsigned __int128 dd = (unsigned __int128)v[k] - R[k] - borrow;
+              v[k] = (uint64_t)dd;
+              borrow = (dd >> 64) & 1;
+            }
+          }
+          memcpy(coeff32 + slot * 32, v, 32);
+        }
+        cnt[m]++;
+        c += 4 + fs;
+      }
+    }
+  }
+  if (c != cend) return fail(TKM_ERR_INVALID_ARGUMENT, "R1CS constraints section has %zu trailing bytes", cend - c);
+  if (row_ptr) {
+    for (int m = 0; m < 3; m++) {
+      if (cnt[m] != nnz[m]) return fail(TKM_ERR_INVALID_ARGUMENT, "R1CS entry counts changed between passes");
+      row_ptr[(size_t)m * (nc + 1) + nc] = (uint32_t)(base[m] + cnt[m]);
+    }
+  } else {
+    for (int m = 0; m < 3; m++) nnz[m] = cnt[m];
+  }
+  return TKM_OK;
+}
+
 int32_t tkm_event_time_begin(tkm_ctx *ctx) {
   API_BEGIN
   TKM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));

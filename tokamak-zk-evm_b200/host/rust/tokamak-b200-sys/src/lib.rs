@@ -108,6 +108,9 @@ extern "C" {
                                  coset32: *const u8, peer_out: *const *mut c_void, n_peers: u32, stride_a: u64, stride_b: u64, b0: u64) -> i32;
     pub fn tkm_g1_bases_from_mont(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, n: usize) -> i32;
     pub fn tkm_kernel_time_last(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
+    pub fn tkm_host_parse_hex_scalars(text: *const c_char, len: usize, out32: *mut u8, capacity: usize, out_count: *mut usize) -> i32;
+    pub fn tkm_host_parse_r1cs(data: *const u8, len: usize, n_wires: *mut u32, n_constraints: *mut u32, nnz: *mut usize, row_ptr: *mut u32,
+                               wire: *mut u32, coeff32: *mut u8) -> i32;
     pub fn tkm_event_time_begin(ctx: *mut tkm_ctx) -> i32;
     pub fn tkm_event_time_end(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_launch_count(ctx: *mut tkm_ctx, out: *mut u64) -> i32;

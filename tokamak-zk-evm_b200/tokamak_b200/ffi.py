@@ -88,6 +88,8 @@ SIGNATURES = {
     "tkm_poly_commit": [c_void_p, c_void_p, c_void_p, c_void_p],
     "tkm_poly_commit_begin": [c_void_p, c_void_p, c_void_p, P(c_int32)],
     "tkm_commit_end": [c_void_p, c_int32, c_void_p],
+    "tkm_host_parse_hex_scalars": [ctypes.c_char_p, c_size_t, c_void_p, c_size_t, P(c_size_t)],
+    "tkm_host_parse_r1cs": [ctypes.c_char_p, c_size_t, P(c_uint32), P(c_uint32), P(c_size_t), c_void_p, c_void_p, c_void_p],
     "tkm_event_time_begin": [c_void_p],
     "tkm_event_time_end": [c_void_p, P(ctypes.c_float)],
     "tkm_launch_count": [c_void_p, P(c_uint64)],

@@ -47,10 +47,36 @@ class SubcircuitInfo:
     flattenMap: List[int]
 
 
+class ScalarArray:
+    """A placement's variables as a (k, 4) uint64 array of canonical little-endian limbs (what the native loader
+    produces and what the device takes) that still reads like a list of integers for the host-side code paths."""
+
+    def __init__(self, limbs):
+        import numpy as np
+
+        self.limbs = np.ascontiguousarray(limbs, dtype=np.uint64).reshape(-1, 4)
+
+    def __len__(self):
+        return self.limbs.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        a = self.limbs[i]
+        return int(a[0]) | (int(a[1]) << 64) | (int(a[2]) << 128) | (int(a[3]) << 192)
+
+    def __iter__(self):
+        b = self.limbs.tobytes()
+        return (int.from_bytes(b[k:k + 32], "little") for k in range(0, len(b), 32))
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
 @dataclass
 class PlacementVariables:
     subcircuitId: int
-    variables: List[int]  # field elements (JSON: hex strings)
+    variables: List[int]  # field elements (JSON: hex strings); a ScalarArray when read by the native loader
 
 
 @dataclass
@@ -160,6 +186,20 @@ def write_library(qap_path, params: SetupParams, infos, r1cs_list):
         write_r1cs(os.path.join(qap_path, "r1cs", f"subcircuit{s.id}.r1cs"), r, n_pub_out=s.Out_idx[1], n_pub_in=s.In_idx[1])
 
 
+def read_library_meta(qap_path):
+    """setupParams.json + subcircuitInfo.json (+ the globalWireList consistency check) without the .r1cs binaries, which
+    qap.library_csr_from_files parses natively."""
+    params = SetupParams(**json.load(open(os.path.join(qap_path, "setupParams.json"))))
+    infos = [SubcircuitInfo(**{k: d[k] for k in ("id", "name", "Nwires", "Nconsts", "Out_idx", "In_idx", "flattenMap")})
+             for d in json.load(open(os.path.join(qap_path, "subcircuitInfo.json")))]
+    gwl = json.load(open(os.path.join(qap_path, "globalWireList.json")))
+    for s in infos:
+        for local, g in enumerate(s.flattenMap):
+            if gwl[g] != [s.id, local]:
+                raise ValueError("GlobalWireList is not the inverse of flattenMap.")
+    return params, infos
+
+
 def read_library(qap_path):
     params = SetupParams(**json.load(open(os.path.join(qap_path, "setupParams.json"))))
     infos = [SubcircuitInfo(**{k: d[k] for k in ("id", "name", "Nwires", "Nconsts", "Out_idx", "In_idx", "flattenMap")})
@@ -186,7 +226,44 @@ def write_synthesizer_output(path, placements, permutation, instance: Instance):
     _dump(os.path.join(path, "instance.json"), {k: [to_hex(v) for v in getattr(instance, k)] for k in ("a_pub_user", "a_pub_block", "a_pub_function")})
 
 
-def read_synthesizer_output(path):
+def read_placement_variables_native(path, infos):
+    """placementVariables.json through the library's host-side loader (tkm_host_parse_hex_scalars): the file is scanned
+    once in native code, the values never become Python integers.  `infos` gives the wire count of every subcircuit."""
+    import ctypes
+    import re
+
+    import numpy as np
+
+    from .. import ffi
+
+    data = open(os.path.join(path, "placementVariables.json"), "rb").read()
+    ids = [int(m) for m in re.findall(rb'"subcircuitId"\s*:\s*(\d+)', data)]
+    total = sum(infos[i].Nwires for i in ids)
+    vals = np.empty((total, 4), dtype=np.uint64)
+    count = ctypes.c_size_t()
+    ffi.check(ffi.load().tkm_host_parse_hex_scalars(data, len(data), vals.ctypes.data_as(ctypes.c_void_p), total, ctypes.byref(count)))
+    if count.value != total:
+        raise ValueError("Corrupted placement variables.")
+    out, off = [], 0
+    for i in ids:
+        k = infos[i].Nwires
+        out.append(PlacementVariables(i, ScalarArray(vals[off:off + k])))
+        off += k
+    return out
+
+
+def read_synthesizer_output(path, infos=None):
+    """permutation.json, instance.json and placementVariables.json; with `infos` the 40 MB of hex strings go through the
+    native loader."""
+    if infos is not None:
+        placements = read_placement_variables_native(path, infos)
+        permutation = [Permutation(d["row"], d["col"], d["X"], d["Y"]) for d in json.load(open(os.path.join(path, "permutation.json")))]
+        d = json.load(open(os.path.join(path, "instance.json")))
+        return placements, permutation, Instance(*[[from_hex(v) for v in d[k]] for k in ("a_pub_user", "a_pub_block", "a_pub_function")])
+    return _read_synthesizer_output_python(path)
+
+
+def _read_synthesizer_output_python(path):
     # int(v, 16) accepts the 0x prefix; values above r (never produced by the synthesizer) are reduced like from_hex does
     placements = []
     for d in json.load(open(os.path.join(path, "placementVariables.json"))):

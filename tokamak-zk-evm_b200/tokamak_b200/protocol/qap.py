@@ -52,6 +52,52 @@ class LibraryCSR:
         self.r1cs_list = r1cs_list
 
 
+def library_csr_from_files(qap_path, params, infos):
+    """LibraryCSR straight from r1cs/subcircuit{i}.r1cs through the library's host-side parser (tkm_host_parse_r1cs): no
+    Python-level constraint lists are built.  Checks nWires / nConstraints against subcircuitInfo.json and n like
+    SubcircuitR1CS::from_r1cs_with_mode (iotools/mod.rs:714-734)."""
+    import ctypes
+    import os
+
+    from .. import ffi
+
+    lib = ffi.load()
+    s_d = len(infos)
+    csr = LibraryCSR.__new__(LibraryCSR)
+    csr.n_rows = np.zeros(s_d, dtype=np.uint32)
+    csr.rp_base = np.zeros(s_d * 3, dtype=np.uint64)
+    rps, wires, coeffs = [], [], []
+    rp_off = ent_off = 0
+    for s, info in enumerate(infos):
+        data = open(os.path.join(qap_path, "r1cs", f"subcircuit{info.id}.r1cs"), "rb").read()
+        nw, nc = ctypes.c_uint32(), ctypes.c_uint32()
+        nnz = (ctypes.c_size_t * 3)()
+        ffi.check(lib.tkm_host_parse_r1cs(data, len(data), ctypes.byref(nw), ctypes.byref(nc), nnz, None, None, None))
+        if nw.value != info.Nwires or nc.value != info.Nconsts:
+            raise ValueError(f"R1CS shape mismatch for subcircuit {info.id}")
+        if params.n < nc.value:
+            raise ValueError("n is smaller than the actual number of constraints.")
+        total = nnz[0] + nnz[1] + nnz[2]
+        rp = np.zeros(3 * (nc.value + 1), dtype=np.uint32)
+        wi = np.zeros(max(total, 1), dtype=np.uint32)
+        co = np.zeros((max(total, 1), 4), dtype=np.uint64)
+        ffi.check(lib.tkm_host_parse_r1cs(data, len(data), ctypes.byref(nw), ctypes.byref(nc), nnz, rp.ctypes.data_as(ctypes.c_void_p),
+                                          wi.ctypes.data_as(ctypes.c_void_p), co.ctypes.data_as(ctypes.c_void_p)))
+        csr.n_rows[s] = nc.value
+        for m in range(3):
+            csr.rp_base[3 * s + m] = rp_off + m * (nc.value + 1)
+        rps.append(rp + np.uint32(ent_off))
+        wires.append(wi[:total])
+        coeffs.append(co[:total])
+        rp_off += rp.shape[0]
+        ent_off += total
+    csr.row_ptr = np.concatenate(rps)
+    csr.wire = np.concatenate(wires) if ent_off else np.zeros(0, dtype=np.uint32)
+    csr.coeff = np.concatenate(coeffs) if ent_off else np.zeros((0, 4), dtype=np.uint64)
+    csr.r1cs_list = None
+    return csr
+
+
 class WitnessTable:
     """All placement variables as one (total, 4) uint64 array of canonical limbs + per-column offsets: the in-memory form
     of placementVariables.json the vectorised host code and the device kernels work on."""
@@ -70,7 +116,8 @@ class WitnessTable:
             self.sub_of_col[col] = pl.subcircuitId
             self.var_off[col] = off
             off += len(pl.variables)
-            chunks.append(b"".join([v.to_bytes(32, "little") for v in pl.variables]))
+            limbs = getattr(pl.variables, "limbs", None)  # ScalarArray from the native loader: already in device layout
+            chunks.append(limbs.tobytes() if limbs is not None else b"".join([v.to_bytes(32, "little") for v in pl.variables]))
         self.values = np.frombuffer(b"".join(chunks), dtype=np.uint64).reshape(-1, 4)
         self.fmap = [np.array(s.flattenMap, dtype=np.int64) for s in infos]
 
