@@ -117,3 +117,65 @@ def test_g1_ops(L):
     o = np.zeros(24, dtype=np.uint32)
     L.h_g1_dbl_n(pp(g1b(pts[1])), 16, pp(o))
     assert g1t(o) == P.g1_mul(pts[1], 1 << 16)
+
+
+LAMBDA = 0xAC45A4010001A40200000000FFFFFFFF
+
+
+def test_glv_split_and_digits(L):
+    """csrc/glv.cuh: k = k1 + k2*lambda (mod r) with both halves below 2^127, and the signed-digit streams k_decompose
+    emits (plain and GLV) rebuild the scalar for every window width the MSM picks."""
+    assert (LAMBDA * LAMBDA + LAMBDA + 1) == P.R_MOD
+    rng = random.Random(11)
+    r = P.R_MOD
+    edge = [0, 1, 2, r - 1, r - 2, LAMBDA - 1, LAMBDA, LAMBDA + 1, LAMBDA // 2, LAMBDA // 2 + 1, (LAMBDA + 1) // 2 * LAMBDA,
+            ((LAMBDA + 1) // 2 + 1) * LAMBDA, ((LAMBDA + 1) // 2 + 1) * LAMBDA - 1, (LAMBDA + 1) * LAMBDA, r // 2, r // 2 + 1,
+            (1 << 127) - 1, 1 << 127, (1 << 128) - 1, 1 << 128, (1 << 255) % r, (1 << 64) - 1,
+            r, r + 1, 2 * r, 2 * r + 5, (1 << 256) - 1]  # non-canonical inputs fold into [0, r)
+    vals = edge + [rng.randrange(r) for _ in range(3000)] + [rng.randrange(1 << k) for k in (8, 32, 64, 126, 127, 128, 129, 200) for _ in range(40)]
+    vals += [q * LAMBDA + d for q in (0, 1, (LAMBDA + 1) // 2 - 1, (LAMBDA + 1) // 2, (LAMBDA + 1) // 2 + 1, LAMBDA) for d in (0, 1, LAMBDA // 2, LAMBDA // 2 + 1, LAMBDA - 1)]
+    out = np.zeros(10, dtype=np.uint32)
+    digs = np.zeros(160, dtype=np.int32)
+    for k in vals:
+        L.h_glv_split(pp(u32(k, 8)), pp(out))
+        m1, m2 = toint(out[0:4]), toint(out[4:8])
+        k1 = -m1 if out[8] else m1
+        k2 = -m2 if out[9] else m2
+        assert m1 < (1 << 127) and m2 < (1 << 127), hex(k)
+        assert (k1 + k2 * LAMBDA - k) % r == 0, hex(k)
+        for c in (4, 7, 8, 11, 13, 15, 16, 17, 20):
+            nw = L.h_msm_digits(pp(u32(k, 8)), c, 1, pp(digs))
+            wh = (128 + c - 1) // c
+            assert nw == 2 * wh
+            d = [int(x) for x in digs[:nw]]
+            assert all(abs(x) <= (1 << (c - 1)) for x in d)  # bucket index |digit| - 1 < 2^(c-1)
+            assert sum(x << (c * w) for w, x in enumerate(d[:wh])) == k1
+            assert sum(x << (c * w) for w, x in enumerate(d[wh:])) == k2
+            if k < (1 << 255):
+                nw = L.h_msm_digits(pp(u32(k, 8)), c, 0, pp(digs))
+                assert nw == (256 + c - 1) // c
+                assert sum(int(x) << (c * w) for w, x in enumerate(digs[:nw])) == k
+
+
+def test_glv_endomorphism(L):
+    rng = random.Random(12)
+    for _ in range(4):
+        pt = P.g1_mul(P.G1_GEN, rng.randrange(P.R_MOD))
+        o = np.zeros(24, dtype=np.uint32)
+        L.h_g1_phi(pp(g1b(pt)), pp(o))
+        assert g1t(o) == P.g1_mul(pt, LAMBDA)
+
+
+@pytest.mark.parametrize("name", ["fr", "fq"])
+def test_binary_gcd_inverse(L, name):
+    """Fp::inv_bgcd (binary extended Euclid, used by the MSM tail) equals the Fermat inverse; inv(0) = 0."""
+    mod, n, fn = (P.R_MOD, 8, L.h_fr_op) if name == "fr" else (P.Q_MOD, 12, L.h_fq_op)
+    rng = random.Random(21)
+    R = 1 << (32 * n)
+    vals = [0, 1, 2, 3, 4, mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1, R % mod, pow(R, -1, mod), (1 << 32) - 1, 1 << 32, 1 << (32 * n - 2)]
+    vals += [rng.randrange(mod) for _ in range(300)] + [1 << k for k in range(0, 32 * n - 1, 37)]
+    for a in vals:
+        a %= mod
+        o = np.zeros(n, dtype=np.uint32)
+        fn(7, pp(u32(a, n)), pp(u32(a, n)), pp(o))
+        assert toint(o) == (pow(a, mod - 2, mod) if a else 0), (name, hex(a))

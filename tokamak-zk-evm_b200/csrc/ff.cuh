@@ -379,6 +379,73 @@ struct alignas(16) Fp {
     }
     return acc;
   }
+  // The same inverse by the binary extended Euclid (shifts and subtractions only): ~2*bits cheap steps instead of ~1.5*bits
+  // dependent Montgomery products.  For the latency-bound single-chain tails (one warp converting one point to affine) it is
+  // several times faster than the Fermat chain; the loop trip counts depend on the value, so it is for replicated or scalar
+  // use, not for lanes that hold different values.  Invariants: a*x1 = u, a*x2 = v (mod p) with a the limbs of *this read
+  // as an integer; they end at u = 1 or v = 1.  *this = A*R gives (A*R)^-1; two Montgomery products by R^2 restore A^-1*R.
+  TKM_HD Fp inv_bgcd() const {
+    if (is_zero()) return zero();
+    uint32_t u[N], w[N];
+    Fp x1 = zero(), x2 = zero();
+    x1.v[0] = 1;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      u[i] = v[i];
+      w[i] = P::mod(i);
+    }
+    for (;;) {
+      while (!(u[0] & 1)) {
+        shr1(u, 0);
+        x1.halve();
+      }
+      if (is_one(u)) break;
+      while (!(w[0] & 1)) {
+        shr1(w, 0);
+        x2.halve();
+      }
+      if (is_one(w)) break;
+      uint32_t d[N];
+      d[0] = sub_cc(u[0], w[0]);
+#pragma unroll
+      for (int i = 1; i < N; i++) d[i] = subc_cc(u[i], w[i]);
+      const uint32_t borrow = subc(0, 0);  // all-ones if u < w
+      if (!borrow) {
+#pragma unroll
+        for (int i = 0; i < N; i++) u[i] = d[i];
+        x1 = x1 - x2;
+      } else {
+        w[0] = sub_cc(w[0], u[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) w[i] = subc_cc(w[i], u[i]);
+        w[N - 1] = subc(w[N - 1], u[N - 1]);
+        x2 = x2 - x1;
+      }
+    }
+    const Fp t = is_one(u) ? x1 : x2;
+    return (t * r2()) * r2();
+  }
+  // helpers of inv_bgcd
+  TKM_HD static bool is_one(const uint32_t *a) {
+    uint32_t acc = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < N; i++) acc |= a[i];
+    return acc == 0;
+  }
+  TKM_HD static void shr1(uint32_t *a, uint32_t top_bit) {
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[N - 1] = (a[N - 1] >> 1) | (top_bit << 31);
+  }
+  // x/2 mod p for x in [0, p): (x odd ? x + p : x) >> 1.  x + p < 2^(32N) for both fields (no carry out of the container).
+  TKM_HD void halve() {
+    const uint32_t mask = 0u - (v[0] & 1u);
+    v[0] = add_cc(v[0], P::mod(0) & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) v[i] = addc_cc(v[i], P::mod(i) & mask);
+    v[N - 1] = addc(v[N - 1], P::mod(N - 1) & mask);
+    shr1(v, 0);
+  }
 };
 
 using Fr = Fp<FrParams>;

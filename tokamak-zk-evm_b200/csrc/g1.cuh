@@ -78,7 +78,9 @@ __device__ __forceinline__ Fq g1_bcast4(const Fq &v, int src_sub) {
   return r;
 }
 __device__ __forceinline__ G1Xyzz g1_dbl_coop4(const G1Xyzz &p) {
-  if (p.is_identity()) return p;  // replicas agree, so the whole group takes the same branch
+  // No early return for the identity: groups of one warp may carry different accumulators (the two GLV chains of
+  // k_final) and every lane must reach the full-mask shuffles.  The formulas map the all-zero identity to itself
+  // (every product has a zero factor; ZZ3 = V*ZZ = 0 for any representation with ZZ = 0).
   const int sub = threadIdx.x & 3;
   const Fq U = p.Y.dbl();
   // level 1: V = U^2 | XX = X^2

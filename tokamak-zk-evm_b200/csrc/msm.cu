@@ -4,7 +4,8 @@
 // commitment (libs/src/iotools/mod.rs:2093-2099; libs/src/group_structures/mod.rs:108-114,135-141).
 //
 // Pipeline (all on the context stream, no host synchronisation until the 96-byte result is read):
-//   1. k_decompose     one thread per scalar: (optional from-Montgomery,) signed c-bit digits;
+//   1. k_decompose     one thread per scalar: (optional from-Montgomery,) GLV split k = k1 + k2*lambda into
+//                      two signed 127-bit halves (glv.cuh), signed c-bit digits of each half;
 //                      emits (bucket key, base index | sign) pairs, window-major, zero digits keyed
 //                      to a trash bucket that sorts last.
 //   2. cub radix sort  of the pairs by bucket key (only the significant key bits).
@@ -16,20 +17,23 @@
 //                      full XYZZ additions, 32 entries per warp), repeated until one warp remains.
 //   5. k_bucket_seg /  parallel window reduction: running sums over 16-bucket segments, then per
 //      k_bucket_bits   window a masked tree-sum per index bit (sum_d d*B_d = sum_k 2^k sum_{d: bit k} B_d),
-//   6. k_final         per-window recombination in parallel lanes, Horner over windows, one inversion
-//                      to affine.
+//   6. k_final         per-window recombination in parallel lanes, Horner over the windows of each half as two
+//                      concurrent chains, sum = chain1 + phi(chain2), one inversion to affine.
 // Integer-pipe bound: N*W mixed additions of ~10 Fq products each; no tensor cores.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdlib>
 
 #include "common.cuh"
+#include "glv.cuh"
 
 namespace tkm {
 
 struct MsmGeom {
   uint32_t c;        // window bits
-  uint32_t Wd;       // digit windows of the scalar decomposition
+  uint32_t Wd;       // digit windows of the scalar decomposition (GLV: 2*Wh, half h owns windows [h*Wh, h*Wh + Wh))
+  uint32_t glv;      // 1: scalars are split k = k1 + k2*lambda (glv.cuh); 0: plain 256-bit digits (fixed-base tables)
+  uint32_t Wh;       // windows per chain of the Horner tail (= Wd/2 with GLV, Wd without)
   uint32_t val_stride;  // 0, or (fixed-base tables) offset of window w's table: base index += w*val_stride
   uint32_t W;        // bucket windows (= Wd; 1 when precomputed tables fold every window into one bucket set)
   uint32_t B;        // buckets per window = 2^(c-1)
@@ -45,8 +49,11 @@ static MsmGeom pick_geom(size_t n, uint32_t fixed_c = 0, uint32_t table_stride =
   // minimise W*(n + 3*2^(c-1)) -- mixed adds plus ~3 madd-equivalents per bucket of reduction
   double best = 1e300;
   uint32_t bc = 8;
+  // GLV halves cover 128 bits each (|k1|, |k2| < 2^127 plus the carry bit of the signed recoding).
+  static const bool glv_off = getenv("TKM_MSM_NO_GLV") != nullptr;  // developer knob: plain 256-bit digits
+  const bool use_glv = !fixed_c && !glv_off;
   for (uint32_t c = 4; c <= 20; c++) {
-    uint32_t W = (256 + c - 1) / c;
+    uint32_t W = use_glv ? 2 * ((128 + c - 1) / c) : (256 + c - 1) / c;
     double cost = (double)W * ((double)n + 3.0 * (double)(1u << (c - 1)));
     if (cost < best) {
       best = cost;
@@ -56,7 +63,9 @@ static MsmGeom pick_geom(size_t n, uint32_t fixed_c = 0, uint32_t table_stride =
   if (fixed_c) bc = fixed_c;
   MsmGeom m;
   m.c = bc;
-  m.Wd = (256 + bc - 1) / bc;
+  m.glv = use_glv ? 1 : 0;
+  m.Wh = use_glv ? (128 + bc - 1) / bc : (256 + bc - 1) / bc;
+  m.Wd = use_glv ? 2 * m.Wh : m.Wh;
   m.val_stride = table_stride;
   m.W = fixed_c ? 1 : m.Wd;
   m.logB = bc - 1;
@@ -96,27 +105,22 @@ __global__ void __launch_bounds__(256) k_decompose(const Fr *__restrict__ scalar
     Fr s = scalars[(size_t)i * s_row_stride + j];
     if (scalars_mont) s = s.from_mont();
     uint32_t base_idx = gather ? gather[k] : (uint32_t)((size_t)i * b_row_stride + j);
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < m.Wd; w++) {
-      uint32_t bit = w * m.c;
-      uint32_t limb = bit >> 5, sh = bit & 31;
-      uint32_t raw = 0;
-      if (limb < 8) {
-        uint64_t two = s.v[limb];
-        if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
-        raw = (uint32_t)(two >> sh) & ((1u << m.c) - 1);
+    GlvSplit sp;
+    if (m.glv) sp = glv_split(s.v);
+    const uint32_t halves = m.glv ? 2 : 1;
+    for (uint32_t h = 0; h < halves; h++) {
+      const uint32_t *limbs = m.glv ? sp.mag[h] : s.v;
+      const uint32_t nl = m.glv ? 4 : 8;
+      const uint32_t flip = m.glv ? sp.neg[h] : 0;
+      uint32_t carry = 0;
+      for (uint32_t wi = 0; wi < m.Wh; wi++) {
+        uint32_t mag, neg;
+        signed_digit(limbs, nl, wi, m.c, carry, mag, neg);
+        const uint32_t w = h * m.Wh + wi;
+        size_t slot = (size_t)w * n + k;
+        keys[slot] = mag ? ((m.W == 1 ? 0u : w * m.B) + mag - 1) : m.nbuckets;
+        vals[slot] = (base_idx + w * m.val_stride) | ((neg ^ flip) << 31);
       }
-      raw += carry;
-      uint32_t neg = 0, mag = raw;
-      carry = 0;
-      if (raw > m.B) {
-        mag = (1u << m.c) - raw;
-        neg = 1;
-        carry = 1;
-      }
-      size_t slot = (size_t)w * n + k;
-      keys[slot] = mag ? ((m.W == 1 ? 0u : w * m.B) + mag - 1) : m.nbuckets;
-      vals[slot] = (base_idx + w * m.val_stride) | (neg << 31);
     }
   }
 }
@@ -201,6 +205,13 @@ __device__ __forceinline__ Fq shfl_down_fq(const Fq &a, int d) {
   Fq r;
 #pragma unroll
   for (int i = 0; i < Fq::N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+  return r;
+}
+
+__device__ __forceinline__ Fq shfl_fq(const Fq &a, int src_lane) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < Fq::N; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src_lane);
   return r;
 }
 
@@ -346,13 +357,29 @@ __global__ void __launch_bounds__(32) k_final(const G1Xyzz *__restrict__ parts, 
     store_xyzz(window_sums + w, acc);
   }
   __syncthreads();
-  // Horner over windows: one dependency chain of W*c doublings.  Every lane carries a replica of the accumulator
-  // and groups of four lanes split each doubling's products (g1_dbl_coop4) to cut the chain latency.
+  // Horner over windows: a dependency chain of Wh*c doublings per half.  Every lane carries a replica of an accumulator
+  // and groups of four lanes split each doubling's products (g1_dbl_coop4) to cut the chain latency.  With GLV the
+  // groups with (lane>>2) even run the k1 chain (windows 0..Wh-1) and the odd groups the k2 chain (windows Wh..2Wh-1)
+  // at the same time; the result is chain1 + phi(chain2), phi(X, Y, ZZ, ZZZ) = (beta*X, Y, ZZ, ZZZ).
+  const uint32_t chain = m.glv ? ((lane >> 2) & 1) : 0;
+  const uint32_t Wc = m.glv ? m.Wh : m.W;  // bucket windows per chain (W = 1 with fixed-base tables)
   G1Xyzz acc = G1Xyzz::identity();
-  for (int w = (int)m.W - 1; w >= 0; w--) {
+  for (int w = (int)Wc - 1; w >= 0; w--) {
     for (uint32_t k = 0; k < m.c; k++) acc = g1_dbl_coop4(acc);
-    G1Xyzz s = load_xyzz(window_sums + w);
+    G1Xyzz s = load_xyzz(window_sums + chain * Wc + w);
     g1_add(acc, s);
+    __syncwarp();
+  }
+  if (m.glv) {
+    G1Xyzz a, b;
+    a.X = shfl_fq(acc.X, 0); a.Y = shfl_fq(acc.Y, 0); a.ZZ = shfl_fq(acc.ZZ, 0); a.ZZZ = shfl_fq(acc.ZZZ, 0);
+    b.X = shfl_fq(acc.X, 4); b.Y = shfl_fq(acc.Y, 4); b.ZZ = shfl_fq(acc.ZZ, 4); b.ZZZ = shfl_fq(acc.ZZZ, 4);
+    Fq beta;
+#pragma unroll
+    for (int i = 0; i < Fq::N; i++) beta.v[i] = glv::beta(i);
+    b.X = b.X * beta.to_mont();
+    acc = a;
+    g1_add(acc, b);
   }
   G1Affine r = g1_to_affine_coop(acc);
   if (lane == 0) {
