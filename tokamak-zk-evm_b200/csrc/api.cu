@@ -24,7 +24,7 @@ __global__ void k_g1_add_single(const G1Affine *a, const G1Affine *b, uint32_t *
 }
 
 // Sum of n canonical affine points (partial sums of the point-range shards): one warp, every lane
-// carries a replica so the final inversion can use the cooperative two-lane ladder.
+// carries a replica (g1_to_affine_coop).
 __global__ void __launch_bounds__(32) k_g1_sum_canonical(const G1Affine *pts, size_t n, uint32_t *out_canonical) {
   G1Xyzz acc = G1Xyzz::identity();
   for (size_t i = 0; i < n; i++) {

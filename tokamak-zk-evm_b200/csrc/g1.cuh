@@ -81,6 +81,7 @@ __device__ __forceinline__ G1Xyzz g1_dbl_coop4(const G1Xyzz &p) {
   // No early return for the identity: groups of one warp may carry different accumulators (the two GLV chains of
   // k_final) and every lane must reach the full-mask shuffles.  The formulas map the all-zero identity to itself
   // (every product has a zero factor; ZZ3 = V*ZZ = 0 for any representation with ZZ = 0).
+  if (__all_sync(0xffffffffu, p.is_identity())) return p;  // warp-uniform: nothing to double anywhere
   const int sub = threadIdx.x & 3;
   const Fq U = p.Y.dbl();
   // level 1: V = U^2 | XX = X^2
@@ -103,36 +104,12 @@ __device__ __forceinline__ G1Xyzz g1_dbl_coop4(const G1Xyzz &p) {
   r.ZZZ = g1_bcast4(r3, 3);
   return r;
 }
-// Fermat inverse with the squaring chain and the multiply chain on two cooperating lanes (even lane squares the
-// base, odd lane multiplies the accumulator): 381 product latencies instead of ~570.  Replicated input/output.
-__device__ __forceinline__ Fq fq_inv_coop2(const Fq &a) {
-  const int role = threadIdx.x & 1;
-  const int pair = threadIdx.x & 30;
-  Fq acc = Fq::one(), base = a;
-  uint32_t borrow = 2;
-  for (int i = 0; i < Fq::N; i++) {
-    uint32_t m = FqParams::mod(i);
-    uint32_t e = m - borrow;
-    borrow = (m < borrow) ? 1u : 0u;
-    for (int b = 0; b < 32; b++) {
-      Fq x = role ? acc : base;
-      Fq r = x * base;  // even lane: base^2, odd lane: acc*base
-      Fq nb, na;
-#pragma unroll
-      for (int k = 0; k < Fq::N; k++) {
-        nb.v[k] = __shfl_sync(0xffffffffu, r.v[k], pair);
-        na.v[k] = __shfl_sync(0xffffffffu, r.v[k], pair + 1);
-      }
-      base = nb;
-      if ((e >> b) & 1) acc = na;
-    }
-  }
-  return acc;
-}
-// Affine conversion for replicated inputs (every lane of the warp calls it with the same point).
+// Affine conversion for replicated inputs (every lane of the warp calls it with the same point): a single latency-bound
+// chain, so the inverse is the binary extended Euclid (Fp::inv_bgcd, ~0.8 k shift/subtract steps) rather than the Fermat
+// chain of ~570 dependent Montgomery products.  The replicas run the same data-dependent loops: no divergence.
 __device__ __forceinline__ G1Affine g1_to_affine_coop(const G1Xyzz &p) {
   if (p.is_identity()) return G1Affine::identity();
-  Fq t = fq_inv_coop2(p.ZZ * p.ZZZ);
+  Fq t = (p.ZZ * p.ZZZ).inv_bgcd();
   Fq zz_inv = t * p.ZZZ;
   Fq zzz_inv = t * p.ZZ;
   return G1Affine{p.X * zz_inv, p.Y * zzz_inv};

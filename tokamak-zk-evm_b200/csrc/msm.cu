@@ -16,9 +16,10 @@
 //   4. k_segreduce     warp-cooperative segmented reduction of the partial list (shuffle tree of
 //                      full XYZZ additions, 32 entries per warp), repeated until one warp remains.
 //   5. k_bucket_seg /  parallel window reduction: running sums over 16-bucket segments, then per
-//      k_bucket_bits   window a masked tree-sum per index bit (sum_d d*B_d = sum_k 2^k sum_{d: bit k} B_d),
-//   6. k_final         per-window recombination in parallel lanes, Horner over the windows of each half as two
-//                      concurrent chains, sum = chain1 + phi(chain2), one inversion to affine.
+//      k_bucket_bits / window a masked tree-sum per index bit (sum_d d*B_d = sum_k 2^k sum_{d: bit k} B_d), each
+//      k_window_sums   part weighted by its 2^k where it is produced, window sums as shuffle tree-sums,
+//   6. k_final         Horner over the windows of each half as two concurrent chains, sum = chain1 + phi(chain2),
+//                      one inversion (binary extended Euclid) to affine.
 // Integer-pipe bound: N*W mixed additions of ~10 Fq products each; no tensor cores.
 #include <cub/device/device_radix_sort.cuh>
 
@@ -287,6 +288,15 @@ __global__ void __launch_bounds__(128) k_bucket_seg(const G1Xyzz *__restrict__ b
 }
 
 constexpr int BITS_THREADS = 128;
+// Part (w, k) of the window reduction enters the window sum as g * 2^k * M_{w,k} (k < nbits) or as A_w (k == nbits):
+// the k + log2(g) doublings are done here, by the first warp of the block that finished the part (cooperative doubling on
+// replicas), so that all parts are weighted concurrently on different SMs and the window sum is a plain tree-sum.
+__device__ __forceinline__ void weigh_and_store_part(const G1Xyzz &part, uint32_t k, uint32_t nbits, uint32_t logg, G1Xyzz *dst) {
+  G1Xyzz a = part;
+  const uint32_t nd = (k == nbits) ? 0 : k + logg;
+  for (uint32_t i = 0; i < nd; i++) a = g1_dbl_coop4(a);
+  if ((threadIdx.x & 31) == 0) store_xyzz(dst, a);
+}
 // Block (w, k, slice): k < nbits -> partial of M_k = sum over segments s with bit k set of run_s ; k == nbits -> partial of
 // A = sum_s acc_s.  Each block tree-sums one slice of the window's segments (`splits` slices per (w, k)) so the
 // reduction stays parallel when there are few windows (fixed-base tables: one window, 2^19 buckets).
@@ -315,10 +325,16 @@ __global__ void __launch_bounds__(BITS_THREADS) k_bucket_bits(const G1Xyzz *__re
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
+  if (splits > 1) {
+    if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
+    return;
+  }
+  if (threadIdx.x < 32) weigh_and_store_part(sh[0], k, m.nbits, m.logg, out + blockIdx.x);
 }
-// out[g] = sum of the `count` consecutive points in[g*count ..] (second stage of the sliced reduction).
-__global__ void __launch_bounds__(32) k_sum_groups(const G1Xyzz *__restrict__ in, uint32_t count, G1Xyzz *__restrict__ out) {
+// out[g] = sum of the `count` consecutive points in[g*count ..] (second stage of the sliced reduction), weighted like
+// k_bucket_bits' single-slice result.
+__global__ void __launch_bounds__(32) k_sum_groups(const G1Xyzz *__restrict__ in, uint32_t count, uint32_t nbits, uint32_t logg,
+                                                  G1Xyzz *__restrict__ out) {
   __shared__ G1Xyzz sh[32];
   G1Xyzz acc = G1Xyzz::identity();
   for (uint32_t s = threadIdx.x; s < count; s += 32) {
@@ -335,28 +351,31 @@ __global__ void __launch_bounds__(32) k_sum_groups(const G1Xyzz *__restrict__ in
     }
     __syncwarp();
   }
-  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
+  weigh_and_store_part(sh[0], blockIdx.x % (nbits + 1), nbits, logg, out + blockIdx.x);
+}
+
+// Window sums S_w = A_w + g * sum_k 2^k M_{w,k} from the weighted parts: block w, one lane per part, shuffle tree.
+__global__ void __launch_bounds__(32) k_window_sums(const G1Xyzz *__restrict__ parts, uint32_t nparts, G1Xyzz *__restrict__ window_sums) {
+  const uint32_t lane = threadIdx.x;
+  G1Xyzz pt = G1Xyzz::identity();
+  if (lane < nparts) pt = load_xyzz(parts + (size_t)blockIdx.x * nparts + lane);  // nparts = nbits + 1 <= 22
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) {
+    G1Xyzz o;
+    o.X = shfl_down_fq(pt.X, d);
+    o.Y = shfl_down_fq(pt.Y, d);
+    o.ZZ = shfl_down_fq(pt.ZZ, d);
+    o.ZZZ = shfl_down_fq(pt.ZZZ, d);
+    if (lane + d < 32) g1_add(pt, o);
+  }
+  if (lane == 0) store_xyzz(window_sums + blockIdx.x, pt);
 }
 
 // ---------------------------------------------------------------- 6. recombination
-// Lane w: S_w = A_w + g * sum_k 2^k M_{w,k}.  Lane 0 then runs Horner over windows and converts to affine.
-__global__ void __launch_bounds__(32) k_final(const G1Xyzz *__restrict__ parts, MsmGeom m, G1Xyzz *__restrict__ window_sums,
-                                             G1Affine *__restrict__ out_mont, uint32_t *__restrict__ out_canonical) {
+// One warp: Horner over the window sums, conversion to affine.
+__global__ void __launch_bounds__(32) k_final(const G1Xyzz *__restrict__ window_sums, MsmGeom m, G1Affine *__restrict__ out_mont,
+                                             uint32_t *__restrict__ out_canonical) {
   const uint32_t lane = threadIdx.x;
-  for (uint32_t w = lane; w < m.W; w += 32) {
-    const G1Xyzz *pw = parts + (size_t)w * (m.nbits + 1);
-    G1Xyzz acc = G1Xyzz::identity();
-    for (int k = (int)m.nbits - 1; k >= 0; k--) {
-      acc = g1_dbl(acc);
-      G1Xyzz mk = load_xyzz(pw + k);
-      g1_add(acc, mk);
-    }
-    for (uint32_t k = 0; k < m.logg; k++) acc = g1_dbl(acc);
-    G1Xyzz a = load_xyzz(pw + m.nbits);
-    g1_add(acc, a);
-    store_xyzz(window_sums + w, acc);
-  }
-  __syncthreads();
   // Horner over windows: a dependency chain of Wh*c doublings per half.  Every lane carries a replica of an accumulator
   // and groups of four lanes split each doubling's products (g1_dbl_coop4) to cut the chain latency.  With GLV the
   // groups with (lane>>2) even run the k1 chain (windows 0..Wh-1) and the odd groups the k2 chain (windows Wh..2Wh-1)
@@ -571,8 +590,8 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   return TKM_OK;
 }
 
-// Window reduction of a filled bucket set into `parts` on the context stream, then the recombination kernel (one warp,
-// latency-bound: ~1-2 ms) on `final_stream`.  When that is a side stream the caller can already queue the next MSM: the
+// Window reduction of a filled bucket set into weighted `parts` and window sums on the context stream, then the
+// recombination kernel (one warp, latency-bound: < 1 ms) on `final_stream`.  When that is a side stream the caller can already queue the next MSM: the
 // serial tail overlaps the next accumulation instead of idling 147 SMs.
 static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets, G1Xyzz *parts, G1Xyzz *wsum, uint32_t *res_dev,
                              cudaStream_t final_stream, cudaEvent_t ready) {
@@ -596,15 +615,17 @@ static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *bucke
       TKM_TRY(sliced.alloc(ctx, (size_t)groups * splits));
       k_bucket_bits<<<groups * splits, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, splits, sliced.p);
       TKM_TRY(launch_check(ctx, "k_bucket_bits"));
-      k_sum_groups<<<groups, 32, 0, ctx->stream>>>(sliced.p, splits, parts);
+      k_sum_groups<<<groups, 32, 0, ctx->stream>>>(sliced.p, splits, m.nbits, m.logg, parts);
       TKM_TRY(launch_check(ctx, "k_sum_groups"));
     }
   }
+  k_window_sums<<<m.W, 32, 0, ctx->stream>>>(parts, m.nbits + 1, wsum);
+  TKM_TRY(launch_check(ctx, "k_window_sums"));
   if (final_stream != ctx->stream) {
     TKM_CUDA(cudaEventRecord(ready, ctx->stream));
     TKM_CUDA(cudaStreamWaitEvent(final_stream, ready, 0));
   }
-  k_final<<<1, 32, 0, final_stream>>>(parts, m, wsum, nullptr, res_dev);
+  k_final<<<1, 32, 0, final_stream>>>(wsum, m, nullptr, res_dev);
   return launch_check(ctx, "k_final");
 }
 
