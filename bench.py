@@ -325,16 +325,17 @@ def main():
                     acc_ms.append(ctx.kernel_time_last())
                 acc_ms = float(np.mean(acc_ms))
                 adds = n * W
-                # wide IMADs the kernel actually issues per mixed addition: 8 general products x 288 (144 a*b + 144 reduction)
-                # + 2 dedicated squarings x 222 (78 + 144); the nominal count of SURVEY 8d is 10 x 288 = 2880
-                wide_per_add = 8 * 288 + 2 * 222
+                # wide IMADs the kernel actually issues per mixed addition: 6 general products x 288 (144 a*b + 144 reduction)
+                # + 2 dedicated squarings x 222 (78 + 144) + the fused two-product Y3 (Fq::dot2: 288 + one reduction of 144);
+                # the nominal count of SURVEY 8d is 10 x 288 = 2880
+                wide_per_add = 6 * 288 + 2 * 222 + 432
                 ach = adds * wide_per_add / (acc_ms * 1e-3)
                 peak = max(imad_wide, imad_wide_x)
                 line["roofline"] = {"bound": "int32", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T(32x32+64 IMAD.WIDE)/s", "frac": ach / peak,
                                     "traffic": NCU_TRAFFIC["k_accumulate"], "traffic_unit": "GB per launch (dram read+write, ncu --set full capture in profiles/)",
                                     "algorithmic_gb": adds * 104 / 1e9, "kernel": "k_accumulate", "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_res,
                                     "note": "MSM is integer-pipe bound (SURVEY.md 8d; the schema's hbm/tensor bounds do not describe it): "
-                                            "N*W mixed additions x 2748 issued wide IMADs (8 products x 288 + 2 squarings x 222) per launch / k_accumulate's event-timed duration; "
+                                            "N*W mixed additions x 2604 issued wide IMADs (6 products x 288 + 2 squarings x 222 + one fused two-product Y3 x 432) per launch / k_accumulate's event-timed duration; "
                                             "peak = best measured IMAD.WIDE.U32 stream on this GPU (64-bit-addend or carry-chain form)",
                                     "whole_msm_frac": adds * wide_per_add / (ms_res * 1e-3) / peak,
                                     # the schema's HBM view of the same kernel, for completeness: 104 algorithmic bytes per addition

@@ -89,4 +89,9 @@ void h_g1_phi(const uint32_t *pt, uint32_t *o) {
   a.x = a.x * b.to_mont();
   sta(o, a);
 }
+// raw Montgomery a*b + c*d with one reduction: (ab + cd)/R mod q
+void h_fq_dot2(const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *o) {
+  Fq x, y, z, w; memcpy(x.v, a, 48); memcpy(y.v, b, 48); memcpy(z.v, c, 48); memcpy(w.v, d, 48);
+  Fq r = Fq::dot2(x, y, z, w); memcpy(o, r.v, 48);
+}
 }

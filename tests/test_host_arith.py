@@ -179,3 +179,18 @@ def test_binary_gcd_inverse(L, name):
         o = np.zeros(n, dtype=np.uint32)
         fn(7, pp(u32(a, n)), pp(u32(a, n)), pp(o))
         assert toint(o) == (pow(a, mod - 2, mod) if a else 0), (name, hex(a))
+
+
+def test_fq_dot2(L):
+    """Fq::dot2 = a*b + c*d under one interleaved Montgomery reduction (the Y3 of the point formulas), raw limbs."""
+    q, n = P.Q_MOD, 12
+    rng = random.Random(31)
+    rinv = pow(1 << 384, -1, q)
+    edge = [0, 1, q - 1, q - 2, (1 << 384) % q, (1 << 32) - 1, q >> 1, int("ffffffff" * 11, 16)]
+    quads = [(a, b, c, d) for a in edge for b in edge[:4] for c in edge[1:5] for d in edge[2:6]]
+    quads += [(q - 1, q - 1, q - 1, q - 1), (0, 0, 0, 0), (q - 1, q - 1, 0, 0), (0, 5, q - 1, q - 1)]
+    quads += [tuple(rng.randrange(q) for _ in range(4)) for _ in range(2000)]
+    for a, b, c, d in quads:
+        o = np.zeros(n, dtype=np.uint32)
+        L.h_fq_dot2(pp(u32(a, n)), pp(u32(b, n)), pp(u32(c, n)), pp(u32(d, n)), pp(o))
+        assert toint(o) == (a * b + c * d) * rinv % q, (hex(a), hex(b), hex(c), hex(d))

@@ -275,6 +275,63 @@ struct alignas(16) Fp {
     final_sub(r.v);
     return r;
   }
+  // (lo,hi)(acc[j-1],acc[j]) += c[j]*d for the odd limbs j = 1,3,..,N-1, one carry chain (no carry out by the T bound).
+  TKM_HD static void chain_mad_odd(uint32_t *acc, const uint32_t *c, uint32_t d) {
+    acc[0] = mad_lo_cc(c[1], d, acc[0]);
+    acc[1] = madc_hi_cc(c[1], d, acc[1]);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) {
+      acc[j - 1] = madc_lo_cc(c[j], d, acc[j - 1]);
+      acc[j] = madc_hi_cc(c[j], d, acc[j]);
+    }
+  }
+  // a*b + c*d with ONE interleaved reduction: 2 N^2 product IMADs + N^2 reduction IMADs instead of 4 N^2 for two
+  // Montgomery products (Fq: 432 instead of 576).  The point formulas end in Y3 = R*(Q - X3) - Y*PPP, which is this with
+  // c = -Y.  Row i adds a*b_i + c*d_i + m_i*p before the division by 2^32, so T < 3p + 3p*2^32 must stay below
+  // 2^(32(N+1)): true for Fq (2^414.6 < 2^416), false for Fr -- the same spare-bit condition as the dedicated squaring.
+  // The result (ab + cd + Mp)/R < p(2p/R + 1) < 2p, so one final subtraction is enough.
+  TKM_HD static Fp dot2(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
+    static_assert(P::DEDICATED_SQR, "dot2 needs the spare bits of the container (Fq only)");
+    uint32_t X[N], Y[N];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      X[j] = mul_lo(a.v[j], b.v[0]);
+      X[j + 1] = mul_hi(a.v[j], b.v[0]);
+      Y[j] = mul_lo(a.v[j + 1], b.v[0]);
+      Y[j + 1] = mul_hi(a.v[j + 1], b.v[0]);
+    }
+    chain_mad(X, c.v, d.v[0]);          // even limbs of c: columns (0,1),(2,3),..; carry out -> column N = Y[N-1]
+    Y[N - 1] = addc(Y[N - 1], 0);
+    chain_mad_odd(Y, c.v, d.v[0]);      // odd limbs of c: columns (1,2),(3,4),..
+    reduce_row(X, Y);
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      uint32_t *E = (i & 1) ? X : Y;
+      uint32_t *O = (i & 1) ? Y : X;
+      const uint32_t bi = b.v[i], di = d.v[i];
+      O[0] = add_cc(O[0], E[1]);
+#pragma unroll
+      for (int j = 1; j < N - 1; j += 2) {
+        E[j - 1] = madc_lo_cc(a.v[j], bi, E[j + 1]);
+        E[j] = madc_hi_cc(a.v[j], bi, E[j + 2]);
+      }
+      E[N - 2] = madc_lo_cc(a.v[N - 1], bi, 0);
+      E[N - 1] = madc_hi(a.v[N - 1], bi, 0);
+      chain_mad(O, a.v, bi);
+      E[N - 1] = addc(E[N - 1], 0);
+      chain_mad(O, c.v, di);
+      E[N - 1] = addc(E[N - 1], 0);
+      chain_mad_odd(E, c.v, di);
+      reduce_row(O, E);
+    }
+    Fp r;
+    r.v[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.v[k] = addc_cc(X[k], Y[k + 1]);
+    r.v[N - 1] = addc(X[N - 1], 0);
+    final_sub(r.v);
+    return r;
+  }
   // Dedicated Montgomery squaring: a^2 = sum_i a_i * c^(i) * 2^(32 i) with c^(i) = a_i 2^(32 i) + 2 * sum_{j>i} a_j 2^(32 j),
   // so row i needs only the N - i products with j >= i: N(N+1)/2 wide IMADs for the product instead of N^2 (Fq: 78 + 144
   // for the interleaved reduction = 222 instead of 288).  The doubled multiplicand is taken limb-wise: position i is a_i,

@@ -42,7 +42,7 @@ TKM_HD G1Xyzz g1_mdbl(const G1Affine &p) {
   Fq M = XX.dbl() + XX;
   G1Xyzz r;
   r.X = M.sqr() - S.dbl();
-  r.Y = M * (S - r.X) - W * p.y;
+  r.Y = Fq::dot2(M, S - r.X, W, p.y.neg());
   r.ZZ = V;
   r.ZZZ = W;
   return r;
@@ -59,7 +59,7 @@ TKM_HD G1Xyzz g1_dbl(const G1Xyzz &p) {
   Fq M = XX.dbl() + XX;
   G1Xyzz r;
   r.X = M.sqr() - S.dbl();
-  r.Y = M * (S - r.X) - W * p.Y;
+  r.Y = Fq::dot2(M, S - r.X, W, p.Y.neg());
   r.ZZ = V * p.ZZ;
   r.ZZZ = W * p.ZZZ;
   return r;
@@ -116,7 +116,7 @@ __device__ __forceinline__ G1Affine g1_to_affine_coop(const G1Xyzz &p) {
 }
 #endif
 
-// acc += (x, y)  (madd-2008-s), all exceptional cases handled.
+// acc += (x, y)  (madd-2008-s: 7 products + 2 squarings + one fused two-product Y3), all exceptional cases handled.
 TKM_HD void g1_madd(G1Xyzz &acc, const G1Affine &p) {
   if (p.is_identity()) return;
   if (acc.is_identity()) {
@@ -138,11 +138,10 @@ TKM_HD void g1_madd(G1Xyzz &acc, const G1Affine &p) {
   Fq PPP = Pd * PP;
   Fq Q = acc.X * PP;
   Fq X3 = Rd.sqr() - PPP - Q.dbl();
-  Fq Y3 = Rd * (Q - X3) - acc.Y * PPP;
-  acc.X = X3;
-  acc.Y = Y3;
   acc.ZZ = acc.ZZ * PP;
   acc.ZZZ = acc.ZZZ * PPP;
+  acc.Y = Fq::dot2(Rd, Q - X3, acc.Y.neg(), PPP);  // R*(Q - X3) - Y*PPP under one Montgomery reduction
+  acc.X = X3;
 }
 
 // acc += q  (add-2008-s), all exceptional cases handled.
@@ -169,7 +168,7 @@ TKM_HD void g1_add(G1Xyzz &acc, const G1Xyzz &q) {
   Fq PPP = Pd * PP;
   Fq Q = U1 * PP;
   Fq X3 = Rd.sqr() - PPP - Q.dbl();
-  Fq Y3 = Rd * (Q - X3) - S1 * PPP;
+  Fq Y3 = Fq::dot2(Rd, Q - X3, S1.neg(), PPP);
   acc.X = X3;
   acc.Y = Y3;
   acc.ZZ = acc.ZZ * q.ZZ * PP;

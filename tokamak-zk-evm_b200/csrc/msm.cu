@@ -151,7 +151,7 @@ __device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *src) {
 
 constexpr int ACC_THREADS = 128;
 
-__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(ACC_THREADS, 3) k_accumulate(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                            size_t M, uint32_t chunk, const G1Affine *__restrict__ bases,
                                                            uint32_t invalid_key, G1Xyzz *__restrict__ buckets,
                                                            uint32_t *__restrict__ pkeys, G1Xyzz *__restrict__ ppts,
