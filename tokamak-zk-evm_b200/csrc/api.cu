@@ -18,7 +18,7 @@ __global__ void k_g1_add_single(const G1Affine *a, const G1Affine *b, uint32_t *
   G1Xyzz acc = G1Xyzz::identity();
   g1_madd(acc, pa);
   g1_madd(acc, pb);
-  G1Affine r = g1_to_affine(acc);
+  G1Affine r = g1_to_affine_single(acc);
   Fq x = r.x.from_mont(), y = r.y.from_mont();
   for (int i = 0; i < 12; i++) { out_canonical[i] = x.v[i]; out_canonical[12 + i] = y.v[i]; }
 }
@@ -540,6 +540,10 @@ int32_t tkm_g1_sum(tkm_ctx *ctx, const uint8_t *points96, size_t n, uint8_t out9
 int32_t tkm_g1_mul(tkm_ctx *ctx, const uint8_t a96[96], const uint8_t k32[32], uint8_t out96[96]) {
   API_BEGIN
   TKM_REQUIRE(a96 && k32 && out96, "null argument");
+  // A base whose window table is already on the context (setup multiplies one generator many times) uses it; any other
+  // base is a one-point MSM (GLV halves, ~1.5 ms) -- building a 64 x 16 table for one product would be a serial 20 ms job,
+  // and would evict the generator's table.  (G1serde * ScalarField, group_structures/mod.rs:929-947.)
+  if (!ctx->fb_valid || memcmp(ctx->fb_base, a96, 96) != 0) return tkm_msm_g1_host(ctx, k32, a96, 1, out96);
   Scratch<Fr> s;
   Scratch<G1Affine> r;
   TKM_TRY(s.alloc(ctx, 1));

@@ -184,6 +184,17 @@ TKM_HD G1Affine g1_to_affine(const G1Xyzz &p) {
   return G1Affine{p.X * zz_inv, p.Y * zzz_inv};
 }
 
+// The same conversion for a single value (one thread, or replicas): the inverse is one latency-bound chain, so the binary
+// extended Euclid (Fp::inv_bgcd) beats the Fermat chain by several times.  Not for lanes holding different values (the trip
+// counts depend on the value).
+TKM_HD G1Affine g1_to_affine_single(const G1Xyzz &p) {
+  if (p.is_identity()) return G1Affine::identity();
+  Fq t = (p.ZZ * p.ZZZ).inv_bgcd();
+  Fq zz_inv = t * p.ZZZ;
+  Fq zzz_inv = t * p.ZZ;
+  return G1Affine{p.X * zz_inv, p.Y * zzz_inv};
+}
+
 // k * P by left-to-right double-and-add, k canonical (non-Montgomery) little-endian limbs.
 // Used for the handful of single scalar multiplications of the prover
 // (G1serde * ScalarField, group_structures/mod.rs:929-947).

@@ -62,6 +62,10 @@ static MsmGeom pick_geom(size_t n, uint32_t fixed_c = 0, uint32_t table_stride =
     }
   }
   if (fixed_c) bc = fixed_c;
+  else if (const char *e = getenv("TKM_MSM_C")) {  // developer knob: force the window width (scripts/msm_c_sweep.py)
+    const uint32_t v = (uint32_t)atoi(e);
+    if (v >= 4 && v <= 20) bc = v;
+  }
   MsmGeom m;
   m.c = bc;
   m.glv = use_glv ? 1 : 0;
