@@ -253,6 +253,42 @@ def test_msm_empty_and_degenerate(ctx):
     assert np.array_equal(ctx.msm_g1_host(mix, pts), O.msm_g1(mix, pts))
 
 
+LAMBDA_GLV = 0xAC45A4010001A40200000000FFFFFFFF  # phi(P) = lambda*P on G1; r = lambda^2 + lambda + 1 (csrc/glv.cuh)
+
+
+def test_msm_glv_edge_scalars(ctx):
+    """The GLV split inside k_decompose (k = k1 + k2*lambda, signed halves below 2^127) on the scalars that sit on its
+    branch boundaries: halves that are zero, negative, maximal, multiples of lambda, and values at or above r (folded).
+    One chain of the Horner tail being empty (all k2 = 0 / all k1 = 0) is a separate case."""
+    G = g1s([P.G1_GEN])[0]
+    lam, r = LAMBDA_GLV, P.R_MOD
+    h1 = (lam + 1) // 2
+    edge = [0, 1, 2, r - 1, r - 2, lam - 1, lam, lam + 1, lam // 2, lam // 2 + 1, h1 * lam, (h1 + 1) * lam, (h1 + 1) * lam - 1,
+            (lam + 1) * lam, r // 2, r // 2 + 1, (1 << 127) - 1, 1 << 127, (1 << 128) - 1, 1 << 128, (1 << 255) % r, (1 << 64) - 1]
+    edge += [q * lam + d for q in (1, h1 - 1, h1, h1 + 1, lam) for d in (0, 1, lam // 2, lam // 2 + 1, lam - 1)]
+    edge = [e % r for e in edge]
+    n = len(edge)
+    ks = O.random_fr(81, n)
+    pts = O.g1_fixed_base_mul_batch(G, ks)
+    ki = to_ints(ks)
+    assert g1_tuple(ctx.msm_g1_host(frs(edge), pts)) == P.g1_mul(P.G1_GEN, sum(a * b for a, b in zip(edge, ki)) % r)
+    # every scalar separately against the scalar multiplication (one-point MSMs)
+    for e, pt, k in list(zip(edge, pts, ki))[:24]:
+        assert g1_tuple(ctx.msm_g1_host(frs([e]), pt[None, :])) == P.g1_mul(P.G1_GEN, e * k % r), hex(e)
+    # only the k1 chain is populated (scalars below 2^100), then only the k2 chain (multiples of lambda)
+    import random
+    rng = random.Random(82)
+    small = [rng.randrange(1 << 100) for _ in range(n)]
+    assert g1_tuple(ctx.msm_g1_host(frs(small), pts)) == P.g1_mul(P.G1_GEN, sum(a * b for a, b in zip(small, ki)) % r)
+    mult = [rng.randrange(1 << 100) * lam % r for _ in range(n)]
+    assert g1_tuple(ctx.msm_g1_host(frs(mult), pts)) == P.g1_mul(P.G1_GEN, sum(a * b for a, b in zip(mult, ki)) % r)
+    # non-canonical limbs (>= r) are folded into [0, r): same group element
+    big = [r, r + 1, 2 * r + 5, (1 << 256) - 1]
+    raw = np.array([[(v >> (64 * i)) & ((1 << 64) - 1) for i in range(4)] for v in big], dtype=np.uint64)
+    exp = P.g1_mul(P.G1_GEN, sum((a % r) * b for a, b in zip(big, ki)) % r)
+    assert g1_tuple(ctx.msm_g1_host(raw, pts[:4])) == exp
+
+
 @pytest.mark.parametrize("n,pieces", [(1, 4), (5, 4), (1000, 3), (4097, 4), (6000, 16)])
 def test_msm_host_pipelined_pieces(ctx, n, pieces, monkeypatch):
     """tkm_msm_g1_host cut into point ranges (copy/compute pipeline): every piece adds into the same bucket set, so the
