@@ -649,7 +649,12 @@ static int32_t msm_reduce(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets,
 // ---- asynchronous MSMs: tickets own the small buffers the side-stream tail reads
 constexpr size_t TICKET_PARTS = 2048;  // >= W * (nbits + 1) for every geometry (W <= 64, nbits <= 21)
 static int32_t ticket_acquire(tkm_ctx *ctx, int32_t *out) {
-  if (!ctx->side_stream) TKM_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  if (!ctx->side_stream) {
+    // highest priority: the one-warp tail should get an SM slot as soon as a CTA of the next accumulation retires
+    int lo = 0, hi = 0;
+    TKM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TKM_CUDA(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+  }
   for (int t = 0; t < TKM_MAX_TICKETS; t++) {
     tkm_ctx::Ticket &k = ctx->tickets[t];
     if (k.busy) continue;
