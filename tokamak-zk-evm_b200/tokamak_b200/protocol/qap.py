@@ -158,7 +158,12 @@ def permutation_evals(permutation, m_i, s_max, omega_m_i, omega_s_max):
     yl = np.array([limbs(v) for v in yp], dtype=np.uint64)
     s0 = np.repeat(xl, s_max, axis=0)
     s1 = np.tile(yl, (m_i, 1))
-    for p in permutation:
-        s0[p.row * s_max + p.col] = xl[p.X]
-        s1[p.row * s_max + p.col] = yl[p.Y]
+    if len(permutation):
+        e = np.array([(p.row, p.col, p.X, p.Y) for p in permutation], dtype=np.int64)
+        idx = e[:, 0] * s_max + e[:, 1]
+        # a later entry for the same (row, col) overrides an earlier one, like the reference's sequential loop
+        _, last = np.unique(idx[::-1], return_index=True)
+        keep = len(idx) - 1 - last
+        s0[idx[keep]] = xl[e[keep, 2]]
+        s1[idx[keep]] = yl[e[keep, 3]]
     return s0, s1
