@@ -1,5 +1,5 @@
-"""Developer probe: MSM time against the bucket-segment length (TKM_MSM_LOGG) and the accumulation chunk target
-(TKM_MSM_CHUNK) at the prover's commitment sizes.  The knobs are read at every call."""
+"""Developer probe: MSM time against the bucket-segment length (TKM_MSM_LOGG), the accumulation chunk target
+(TKM_MSM_CHUNK) and the slices per (window, bit) of the window reduction (TKM_MSM_SPLITS) at the prover's commitment sizes.  The knobs are read at every call."""
 import ctypes
 import json
 import os
@@ -14,6 +14,7 @@ import oracle_ffi as O  # noqa: E402  (input generation only)
 import pyref as P  # noqa: E402
 import tokamak_b200 as T  # noqa: E402
 
+KNOBS = ("TKM_MSM_LOGG", "TKM_MSM_CHUNK", "TKM_MSM_SPLITS")
 ctx = T.Context(0)
 G = np.frombuffer(P.g1_to_bytes(P.G1_GEN), dtype=np.uint64).copy()
 out = {}
@@ -25,13 +26,13 @@ for logn in (18, 20, 22):
     T.check(ctx.lib.tkm_g1_fixed_base_mul(ctx.h, G.ctypes.data, ctypes.c_void_p(dk), 0, n, ctypes.c_void_p(dp)))
     T.check(ctx.lib.tkm_g1_bases_to_mont(ctx.h, ctypes.c_void_p(dp), ctypes.c_void_p(dp), n))
     ds = ctx.upload_fr(ss, to_mont=False)
-    for k in ("TKM_MSM_LOGG", "TKM_MSM_CHUNK"):
+    for k in KNOBS:
         os.environ.pop(k, None)
     ref = ctx.msm_g1_dev(ds, False, dp, n)
     row = {}
-    for knob, vals in (("TKM_MSM_LOGG", (None, 2, 3, 4, 5, 6)), ("TKM_MSM_CHUNK", (None, 96, 128, 192, 256, 320, 384, 512))):
+    for knob, vals in (("TKM_MSM_LOGG", (None, 3, 4, 5)), ("TKM_MSM_CHUNK", (None, 192, 256, 384)), ("TKM_MSM_SPLITS", (None, 1, 2, 4, 8))):
         for v in vals:
-            for k in ("TKM_MSM_LOGG", "TKM_MSM_CHUNK"):
+            for k in KNOBS:
                 os.environ.pop(k, None)
             if v is not None:
                 os.environ[knob] = str(v)

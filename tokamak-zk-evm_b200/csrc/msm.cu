@@ -606,11 +606,21 @@ static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *bucke
   k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets, m, seg_acc.p, seg_run.p);
   TKM_TRY(launch_check(ctx, "k_bucket_seg"));
   {
-    // slices per (window, bit): keep every thread at <= ~4 segment sums, at most 64 slices
-    uint32_t splits = (m.nseg + BITS_THREADS * 4 - 1) / (BITS_THREADS * 4);
+    // Slices per (window, bit).  The blocks are latency-bound tree-sums, so what matters is that the launch is ONE wave:
+    // as many slices as fit the resident block slots (2^22 points: 192 groups -> 1 slice, no second stage; fixed-base
+    // tables: 16 groups -> 18 slices), never more than one slice per BITS_THREADS segments.
+    const uint32_t groups = m.W * (m.nbits + 1);
+    static int bits_occ = 0;
+    if (!bits_occ) {
+      TKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bits_occ, k_bucket_bits, BITS_THREADS, 0));
+      if (bits_occ < 1) bits_occ = 1;
+    }
+    uint32_t splits = (uint32_t)(ctx->sm_count * bits_occ) / groups;
+    const uint32_t max_useful = (m.nseg + BITS_THREADS - 1) / BITS_THREADS;
+    if (splits > max_useful) splits = max_useful;
+    if (const char *e = getenv("TKM_MSM_SPLITS")) splits = (uint32_t)atoi(e);  // developer knob
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
-    const uint32_t groups = m.W * (m.nbits + 1);
     if (splits == 1) {
       k_bucket_bits<<<groups, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, 1, parts);
       TKM_TRY(launch_check(ctx, "k_bucket_bits"));
