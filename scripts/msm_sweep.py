@@ -17,7 +17,7 @@ import tokamak_b200 as T  # noqa: E402
 ctx = T.Context(0)
 G = np.frombuffer(P.g1_to_bytes(P.G1_GEN), dtype=np.uint64).copy()
 rows = []
-for logn in range(16, 25):
+for logn in ([int(v) for v in os.environ["TKM_SWEEP_LOGN"].split(",")] if os.environ.get("TKM_SWEEP_LOGN") else range(16, 25)):
     n = 1 << logn
     ks, ss = O.random_fr(1000 + logn, n), O.random_fr(2000 + logn, n)
     dk = ctx.upload_fr(ks, to_mont=False)

@@ -154,8 +154,13 @@ __device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *src) {
 }
 
 constexpr int ACC_THREADS = 128;
+// Resident CTAs per SM the accumulation kernel is compiled for (register cap 168 at 3).  Overridable for the occupancy
+// probe of scripts/ubench (a mixed-addition stream alone is 3 % faster at 2 CTAs/SM with 206 registers).
+#ifndef TKM_ACC_MIN_BLOCKS
+#define TKM_ACC_MIN_BLOCKS 3
+#endif
 
-__global__ void __launch_bounds__(ACC_THREADS, 3) k_accumulate(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(ACC_THREADS, TKM_ACC_MIN_BLOCKS) k_accumulate(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                            size_t M, uint32_t chunk, const G1Affine *__restrict__ bases,
                                                            uint32_t invalid_key, G1Xyzz *__restrict__ buckets,
                                                            uint32_t *__restrict__ pkeys, G1Xyzz *__restrict__ ppts,
