@@ -27,6 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
 LOG_N = 22
 NTT_X, NTT_Y = 16384, 512
 NTT_BUTTERFLIES = NTT_X * NTT_Y * ((14 - 2) / 2 + (9 - 2) / 2 + 0.5)  # 83.9 M products per transform
+FR_MUL_WIDE_IMADS = 112  # Fr Montgomery product: 64 a*b + 48 reduction wide IMADs (r's two low limbs need no multiplier)
+WIDE_PER_MADD = 6 * 288 + 2 * 222 + 432  # XYZZ mixed addition: 6 products + 2 dedicated squarings + the fused two-product Y3
 METRIC = "BLS12-381 G1 MSM throughput at 2^22 points"
 UNIT = "Mpts/s"
 G1_GEN = (
@@ -35,9 +37,28 @@ G1_GEN = (
 )
 
 
+def bench_config(log_n, world):
+    """The workload description both arms print (the reference arm must describe the same job as ours)."""
+    return {"workload": f"G1 MSM 2^{log_n} points per GPU, uniform random scalars (seed 2000+rank), distinct bases k_i*G (k_i uniform, seed 1000+rank)",
+            "log2_points_per_gpu": log_n, "parallelism": f"point-range shards x{world}, partial sums all-gathered and combined on rank 0" if world > 1 else "single GPU",
+            "l2": "inputs (0.5 GiB) larger than the 126 MB L2"}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ncu_k_accumulate_summary.csv: 2^22-point MSM; profiles/r01_ncu_k_ntt_pass_summary.csv: 16384 x 512 forward)
 NCU_TRAFFIC = {"k_accumulate": 11.913, "k_ntt_pass_x3": 1.464}
+
+
+def msm_windows(n):
+    """Digit windows per scalar the library picks for an n-point MSM (pick_geom in csrc/msm.cu: GLV halves of 128 bits,
+    c minimising W*(n + 3*2^(c-1))): (c, W)."""
+    best, bc = None, 8
+    for c in range(4, 21):
+        W = 2 * ((128 + c - 1) // c)
+        cost = W * (n + 3.0 * (1 << (c - 1)))
+        if best is None or cost < best:
+            best, bc = cost, c
+    return bc, 2 * ((128 + bc - 1) // bc)
 
 
 def measured_peaks():
@@ -128,42 +149,52 @@ def run_reference(args, rank, world):
 
     O.build()
     O.set_num_threads(len(os.sched_getaffinity(0)))  # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
-    log_sample = 18  # bounded sample of the 2^22 workload: ~1-2 s per step on 8 threads
-    n = 1 << log_sample
+    # the SAME workload as rank 0 of our arm: 2^log_n points, the same seeds (bases k_i*G from seed 1000, scalars from seed 2000)
+    n = 1 << args.log_n
     G = np.frombuffer(G1_GEN[0].to_bytes(48, "little") + G1_GEN[1].to_bytes(48, "little"), dtype=np.uint64).copy()
-    bases = O.g1_fixed_base_mul_batch(G, O.random_fr(101, n))
-    scalars = O.random_fr(102, n)
+    t_gen = time.perf_counter()
+    ks = random_scalars(1000, n)
+    bases = O.g1_fixed_base_mul_batch(G, ks)  # untimed input generation (our arm does this on the GPU)
+    scalars = random_scalars(2000, n)
+    t_gen = time.perf_counter() - t_gen
     for _ in range(max(1, min(args.warmup, 1))):
-        O.msm_g1(scalars, bases)
+        res = O.msm_g1(scalars, bases)
+    assert np.array_equal(res, O.g1_mul(G, O.fr_inner_product(scalars, ks))), "CPU MSM differs from (sum s_i k_i)*G"
     t0 = time.perf_counter()
     for _ in range(args.steps):
         O.msm_g1(scalars, bases)
-    dt = (time.perf_counter() - t0) / args.steps
+    t_msm = time.perf_counter() - t0
+    dt = t_msm / args.steps
     val = n / dt / 1e6
     cores = O.num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Fq 381-bit)",
-        "data": "synthetic", "config": {"workload": "G1 MSM, random scalars, random affine bases", "log2_points": LOG_N, "l2": "inputs larger than L2"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"2^{log_sample}-point MSM per step (bounded sample of the 2^{LOG_N} workload), oracle/oracle.c Pippenger, OpenMP"},
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Fr 255-bit scalars, Fq 381-bit coordinates)",
+        "data": "synthetic", "config": bench_config(args.log_n, max(1, args.gpus)),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "nproc": os.cpu_count(), "kind": "port",
+                         "sample": f"the whole 2^{args.log_n}-point MSM of rank 0 per step (same seeds as the GPU arm; no reduction), oracle/oracle.c Pippenger, OpenMP; "
+                                   f"input generation {t_gen:.1f} s untimed; result checked against (sum s_i k_i)*G"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "published_reference_cpu": {"value": 1.01, "unit": UNIT, "note": "ICICLE CPU backend, 8192x511 pts, unnamed macOS host (BASELINE.md)"},
     }
-    if not args.skip_prove:
-        # "prove s/tx" on the CPU path: the protocol driver on the oracle backend, bounded sample (every extent of the
-        # reference shape / 4 = 1/16 of the MSM and NTT work); CRS generated on the CPU first (not timed)
+    if not args.skip_prove and args.gpus == 1:
+        # "prove s/tx" on the CPU path: the protocol driver on the oracle backend at the FULL reference shape (n=4096, s_max=256,
+        # m_I=4096; about 35 s on 16 cores), CRS generated on the CPU first (not timed).  If the MSM steps above already used the
+        # time budget of this arm (slow / few host cores) the shape with every extent / 4 is proved instead, and labelled so.
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
         import prove_full
         from oracle_backend import OracleBackend
+        from tokamak_b200.protocol import synthetic as S
 
-        cpu = prove_full.run(OracleBackend(), prove_full.reduced_shape(), repeats=1, verify=False)
-        line["prove_sample"] = {"metric": "prove s/tx", "value": cpu["prove_s"], "unit": "s", "higher_is_better": False, "cores": cores, "kind": "port",
-                                "sample": "reference shape with every extent / 4 (n=1024, s_max=64, m_I=1024)", "setup_s_not_timed": cpu["setup_s"],
-                                "stage_s": {k: cpu["median_run"][k] for k in ("init_s", "prove0_s", "prove1_s", "prove2_s", "prove3_s", "prove4_s", "encode_s")},
-                                "proof_sha256": cpu["proof_sha256"],
-                                "published_reference_cpu": {"value": 45.7, "unit": "s", "note": "full shape, real template tx, ICICLE CPU backend (BASELINE.md)"}}
+        full = (t_gen + t_msm) < 240.0 and not args.reference_prove_reduced
+        cpu = prove_full.run(OracleBackend(), S.reference_shape() if full else prove_full.reduced_shape(), repeats=1, verify=False, from_files=False)
+        line["prove"] = {"metric": "prove s/tx", "value": cpu["prove_s"], "unit": "s", "higher_is_better": False, "cores": cores, "kind": "port",
+                         "sample": "the full reference shape (n=4096, s_max=256, m_I=4096, l=728): same synthetic circuit, CRS and fixed blinding as the GPU arm's `prove`" if full
+                         else "reference shape with every extent / 4 (n=1024, s_max=64, m_I=1024)", "full_shape": full, "setup_s_not_timed": cpu["setup_s"],
+                         "stage_s": {k: cpu["median_run"][k] for k in ("init_s", "prove0_s", "prove1_s", "prove2_s", "prove3_s", "prove4_s", "encode_s")},
+                         "proof_sha256": cpu["proof_sha256"],
+                         "published_reference_cpu": {"value": 45.7, "unit": "s", "note": "full shape, real template tx, ICICLE CPU backend (BASELINE.md)"}}
     print(json.dumps(line), flush=True)
 
 
@@ -176,7 +207,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="developer override of the MSM size (the graded config is 22)")
     ap.add_argument("--skip-aux", action="store_true", help="skip the biNTT / cpu-baseline / e2e legs (profiling runs)")
+    ap.add_argument("--skip-strong", action="store_true", help="skip the 2^24 strong-scaling MSM leg")
     ap.add_argument("--skip-prove", action="store_true", help="skip the full-prove leg (setup + prove0..4 + verify at the reference shape)")
+    ap.add_argument("--reference-prove-reduced", action="store_true", help="reference arm: prove the shape / 4 instead of the full reference shape")
     ap.add_argument("--no-cpu-prove-full", dest="cpu_prove_full", action="store_false",
                     help="skip the CPU oracle's FULL reference-shape prove (about 35 s on 16 cores); the shape / 4 sample always runs")
     args = ap.parse_args()
@@ -287,13 +320,41 @@ def main():
     assert np.array_equal(r0, r1), "MSM result is not deterministic"
     value = world * n / ms_res / 1e3  # Mpts/s, whole job
 
+    # ---- the timed result against its expected value at every N: the bases are k_i*G with known k_i, so the combined MSM
+    # must equal (sum over ranks of sum_i s_i k_i) * G.  Checker only (CPU oracle: one inner product per rank, one scalar
+    # multiplication on rank 0), after the timed region.
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_ffi as O
+
+    O.build()
+    O.set_num_threads(max(1, len(os.sched_getaffinity(0)) // max(1, world)))
+    R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+    def expected_from_dlogs(sc, kk):
+        """(sum_i sc_i kk_i over all ranks) * G on rank 0 (None elsewhere)."""
+        ip = O.fr_inner_product(sc, kk)
+        if world > 1:
+            t = torch.from_numpy(ip.view(np.int64).copy()).cuda()
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t)
+            ips = [o.cpu().numpy().view(np.uint64) for o in outs]
+        else:
+            ips = [ip]
+        if rank != 0:
+            return None
+        tot = sum(int.from_bytes(v.tobytes(), "little") for v in ips) % R_MOD
+        return O.g1_mul(G, np.frombuffer(tot.to_bytes(32, "little"), dtype=np.uint64).copy())
+
+    exp_main = expected_from_dlogs(scalars, ks)
+    if rank == 0:
+        assert np.array_equal(r1, exp_main), f"timed 2^{args.log_n} x {world} MSM differs from (sum s_i k_i)*G"
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_res,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Fr 255-bit scalars, Fq 381-bit coordinates)",
         "data": "synthetic",
-        "config": {"workload": f"G1 MSM 2^{args.log_n} points per GPU, uniform random scalars, distinct bases k_i*G (device-resident, Montgomery form)",
-                   "log2_points_per_gpu": args.log_n, "parallelism": f"point-range shards x{world}, partial sums all-gathered and combined on rank 0" if world > 1 else "single GPU",
-                   "l2": "inputs (0.5 GiB) larger than the 126 MB L2"},
+        "config": bench_config(args.log_n, world),
+        "checks": {"msm_timed_result": f"combined result of the timed steps == (sum over {world} rank(s) of sum_i s_i k_i)*G (known discrete logs; CPU oracle as checker, outside the timed region)"},
         "clocks": clocks, "gpu_launches": int(launches),
         "ms_per_step_host_clock": {"min": min(timed.last_per_step), "max": max(timed.last_per_step), "all": [round(x, 3) for x in timed.last_per_step]},
     }
@@ -313,7 +374,7 @@ def main():
             imad_wide_x = ctx.microbench(5)
             fq_mul = ctx.microbench(3)
             madd = ctx.microbench(4)
-            W = 16 if args.log_n == 22 else None
+            W = msm_windows(n)[1]
             bfly = ctx.microbench(6)
             line["microbench"] = {"imad_wide_u32_per_s": imad_wide, "imad_wide_x_u32_per_s": imad_wide_x, "imad_u32_per_s": ctx.microbench(0),
                                   "fr_mul_per_s": ctx.microbench(2), "fq_mul_per_s": fq_mul, "xyzz_madd_per_s": madd, "fr_butterfly_per_s": bfly}
@@ -328,7 +389,7 @@ def main():
                 # wide IMADs the kernel actually issues per mixed addition: 6 general products x 288 (144 a*b + 144 reduction)
                 # + 2 dedicated squarings x 222 (78 + 144) + the fused two-product Y3 (Fq::dot2: 288 + one reduction of 144);
                 # the nominal count of SURVEY 8d is 10 x 288 = 2880
-                wide_per_add = 6 * 288 + 2 * 222 + 432
+                wide_per_add = WIDE_PER_MADD
                 ach = adds * wide_per_add / (acc_ms * 1e-3)
                 peak = max(imad_wide, imad_wide_x)
                 line["roofline"] = {"bound": "int32", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T(32x32+64 IMAD.WIDE)/s", "frac": ach / peak,
@@ -366,11 +427,14 @@ def main():
                                  "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_element": 128,
                                  "kernel": "k_ntt_pass x3", "kernel_ms": kms},
                     # the bound that actually binds: 256-bit modular butterflies on the INT32 pipes
-                    "roofline_int32": {"bound": "int32", "unit": "G butterflies/s", "achieved": NTT_BUTTERFLIES / (kms * 1e-3) / 1e9, "peak": bfly / 1e9,
-                                       "frac": NTT_BUTTERFLIES / (kms * 1e-3) / bfly,
+                    "roofline_int32": {"bound": "int32", "unit": "T(32x32+64 IMAD.WIDE)/s", "achieved": NTT_BUTTERFLIES * FR_MUL_WIDE_IMADS / (kms * 1e-3) / 1e12,
+                                       "peak": max(imad_wide, imad_wide_x) / 1e12,
+                                       "frac": NTT_BUTTERFLIES * FR_MUL_WIDE_IMADS / (kms * 1e-3) / max(imad_wide, imad_wide_x),
+                                       "butterfly_stream": {"achieved_g_per_s": NTT_BUTTERFLIES / (kms * 1e-3) / 1e9, "measured_stream_g_per_s": bfly / 1e9},
                                        "note": "product-carrying butterflies of a 16384x512 transform: N*((log2 x - 2)/2 + (log2 y - 2)/2 + 1/2) = 83.9 M "
-                                               "(the radix-4 tail of each axis needs one product per four elements); peak = measured Fr "
-                                               "product+add+sub stream on this GPU"}}
+                                               "(the radix-4 tail of each axis needs one product per four elements) x 112 wide IMADs per Fr product "
+                                               "(64 a*b + 48 reduction; ff.cuh) / the k_ntt_pass launches' event-timed duration; peak = the same measured "
+                                               "IMAD.WIDE.U32 issue peak the MSM roofline uses"}}
             # e2e biNTT through the host-buffer entry point (pinned buffers)
             h_poly = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)
             h_out = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)
@@ -410,6 +474,47 @@ def main():
                                     "sample": f"first 2^{ls} points of the same inputs, oracle/oracle.c Pippenger (OpenMP); result compared bit-exactly with the GPU",
                                     "bintt": {"value": x2 * y2 / dt_ntt / 1e9, "unit": "Gelem/s", "sample": "4096x256 forward biNTT, oracle/oracle.c radix-2 (OpenMP)"},
                                     "published_reference": "ICICLE CPU backend: 1.01 Mpts/s at 8192x511 pts; biNTT 2^23 forward 497 ms (unnamed macOS host, BASELINE.md)"}
+
+    if not args.skip_aux and not args.skip_strong:
+        # ---- strong scaling (north star): ONE 2^24-point MSM cut into point ranges over the N ranks (2^24 / N points each),
+        # partial sums combined on rank 0; result checked against the known discrete logs; k_accumulate's roofline per N
+        LOG_S = 24
+        ns = (1 << LOG_S) // world
+        ks2, sc2 = random_scalars(5000 + rank, ns), random_scalars(6000 + rank, ns)
+        d_k2 = ctx.upload_fr(ks2, to_mont=False)
+        d_b2 = ctx.dev_alloc(ns * 96)
+        T.check(lib.tkm_g1_fixed_base_mul(h, G.ctypes.data, d_k2, 0, ns, d_b2))
+        T.check(lib.tkm_g1_bases_to_mont(h, d_b2, d_b2, ns))
+        ctx.dev_free(d_k2)
+        d_s2 = ctx.upload_fr(sc2, to_mont=False)
+
+        def step_strong():
+            return combine(ctx.msm_g1_dev(d_s2, False, d_b2, ns))
+
+        for _ in range(3):
+            step_strong()
+        ms_strong, _, clocks_s, rs = timed(step_strong, max(3, min(args.steps, 10)))
+        acc_s = ctx.kernel_time_last()
+        if world > 1:
+            tt = torch.tensor([acc_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            acc_s = float(tt.item())
+        exp_s = expected_from_dlogs(sc2, ks2)
+        for p_ in (d_b2, d_s2):
+            ctx.dev_free(p_)
+        if rank == 0:
+            assert np.array_equal(rs, exp_s), f"2^{LOG_S} MSM over {world} rank(s) differs from (sum s_i k_i)*G"
+            c_s, W_s = msm_windows(ns)
+            peak_s = line.get("roofline", {}).get("peak")
+            work = ns * W_s * WIDE_PER_MADD
+            line["msm_2p24_strong"] = {
+                "metric": "one 2^24-point G1 MSM, point ranges over N GPUs", "log2_points_total": LOG_S, "ranks": world, "points_per_rank": ns,
+                "ms": ms_strong, "value": (1 << LOG_S) / ms_strong / 1e3, "unit": UNIT, "scaling": "strong", "window_bits": c_s, "windows": W_s,
+                "checked": "combined result == (sum s_i k_i)*G over all ranks (known discrete logs)",
+                "roofline": {"bound": "int32", "kernel": "k_accumulate", "kernel_ms_max_over_ranks": acc_s, "achieved": work / (acc_s * 1e-3) / 1e12,
+                             "peak": peak_s, "unit": "T(32x32+64 IMAD.WIDE)/s per GPU", "frac": (work / (acc_s * 1e-3) / 1e12 / peak_s) if peak_s else None,
+                             "whole_msm_frac": (work / (ms_strong * 1e-3) / 1e12 / peak_s) if peak_s else None},
+                "clocks": clocks_s}
     if rank == 0 and world == 1 and not args.skip_aux and not args.skip_prove:
         # ---- "prove s/tx" (first part of BASELINE.json's metric): full Prover.init + prove0..prove4 on this GPU at the
         # reference's circuit shape, proof checked by the restated verifier; then the CPU baseline beside it on a bounded
@@ -465,6 +570,14 @@ def main():
         nn = NTT_X * NTT_Y
         lo, hi = D.shard_range(NTT_X, world, rank)
         src = torch.from_numpy(random_scalars(4000 + rank, (hi - lo) * NTT_Y).view(np.int64)).cuda().view(hi - lo, NTT_Y, 4)
+        # expected evaluations of this rank's column shard from the CPU oracle (checker, outside the timed regions).  The device
+        # buffers hold the raw limbs as Montgomery representations; the transform is linear, so the oracle applied to the
+        # same raw values (all < r) gives the same raw output.
+        O.set_num_threads(max(1, len(os.sched_getaffinity(0)) // world))
+        full_in = np.concatenate([random_scalars(4000 + r_, (D.shard_range(NTT_X, world, r_)[1] - D.shard_range(NTT_X, world, r_)[0]) * NTT_Y) for r_ in range(world)])
+        yb = NTT_Y // world
+        exp_cols = torch.from_numpy(np.ascontiguousarray(O.bintt(full_in, NTT_X, NTT_Y, False).reshape(NTT_X, NTT_Y, 4)[:, rank * yb:(rank + 1) * yb]).view(np.int64))
+        del full_in
         res = {}
         for key in ("forward", "roundtrip"):
             def one(buf):
@@ -487,6 +600,8 @@ def main():
             res[key] = float(tt.item())
             if key == "roundtrip":
                 assert torch.equal(out.view(-1), src.view(-1)), "sharded biNTT round trip is not the identity"
+            else:
+                assert torch.equal(out.reshape(NTT_X, yb, 4).cpu(), exp_cols), "sharded biNTT (NCCL all-to-all) differs from the CPU oracle on this rank's column shard"
             del bufs
         # the same transform with the exchange fused into the last NTT pass (P2P stores over NVLink, no NCCL on the data path)
         fused = None
@@ -514,6 +629,8 @@ def main():
                     fres[key] = float(tt.item())
                     if key == "roundtrip":
                         assert torch.equal(out.reshape(-1), src.reshape(-1)), "fused sharded biNTT round trip is not the identity"
+                    else:
+                        assert torch.equal(out.reshape(NTT_X, yb, 4).cpu(), exp_cols), "fused sharded biNTT differs from the CPU oracle on this rank's column shard"
                 fused = {"forward_ms": fres["forward"], "forward_gelem_s": nn / fres["forward"] / 1e6, "roundtrip_ms": fres["roundtrip"],
                          "exchange": "fused into the last k_ntt_pass: 128-bit P2P stores into peer-mapped symmetric memory + 2 stream-ordered barriers",
                          "p2p_bytes_per_rank": (world - 1) * (nn // world // world) * 32}
@@ -524,7 +641,13 @@ def main():
         if rank == 0:
             line["bintt_sharded"] = {"shape": [NTT_X, NTT_Y], "ranks": world, "forward_ms": res["forward"], "forward_gelem_s": nn / res["forward"] / 1e6,
                                      "roundtrip_ms": res["roundtrip"], "scaling": "strong", "exchange": "all_to_all_single (NCCL), one per direction",
-                                     "alltoall_bytes_per_rank": (world - 1) * (nn // world // world) * 32, "fused_exchange": fused}
+                                     "alltoall_bytes_per_rank": (world - 1) * (nn // world // world) * 32, "fused_exchange": fused,
+                                     "checked": "every rank's column shard of the forward result (NCCL and fused) == CPU oracle biNTT of the gathered input; round trips == input",
+                                     "roofline": {"bound": "hbm", "unit": "GB/s per GPU", "peak": measured_peaks()[0],
+                                                  "achieved_nccl": 128.0 * nn / world / (res["forward"] * 1e-3) / 1e9,
+                                                  "frac_nccl": 128.0 * nn / world / (res["forward"] * 1e-3) / 1e9 / measured_peaks()[0],
+                                                  "achieved_fused": (128.0 * nn / world / (fused["forward_ms"] * 1e-3) / 1e9) if fused and "forward_ms" in fused else None,
+                                                  "frac_fused": (128.0 * nn / world / (fused["forward_ms"] * 1e-3) / 1e9 / measured_peaks()[0]) if fused and "forward_ms" in fused else None}}
     sampler.stop()
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

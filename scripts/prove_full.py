@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
 
 
-def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: None, log=lambda *a: None, sigma=None, keep_sigma=False, warmup=0):
+def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: None, log=lambda *a: None, sigma=None, keep_sigma=False, warmup=0, from_files=True):
     from tokamak_b200.protocol import preprocess as PP
     from tokamak_b200.protocol import prover as PV
     from tokamak_b200.protocol import qap
@@ -75,8 +75,10 @@ def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: 
 
     from tokamak_b200.protocol import formats as F
 
-    tmp = tempfile.mkdtemp(prefix="tkm_prove_")
+    tmp = tempfile.mkdtemp(prefix="tkm_prove_") if from_files else None
     try:
+        if not from_files:
+            raise StopIteration
         F.write_library(os.path.join(tmp, "qap"), params, infos, r1cs)
         F.write_synthesizer_output(os.path.join(tmp, "syn"), pl, perm, inst)
         file_runs = []
@@ -101,8 +103,11 @@ def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: 
                                        "r1cs_total": sum(os.path.getsize(os.path.join(tmp, "qap", "r1cs", f)) for f in os.listdir(os.path.join(tmp, "qap", "r1cs")))},
                              "note": "placementVariables.json and the .r1cs binaries go through the library's native loaders "
                                      "(tkm_host_parse_hex_scalars, tkm_host_parse_r1cs); the small JSON files through Python's json"}
+    except StopIteration:
+        pass
     finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+        if tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
     if fixed_base_tables and hasattr(sigma.xy_powers, "precompute"):
         t = time.perf_counter()
         sigma.xy_powers.precompute(20)

@@ -98,6 +98,18 @@ def test_bintt_prover_shapes_vs_oracle(ctx, T, x, y):
     assert np.array_equal(ctx.bintt_host(a, x, y, T.INVERSE), O.bintt(a, x, y, True))
 
 
+def test_bintt_largest_shape_full_compare(ctx, T):
+    """16384 x 512 = 2^23 (BASELINE.json config): every output element of the forward and inverse transform, plain and with
+    cosets on both axes, against the C oracle (oracle.c does the full transform in a fraction of a second)."""
+    x, y = 16384, 512
+    a = O.random_fr(33, x * y)
+    cx, cy = O.random_fr(35, 1)[0], O.random_fr(36, 1)[0]
+    for inv in (False, True):
+        for gx, gy in ((None, None), (cx, cy)):
+            got = ctx.bintt_host(a, x, y, T.INVERSE if inv else T.FORWARD, gx, gy)
+            assert np.array_equal(got, O.bintt(a, x, y, inv, gx, gy)), (inv, gx is not None)
+
+
 def test_bintt_largest_shape_properties(ctx, T):
     """16384 x 512 = 2^23 (BASELINE.json config): round trip (tests.rs:107-131), coset == manual scaling
     (tests.rs:134-180), linearity, and sampled evaluations against Horner on the oracle."""
@@ -321,10 +333,10 @@ def test_msm_host_pipelined_large(ctx):
     assert np.array_equal(ctx.msm_g1_host(ss, pts), O.g1_mul(G, O.fr_inner_product(ss, ks)))
 
 
-@pytest.mark.parametrize("logn", [16, 18, 20])
+@pytest.mark.parametrize("logn", [16, 18, 20, 22, 24])
 def test_msm_large_known_discrete_logs(ctx, logn):
     """Bases k_i*G generated on the device; answer (sum s_i k_i)*G from O(N) field work on the oracle
-    (SURVEY.md §8d config 2)."""
+    (SURVEY.md §8d config 2).  2^22 is BASELINE.json's headline size, 2^24 the top of its sweep."""
     n = 1 << logn
     G = g1s([P.G1_GEN])[0]
     ks = O.random_fr(80 + logn, n)
@@ -403,6 +415,30 @@ def test_msm_rect_and_indexed(ctx):
     assert np.array_equal(got, O.msm_g1(sc2, grid[idx]))
     for p in (dg, ds, ds2, di):
         ctx.dev_free(p)
+
+
+def test_msm_prover_rectangles_of_full_crs_grid(ctx):
+    """The prover's real commitment extents -- 4097 x 257, 4097 x 511, 8192 x 511 -- as strided rectangles of a
+    device-resident 8192 x 512 grid (encode_poly trims the polynomial to its degree and addresses xy_powers with the
+    CRS row stride, iotools/mod.rs:2061-2088).  Bases k_ij*G generated on the device; expected (sum s_ij k_ij)*G."""
+    rs_x, rs_y = 8192, 512
+    n = rs_x * rs_y
+    G = g1s([P.G1_GEN])[0]
+    ks = O.random_fr(610, n)
+    ss = O.random_fr(611, n)
+    dk = ctx.upload_fr(ks, to_mont=False)
+    dg = ctx.dev_alloc(n * 96)
+    ctx.lib.tkm_g1_fixed_base_mul(ctx.h, G.ctypes.data, dk, 0, n, dg)
+    ctx.lib.tkm_g1_bases_to_mont(ctx.h, dg, dg, n)
+    ds = ctx.upload_fr(ss, to_mont=False)
+    k2, s2 = ks.reshape(rs_x, rs_y, 4), ss.reshape(rs_x, rs_y, 4)
+    for rows, cols in ((4097, 257), (4097, 511), (8192, 511), (8192, 512)):
+        got = ctx.msm_g1_rect_dev(ds, False, rs_y, dg, rs_y, rows, cols)
+        sk = np.ascontiguousarray(k2[:rows, :cols]).reshape(-1, 4)
+        sv = np.ascontiguousarray(s2[:rows, :cols]).reshape(-1, 4)
+        assert np.array_equal(got, O.g1_mul(G, O.fr_inner_product(sv, sk))), (rows, cols)
+    for p_ in (dk, dg, ds):
+        ctx.dev_free(p_)
 
 
 # ------------------------------------------------------------------------------------------ polynomial engine

@@ -70,6 +70,10 @@ struct tkm_ctx {
   // copy engine side of the pipelined host-buffer MSM (created on first use)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[17] = {};
+  // per-device launch state (function attributes and occupancy are properties of the device the context lives on, so they
+  // are cached here and not in process-wide statics: a second context on another GPU must get its own shared-memory opt-in)
+  bool ntt_attr_set[4] = {false, false, false, false};
+  int acc_occ = 0, bits_occ = 0;
 };
 
 struct tkm_poly {

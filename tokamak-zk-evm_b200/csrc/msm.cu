@@ -554,7 +554,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   // Chunk length.  Every thread does the same amount of work (one chunk), so the launch runs in lock-step waves of
   // `cap` resident threads: pick the number of waves for chunks of at most ~256 entries (2 partial-list entries per chunk:
   // longer chunks shrink the segmented-reduction levels), then size the chunk so that the waves are full.
-  static int occ = 0;
+  int &occ = ctx->acc_occ;  // per context = per device
   if (!occ) {
     TKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate, ACC_THREADS, 0));
     if (occ < 1) occ = 1;
@@ -615,7 +615,7 @@ static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *bucke
     // as many slices as fit the resident block slots (2^22 points: 192 groups -> 1 slice, no second stage; fixed-base
     // tables: 16 groups -> 18 slices), never more than one slice per BITS_THREADS segments.
     const uint32_t groups = m.W * (m.nbits + 1);
-    static int bits_occ = 0;
+    int &bits_occ = ctx->bits_occ;  // per context = per device
     if (!bits_occ) {
       TKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bits_occ, k_bucket_bits, BITS_THREADS, 0));
       if (bits_occ < 1) bits_occ = 1;

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
 static int32_t launch_pass(tkm_ctx *ctx, const NttPass &p, bool inverse) {
   const uint32_t L = 1u << p.logL, C = 1u << p.logC;
   size_t smem = (size_t)(2 * L * C + 2 * L) * sizeof(uint4);
-  static bool attr_set[2] = {false, false};
+  bool *attr_set = ctx->ntt_attr_set;  // per context = per device (cudaFuncSetAttribute applies to the current device only)
   if (!attr_set[inverse ? 1 : 0]) {
     size_t max_smem = (size_t)(2 * (1u << NTT_TILE_LOG) + 2 * (1u << NTT_MAX_LOGL)) * sizeof(uint4);
     if (inverse)

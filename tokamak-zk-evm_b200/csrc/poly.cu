@@ -3,6 +3,8 @@
 // device in Montgomery form, row-major [x_size][y_size] (X = row index, Y contiguous;
 // bivariate_polynomial/mod.rs:1756).  Every kernel here is HBM-bound (a few field ops per 32-byte
 // element): 128-bit accesses, threads walk the contiguous Y axis.
+#include <vector>
+
 #include "common.cuh"
 
 namespace tkm {
@@ -524,8 +526,24 @@ int32_t tkm_r1cs_uvw_polys(tkm_ctx *ctx, uint32_t s_D, const uint32_t *n_rows, c
     for (int m = 0; m < 3; m++) TKM_REQUIRE(rp_base[3 * s + m] + n_rows[s] + 1 <= row_ptr_len, "row pointer table too short");
   }
   for (size_t i = 0; i < row_ptr_len; i++) TKM_REQUIRE(row_ptr[i] <= nnz, "row pointer exceeds the number of entries");
-  for (size_t c = 0; c < s_max; c++)
-    TKM_REQUIRE(sub_of_col[c] == 0xffffffffu || (sub_of_col[c] < s_D && var_off[c] <= n_vars), "invalid placement column");
+  // CSR rows must be non-decreasing inside every (subcircuit, matrix) block, and every wire an entry of subcircuit s names
+  // must exist in each column that places s: wire_hi[s] = 1 + the largest local wire index of s (0 = no entries).
+  std::vector<uint64_t> wire_hi(s_D, 0);
+  for (uint32_t s = 0; s < s_D; s++) {
+    for (int m = 0; m < 3; m++) {
+      const uint32_t *rp = row_ptr + rp_base[3 * s + m];
+      for (uint32_t r = 0; r < n_rows[s]; r++) TKM_REQUIRE(rp[r] <= rp[r + 1], "row pointers of subcircuit %u are not non-decreasing", s);
+      for (uint32_t e = rp[0]; e < rp[n_rows[s]]; e++)
+        if ((uint64_t)wire[e] + 1 > wire_hi[s]) wire_hi[s] = (uint64_t)wire[e] + 1;
+    }
+  }
+  for (size_t c = 0; c < s_max; c++) {
+    if (sub_of_col[c] == 0xffffffffu) continue;
+    TKM_REQUIRE(sub_of_col[c] < s_D, "invalid placement column");
+    TKM_REQUIRE(var_off[c] <= n_vars && wire_hi[sub_of_col[c]] <= n_vars - var_off[c],
+                "placement column %zu: subcircuit %u reads wire %llu but only %llu variables follow its offset", c, sub_of_col[c],
+                (unsigned long long)(wire_hi[sub_of_col[c]] - 1), (unsigned long long)(n_vars - var_off[c]));
+  }
   Scratch<uint32_t> d_rp, d_wire, d_nrows, d_sub;
   Scratch<uint64_t> d_base, d_off;
   Scratch<Fr> d_coeff, d_wit;
