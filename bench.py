@@ -529,7 +529,7 @@ def main():
         for p_ in (d_bases, d_scalars):
             ctx.dev_free(p_)
         gpu_be = GpuBackend(ctx)
-        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync, warmup=3,
+        full = prove_full.run(gpu_be, S.reference_shape(), repeats=3, verify=True, fixed_base_tables=True, sync=ctx.sync, warmup=3, crs_load=True,
                               keep_sigma=args.cpu_prove_full)
         full_sigma = full.pop("_sigma", None)
         full["reference"] = {"cpu_prove_s": 45.7, "icicle_cuda_prove_s": 21.08, "stage_split_cpu_s": [5.21, 10.09, 2.13, 13.37, 1.56, 13.33],

@@ -158,6 +158,11 @@ int32_t tkm_g1_sum(tkm_ctx *ctx, const uint8_t *points96, size_t n, uint8_t out9
  *      archived form iotools/mod.rs:1701-1783) ------------------------------------------------------- */
 /* Upload rows*cols canonical affine points (row-major, index cols*h + i <-> x^h y^i) once. */
 int32_t tkm_crs_upload(tkm_ctx *ctx, const uint8_t *points96, size_t rows, size_t cols, tkm_crs **out);
+/* The same for points that are already in the device layout: x || y with 48-byte little-endian MONTGOMERY coordinates
+ * (R = 2^384) -- the `ffjs-g1-affine-96` encoding of the reference's flat TZBWASM1 CRS container
+ * (packages/backend-wasm/src/artifacts/binary/binary-format.ts:24-31, specs/prover-crs.v1.json), so a section of a
+ * memory-mapped prover_crs file is uploaded with one copy and no conversion. */
+int32_t tkm_crs_upload_mont(tkm_ctx *ctx, const uint8_t *points96_mont, size_t rows, size_t cols, tkm_crs **out);
 /* Wrap points already on the device in canonical form (converted in place to Montgomery). */
 int32_t tkm_crs_from_device(tkm_ctx *ctx, void *dev_points, size_t rows, size_t cols, int32_t take_ownership,
                             tkm_crs **out);
@@ -207,6 +212,29 @@ int32_t tkm_poly_resize(tkm_ctx *ctx, tkm_poly *p, size_t target_x, size_t targe
 int32_t tkm_poly_optimize_size(tkm_ctx *ctx, tkm_poly *p);
 /* mul_monomial (:1820-1844): multiply by X^ex Y^ey (new polynomial). */
 int32_t tkm_poly_mul_monomial(tkm_ctx *ctx, const tkm_poly *p, size_t ex, size_t ey, tkm_poly **out);
+/* poly_comb! (prove/src/lib.rs:30-38) and the helper polynomials built from it (:48-124) in ONE pass:
+ * out = sum_{t<k} c_t * X^shift_x[t] * Y^shift_y[t] * polys[t] on the union shape (a shifted term has mul_monomial's
+ * shape, bivariate_polynomial/mod.rs:1820-1844).  coeffs32: k canonical 32-byte scalars or NULL (all 1);
+ * shift_x / shift_y: k monomial exponents or NULL (no shift).  k <= 16. */
+int32_t tkm_poly_lincomb(tkm_ctx *ctx, uint32_t k, const tkm_poly *const *polys, const uint8_t *coeffs32, const uint32_t *shift_x,
+                         const uint32_t *shift_y, tkm_poly **out);
+/* PolyExpr::evaluate_fused_with_domain (bivariate_polynomial/mod.rs:227-260, evaluate_on_domain :311-435): the
+ * expression is handed over as a postfix program over `leaves` (the distinct polynomials of the DAG: one forward
+ * biNTT each, the reference's pointer-keyed leaf cache :459-502) and `consts32` (canonical scalars); the whole
+ * pointwise DAG runs as one kernel between the leaf transforms and the single inverse biNTT.  Program words are
+ * opcode | operand << 8.  Errors mirror the reference's panics ("Fused polynomial expression domains must be powers
+ * of two.", "... domain is too small for the expression degree.").  Limits: 16 leaves, 96 ops, 24 constants, depth 8. */
+enum {
+  TKM_PEX_LEAF = 0,  /* push the evaluations of leaves[operand]                    (PolyExpr::Poly)          */
+  TKM_PEX_CONST = 1, /* push the constant consts32[operand]                         (PolyExpr::Scalar)        */
+  TKM_PEX_ADD = 2,   /* b = pop, a = pop, push a + b                                (Add, Sum)                */
+  TKM_PEX_SUB = 3,   /* push a - b                                                  (Sub)                     */
+  TKM_PEX_MUL = 4,   /* push a * b                                                  (Mul)                     */
+  TKM_PEX_SCALE = 5, /* top *= consts32[operand]                                    (Scale)                   */
+  TKM_PEX_XM1 = 6    /* top *= (omega_x^i - 1), the evaluations of X - 1            (MulXMinusOne, :504-518)  */
+};
+int32_t tkm_polyexpr_eval(tkm_ctx *ctx, const tkm_poly *const *leaves, uint32_t n_leaves, const uint32_t *program, uint32_t n_ops,
+                          const uint8_t *consts32, uint32_t n_consts, size_t target_x, size_t target_y, tkm_poly **out);
 /* out = a*ca + b*cb on the max power-of-two shape (operator impls :532-1281 and poly_comb!,
  * prove/src/lib.rs:30-38, fused: no host resize/clone).  ca/cb: 32-byte canonical or NULL (= 1). */
 int32_t tkm_poly_axpby(tkm_ctx *ctx, const tkm_poly *a, const uint8_t *ca32, const tkm_poly *b, const uint8_t *cb32,
@@ -262,6 +290,8 @@ int32_t tkm_event_time_end(tkm_ctx *ctx, float *out_ms);
 /* Duration (CUDA events on the context stream) of the most recent dominant-kernel launch: k_accumulate of the last MSM,
  * or all k_ntt_pass launches of the last (bi)NTT.  Used by bench.py for the per-kernel roofline. */
 int32_t tkm_kernel_time_last(tkm_ctx *ctx, float *out_ms);
+/* The same for the fused expression kernel of the most recent tkm_polyexpr_eval (bench.py's poly_engine GB/s). */
+int32_t tkm_poly_kernel_time_last(tkm_ctx *ctx, float *out_ms);
 /* Kernel launches issued by this library on this context since creation. */
 int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out);
 /* Micro-benchmarks: integer pipe peak (dependent-free IMAD / IMAD.WIDE streams) and field-mul rate.

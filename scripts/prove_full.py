@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
 
 
-def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: None, log=lambda *a: None, sigma=None, keep_sigma=False, warmup=0, from_files=True):
+def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: None, log=lambda *a: None, sigma=None, keep_sigma=False, warmup=0, from_files=True, crs_load=False):
     from tokamak_b200.protocol import preprocess as PP
     from tokamak_b200.protocol import prover as PV
     from tokamak_b200.protocol import qap
@@ -108,6 +108,30 @@ def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: 
     finally:
         if tmp:
             shutil.rmtree(tmp, ignore_errors=True)
+    if crs_load and be.name == "b200":
+        # the reference loads its ~1 GB combined_sigma inside Prover::init (prove/src/lib.rs:675+, sigma_source.rs:17-37): time
+        # the same here -- CRS file (flat TZBWASM1 prover_crs container, page cache warm) -> device tables -> prove
+        from tokamak_b200.protocol import crs_io as C
+
+        tmp2 = tempfile.mkdtemp(prefix="tkm_crs_")
+        try:
+            path = os.path.join(tmp2, "prover_crs.bin")
+            C.write_prover_crs(path, be, sigma)
+            loads = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                sg2 = C.read_prover_crs(path, be, params, verify_digest=False)
+                sync()
+                t_load = time.perf_counter() - t0
+                pv = PV.Prover(be, params, infos, r1cs, sg2, pl, perm, inst, mixer=PV.Mixer.fixed(), library_csr=csr)
+                _, _, fmt_c, _ = PV.prove(pv)
+                loads.append({"total_s": time.perf_counter() - t0, "crs_load_s": t_load})
+                assert fmt_c == fmt, "proof with the CRS loaded from file differs"
+                del pv, sg2
+            out["with_crs_load"] = {"prove_s": min(r["total_s"] for r in loads), "runs": loads, "crs_file_bytes": os.path.getsize(path),
+                                    "note": "prover_crs (TZBWASM1) memory-mapped, four tables uploaded as they are (tkm_crs_upload_mont), then init + prove0..4"}
+        finally:
+            shutil.rmtree(tmp2, ignore_errors=True)
     if fixed_base_tables and hasattr(sigma.xy_powers, "precompute"):
         t = time.perf_counter()
         sigma.xy_powers.precompute(20)

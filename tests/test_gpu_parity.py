@@ -744,6 +744,104 @@ def test_poly_expr_fused_matches_coefficients(ctx, T):
             expr.evaluate_fused_with_domain(sx, sy)
 
 
+def test_polyexpr_program_entry_point(ctx, T):
+    """tkm_polyexpr_eval: the prover's p_comb shape (prove/src/lib.rs:2110-2146) on a 64 x 32 domain against the coefficient-
+    domain operators, shared leaves transformed once, constant-only / scale-by-one programs, and the reference's panics."""
+    E = T.PolyExpr
+    sx, sy = 32, 16
+    r, g, f, r1, r2, KL, K0 = [poly_from(T, ctx, O.random_fr(900 + k, sx * sy), sx, sy) for k in range(7)]
+    kappa = 0x1234567890ABCDEF1234567890ABCDEF % P.R_MOD
+    rg = E.mul(E.poly(r), E.poly(g))
+    p1 = E.mul(E.sub(E.poly(r), E.scalar(1)), E.poly(KL))
+    p2 = E.mul_x_minus_one(E.sub(rg, E.mul(E.poly(r1), E.poly(f))))
+    p3 = E.mul(E.poly(K0), E.sub(rg, E.mul(E.poly(r2), E.poly(f))))
+    expr = E.weighted_sum([(1, p1), (kappa, p2), (kappa * kappa % P.R_MOD, p3)])
+    l0 = ctx.launch_count()
+    fused = expr.evaluate_fused_with_domain(64, 32)
+    launches = ctx.launch_count() - l0
+    # 7 distinct leaves (r, g, f used more than once): 7 x (pad + forward biNTT) + ONE expression kernel + one inverse biNTT
+    assert launches <= 7 * 4 + 1 + 3, launches
+    ref = expr.evaluate_coeffs()
+    ref.resize(64, 32)
+    assert fused.shape == (64, 32)
+    assert np.array_equal(fused.copy_coeffs(), ref.copy_coeffs())
+    assert to_ints(E.scalar(5).evaluate_fused_with_domain(2, 2).copy_coeffs()) == [5, 0, 0, 0]
+    assert np.array_equal(E.scale(1, E.poly(r)).evaluate_fused_with_domain(sx, sy).copy_coeffs(), r.copy_coeffs())
+    assert to_ints(E.weighted_sum([]).evaluate_fused_with_domain(1, 1).copy_coeffs()) == [0]
+    with pytest.raises(ValueError):
+        expr.evaluate_fused_with_domain(32, 32)  # too small for the degree
+    with pytest.raises(ValueError):
+        expr.evaluate_fused_with_domain(48, 32)  # not a power of two
+    # raw entry point: malformed programs are rejected, not executed
+    import ctypes
+    hs = (ctypes.c_void_p * 1)(r.h)
+    out = ctypes.c_void_p()
+    one = frs([1])
+    for prog in ([T.PEX_ADD], [T.PEX_LEAF | 3 << 8], [T.PEX_LEAF, T.PEX_LEAF], [99], [T.PEX_LEAF, T.PEX_SCALE | 7 << 8]):
+        pr = np.array(prog, dtype=np.uint32)
+        st = ctx.lib.tkm_polyexpr_eval(ctx.h, hs, 1, pr.ctypes.data_as(ctypes.c_void_p), len(prog), one.ctypes.data_as(ctypes.c_void_p), 1, sx, sy, ctypes.byref(out))
+        assert st != 0, prog
+
+
+def test_poly_lincomb_matches_chained_operators(ctx, T):
+    """tkm_poly_lincomb (poly_comb!, prove/src/lib.rs:30-38 and the shifted helpers :48-124): k-ary, mixed shapes, monomial
+    shifts, unit coefficients -- against the chain of scalar products, mul_monomial and additions, and against big-int sums."""
+    shapes = [(8, 4), (4, 16), (16, 2), (1, 1), (8, 4)]
+    polys = [poly_from(T, ctx, O.random_fr(950 + k, x * y), x, y) for k, (x, y) in enumerate(shapes)]
+    cs = [int(v) for v in to_ints(O.random_fr(960, 5))]
+    cs[3] = 1
+    terms = [(cs[0], polys[0], 0, 0), (cs[1], polys[1], 1, 0), (cs[2], polys[2], 0, 3), (cs[3], polys[3], 0, 0), (cs[4], polys[4], 2, 1)]
+    fused = T.DensePolynomialExt.lincomb(terms)
+    chained = None
+    for c, p_, sx, sy in terms:
+        t = (p_.mul_monomial(sx, sy) if (sx or sy) else p_) * c
+        chained = t if chained is None else chained + t
+    assert fused.shape == chained.shape
+    assert np.array_equal(fused.copy_coeffs(), chained.copy_coeffs())
+    ox, oy = fused.shape
+    exp = [0] * (ox * oy)
+    for (c, p_, sx, sy), (x, y) in zip(terms, shapes):
+        co = p_.coeffs_ints()
+        for i in range(x):
+            for j in range(y):
+                exp[(i + sx) * oy + j + sy] = (exp[(i + sx) * oy + j + sy] + c * co[i * y + j]) % P.R_MOD
+    assert fused.coeffs_ints() == exp
+    # two-term, unshifted, no coefficients == operator +
+    plain = T.DensePolynomialExt.lincomb([(1, polys[0]), (1, polys[1])])
+    assert np.array_equal(plain.copy_coeffs(), (polys[0] + polys[1]).copy_coeffs())
+    with pytest.raises(T.TkmError):
+        T.DensePolynomialExt.lincomb([(1, polys[0])] * 17)
+
+
+def test_two_contexts_in_one_process(T):
+    """Per-context launch state (shared-memory opt-in, occupancy caches) and cudaSetDevice at every entry: two contexts --
+    on two devices when the box has them, else on the same one -- used alternately, each with its own NTT domain, run the
+    64 KiB-tile NTT path (axis 1024) and an MSM and agree with the oracle."""
+    import torch
+
+    O.build()
+    dev_b = 1 if torch.cuda.device_count() > 1 else 0
+    ca, cb = T.Context(0), T.Context(dev_b)
+    try:
+        ca.init_ntt_domain_for_size(1 << 12)
+        cb.init_ntt_domain_for_size(1 << 20)  # first pass of a 2^20 axis uses L = 1024 tiles (64 KiB of dynamic shared memory)
+        a = O.random_fr(970, 1024 * 4)
+        b = O.random_fr(971, 1 << 20)
+        G = g1s([P.G1_GEN])[0]
+        pts = O.g1_fixed_base_mul_batch(G, O.random_fr(972, 300))
+        ss = O.random_fr(973, 300)
+        exp_msm = O.msm_g1(ss, pts)
+        for _ in range(2):
+            assert np.array_equal(ca.bintt_host(a, 1024, 4, T.FORWARD), O.bintt(a, 1024, 4, False))
+            assert np.array_equal(cb.bintt_host(b, 1 << 20, 1, T.FORWARD), O.bintt(b, 1 << 20, 1, False))
+            assert np.array_equal(cb.bintt_host(a, 1024, 4, T.INVERSE), O.bintt(a, 1024, 4, True))
+            assert np.array_equal(ca.msm_g1_host(ss, pts), exp_msm)
+            assert np.array_equal(cb.msm_g1_host(ss, pts), exp_msm)
+    finally:
+        ca.close()
+        cb.close()
+
+
 def test_transpose_fill_x_minus_one(ctx, T):
     """VecOps::transpose (vector_operations/mod.rs:139), device_vec_from_scalar and x_minus_one_evals
     (bivariate_polynomial/mod.rs:452-457,504-518)."""

@@ -208,3 +208,26 @@ def test_reference_shape_oracle_proof_matches_golden_hash(backends):
     golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prove_reference_shape.json")))
     assert hashlib.sha256(json.dumps(fmt, sort_keys=True).encode()).hexdigest() == golden["proof_sha256"]
     print("oracle prove spans:", {k: round(v, 2) for k, v in pv.t.spans.items() if "." not in k})
+
+
+def test_prove_from_crs_files(backends, tmp_path):
+    """f3: a CRS written in the reference's two containers (flat TZBWASM1 prover_crs, rkyv SigmaRkyv archive) and loaded back
+    onto the device -- TZBWASM1 sections go up as they are (device layout = ffjs Montgomery bytes, tkm_crs_upload_mont) --
+    gives the same tables and the same proof bytes as the generated CRS."""
+    from tokamak_b200.protocol import crs_io as C
+
+    gpu, _ = backends
+    params, infos, r1cs = S.make_library(_small_shape(), seed=3)
+    pl, perm, inst = S.synthesize(params, infos, r1cs, seed=4, small_value_fraction=0.3)
+    sigma = ST.generate(gpu, params, infos, r1cs, ST.Tau.gen_fixed())
+    _, _, fmt0, _ = PV.prove(PV.Prover(gpu, params, infos, r1cs, sigma, pl, perm, inst, mixer=PV.Mixer.fixed()))
+    flat, arch = str(tmp_path / "prover_crs.bin"), str(tmp_path / "combined_sigma.rkyv")
+    C.write_prover_crs(flat, gpu, sigma)
+    C.write_sigma_rkyv(arch, gpu, sigma)
+    # the flat container holds the device bytes verbatim, which are the host conversion of the canonical points
+    assert np.array_equal(sigma.xy_powers.mont_bytes_host()[:64], C.canonical_points_to_mont(sigma.xy_powers.points_host()[:64]))
+    for loaded in (C.read_prover_crs(flat, gpu, params), C.read_sigma_rkyv(arch, gpu, params)[0]):
+        for name in ("xy_powers", "gamma_inv_o_inst", "eta_inv_li_o_inter_alpha4_kj", "delta_inv_li_o_prv"):
+            assert np.array_equal(getattr(loaded, name).points_host(), getattr(sigma, name).points_host()), name
+        _, _, fmt, _ = PV.prove(PV.Prover(gpu, params, infos, r1cs, loaded, pl, perm, inst, mixer=PV.Mixer.fixed()))
+        assert fmt == fmt0

@@ -190,6 +190,8 @@ int32_t tkm_ctx_create(int32_t device_ordinal, tkm_ctx **out) {
   TKM_CUDA(cudaEventCreate(&ctx->ev1));
   TKM_CUDA(cudaEventCreate(&ctx->kev0));
   TKM_CUDA(cudaEventCreate(&ctx->kev1));
+  TKM_CUDA(cudaEventCreate(&ctx->pev0));
+  TKM_CUDA(cudaEventCreate(&ctx->pev1));
   // keep freed scratch in the stream-ordered pool instead of returning it to the driver
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
@@ -214,6 +216,8 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->kev0) cudaEventDestroy(ctx->kev0);
   if (ctx->kev1) cudaEventDestroy(ctx->kev1);
+  if (ctx->pev0) cudaEventDestroy(ctx->pev0);
+  if (ctx->pev1) cudaEventDestroy(ctx->pev1);
   if (ctx->side_stream) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
@@ -587,6 +591,30 @@ int32_t tkm_crs_upload(tkm_ctx *ctx, const uint8_t *points96, size_t rows, size_
   if (st != TKM_OK) cudaFree(d);
   return st;
 }
+int32_t tkm_crs_upload_mont(tkm_ctx *ctx, const uint8_t *points96_mont, size_t rows, size_t cols, tkm_crs **out) {
+  API_BEGIN
+  TKM_REQUIRE(points96_mont && out, "null argument");
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, rows * cols * 96 + 16);
+  if (e != cudaSuccess) return fail(TKM_ERR_ALLOCATION, "cudaMalloc(%zu) failed: %s", rows * cols * 96, cudaGetErrorString(e));
+  e = cudaMemcpyAsync(d, points96_mont, rows * cols * 96, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(TKM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  }
+  tkm_crs *c = new (std::nothrow) tkm_crs();
+  if (!c) {
+    cudaFree(d);
+    return fail(TKM_ERR_ALLOCATION, "out of host memory");
+  }
+  c->d = (G1Affine *)d;
+  c->rows = rows;
+  c->cols = cols;
+  c->owned = true;
+  *out = c;
+  return TKM_OK;
+}
 int32_t tkm_crs_precompute(tkm_ctx *ctx, tkm_crs *crs, uint32_t window_bits) {
   API_BEGIN
   TKM_REQUIRE(crs, "null crs");
@@ -799,6 +827,14 @@ int32_t tkm_kernel_time_last(tkm_ctx *ctx, float *out_ms) {
   TKM_REQUIRE(ctx->kernel_timed, "no dominant-kernel launch has been timed on this context yet");
   TKM_CUDA(cudaEventSynchronize(ctx->kev1));
   TKM_CUDA(cudaEventElapsedTime(out_ms, ctx->kev0, ctx->kev1));
+  return TKM_OK;
+}
+int32_t tkm_poly_kernel_time_last(tkm_ctx *ctx, float *out_ms) {
+  API_BEGIN
+  TKM_REQUIRE(out_ms, "null out pointer");
+  TKM_REQUIRE(ctx->poly_kernel_timed, "no polynomial-engine kernel has been timed on this context yet");
+  TKM_CUDA(cudaEventSynchronize(ctx->pev1));
+  TKM_CUDA(cudaEventElapsedTime(out_ms, ctx->pev0, ctx->pev1));
   return TKM_OK;
 }
 int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out) {

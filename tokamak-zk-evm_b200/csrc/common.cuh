@@ -54,6 +54,9 @@ struct tkm_ctx {
   // bench.py's roofline divides the kernel's algorithmic work by this duration (tkm_kernel_time_last)
   cudaEvent_t kev0 = nullptr, kev1 = nullptr;
   bool kernel_timed = false;
+  // the same for the most recent polynomial-engine kernel of interest (k_polyexpr): bench.py's poly_engine GB/s
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+  bool poly_kernel_timed = false;
   // window table (64 x 16 affine multiples) of the most recent tkm_g1_fixed_base_mul base
   tkm::G1Affine *fb_table = nullptr;
   uint8_t fb_base[96] = {};

@@ -78,6 +78,91 @@ __global__ void __launch_bounds__(256) k_scale_coeffs(Fr *__restrict__ out, cons
   }
 }
 
+// ---------------------------------------------------------------- k-ary linear combination (poly_comb!, prove/src/lib.rs:30-38)
+// out[i][j] = sum_t c_t * p_t[i - sx_t][j - sy_t] on the union shape: the whole chain of scalar products, monomial shifts
+// (mul_monomial), clones, resizes and additions of a `poly_comb!` line in ONE pass -- every operand is read once, the
+// result written once.
+constexpr int LINCOMB_MAX = 16;
+struct LincombArgs {
+  const Fr *p[LINCOMB_MAX];
+  uint32_t x[LINCOMB_MAX], y[LINCOMB_MAX], sx[LINCOMB_MAX], sy[LINCOMB_MAX];
+  Fr c[LINCOMB_MAX];
+  uint32_t one[LINCOMB_MAX];  // coefficient is 1: skip the product
+  uint32_t k;
+};
+__global__ void __launch_bounds__(256) k_lincomb(Fr *__restrict__ out, size_t ox, size_t oy, const __grid_constant__ LincombArgs a) {
+  const size_t total = ox * oy;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t i = (uint32_t)(e / oy), j = (uint32_t)(e % oy);
+    Fr acc = Fr::zero();
+    for (uint32_t t = 0; t < a.k; t++) {
+      const uint32_t ii = i - a.sx[t], jj = j - a.sy[t];  // wraps to a huge value when the shift exceeds the index
+      if (ii < a.x[t] && jj < a.y[t]) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(a.p[t] + (size_t)ii * a.y[t] + jj);
+        uint4 lo = __ldg(q), hi = __ldg(q + 1);
+        Fr v;
+        v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
+        v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+        acc = acc + (a.one[t] ? v : v * a.c[t]);
+      }
+    }
+    out[e] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- fused expression evaluation (PolyExpr, bivariate_polynomial/mod.rs:140-435)
+// The pointwise part of evaluate_on_domain as ONE kernel: a postfix program over the leaves' evaluation vectors, run per
+// element with the top of the stack in registers.  All threads execute the same program, so the interpreter's branches are
+// uniform.  HBM traffic: every leaf read once, the result written once (the reference allocates a fresh 256 MiB vector
+// per node, prove/src/lib.rs:2110-2146).
+constexpr int PEX_MAX_LEAVES = 16, PEX_MAX_OPS = 96, PEX_MAX_CONSTS = 24, PEX_STACK = 8;
+struct PexProgram {
+  const Fr *leaf[PEX_MAX_LEAVES];
+  Fr konst[PEX_MAX_CONSTS];
+  uint32_t op[PEX_MAX_OPS];  // opcode | operand << 8
+  uint32_t n_ops;
+};
+__global__ void __launch_bounds__(256) k_polyexpr(Fr *__restrict__ out, size_t x_size, size_t y_size, const __grid_constant__ PexProgram pr,
+                                                  const Fr *__restrict__ tw, uint32_t log_stride, size_t half_m) {
+  const size_t total = x_size * y_size;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    Fr st[PEX_STACK];
+    Fr top = Fr::zero();
+    int sp = 0;  // entries below the top
+    for (uint32_t pc = 0; pc < pr.n_ops; pc++) {
+      const uint32_t w = pr.op[pc], code = w & 0xffu, arg = w >> 8;
+      switch (code) {
+        case TKM_PEX_LEAF: {
+          st[sp++] = top;
+          const uint4 *q = reinterpret_cast<const uint4 *>(pr.leaf[arg] + e);
+          uint4 lo = __ldg(q), hi = __ldg(q + 1);
+          top.v[0] = lo.x; top.v[1] = lo.y; top.v[2] = lo.z; top.v[3] = lo.w;
+          top.v[4] = hi.x; top.v[5] = hi.y; top.v[6] = hi.z; top.v[7] = hi.w;
+          break;
+        }
+        case TKM_PEX_CONST:
+          st[sp++] = top;
+          top = pr.konst[arg];
+          break;
+        case TKM_PEX_ADD: top = st[--sp] + top; break;
+        case TKM_PEX_SUB: top = st[--sp] - top; break;
+        case TKM_PEX_MUL: top = st[--sp] * top; break;
+        case TKM_PEX_SCALE: top = top * pr.konst[arg]; break;
+        default: {  // TKM_PEX_XM1: times (omega_x^i - 1), omega_x^i from the domain table (second half: -omega^(k - M/2))
+          const size_t ex = (e / y_size) << log_stride;
+          Fr wv;
+          if (x_size == 1) wv = Fr::one();
+          else if (ex <= half_m) wv = tw[ex];
+          else wv = tw[ex - half_m].neg();
+          top = top * (wv - Fr::one());
+          break;
+        }
+      }
+    }
+    out[e] = top;
+  }
+}
+
 // ---------------------------------------------------------------- evaluation
 __device__ __forceinline__ Fr warp_sum(Fr v) {
   for (int d = 16; d > 0; d >>= 1) {
@@ -709,6 +794,101 @@ int32_t tkm_poly_axpby(tkm_ctx *ctx, const tkm_poly *a, const uint8_t *ca32, con
                                                                           ca32 ? 0 : 1, b ? b->d : nullptr, b ? b->x_size : 0,
                                                                           b ? b->y_size : 0, cb, cb32 ? 0 : 1);
   return launch_check(ctx, "k_axpby");
+}
+
+int32_t tkm_poly_lincomb(tkm_ctx *ctx, uint32_t k, const tkm_poly *const *polys, const uint8_t *coeffs32, const uint32_t *shift_x,
+                         const uint32_t *shift_y, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(polys && out && k >= 1, "null argument or empty combination");
+  TKM_REQUIRE(k <= (uint32_t)LINCOMB_MAX, "at most %d terms per combination (got %u)", LINCOMB_MAX, k);
+  static const uint8_t ONE32[32] = {1};
+  LincombArgs a;
+  memset(&a, 0, sizeof a);
+  a.k = k;
+  size_t ox = 1, oy = 1;
+  for (uint32_t t = 0; t < k; t++) {
+    TKM_REQUIRE(polys[t], "null polynomial in term %u", t);
+    const size_t sx = shift_x ? shift_x[t] : 0, sy = shift_y ? shift_y[t] : 0;
+    // a shifted term has mul_monomial's shape (:1820-1844): the next powers of two of (size + shift)
+    const size_t tx = (sx || sy) ? next_pow2(polys[t]->x_size + sx) : polys[t]->x_size;
+    const size_t ty = (sx || sy) ? next_pow2(polys[t]->y_size + sy) : polys[t]->y_size;
+    if (tx > ox) ox = tx;
+    if (ty > oy) oy = ty;
+    a.p[t] = polys[t]->d;
+    a.x[t] = (uint32_t)polys[t]->x_size;
+    a.y[t] = (uint32_t)polys[t]->y_size;
+    a.sx[t] = (uint32_t)sx;
+    a.sy[t] = (uint32_t)sy;
+    const uint8_t *c = coeffs32 ? coeffs32 + 32 * (size_t)t : ONE32;
+    a.one[t] = memcmp(c, ONE32, 32) == 0;
+    a.c[t] = fr_from_bytes_host(c);
+  }
+  TKM_REQUIRE(ox < ((size_t)1 << 31) && oy < ((size_t)1 << 31), "combination shape out of range");
+  TKM_TRY(poly_alloc(ctx, ox, oy, out));
+  k_lincomb<<<grid_for(ox * oy, 256, ctx->sm_count), 256, 0, ctx->stream>>>((*out)->d, ox, oy, a);
+  return launch_check(ctx, "k_lincomb");
+}
+
+int32_t tkm_polyexpr_eval(tkm_ctx *ctx, const tkm_poly *const *leaves, uint32_t n_leaves, const uint32_t *program, uint32_t n_ops,
+                          const uint8_t *consts32, uint32_t n_consts, size_t target_x, size_t target_y, tkm_poly **out) {
+  API_BEGIN
+  TKM_REQUIRE(program && out && n_ops >= 1, "null argument or empty program");
+  TKM_REQUIRE(n_leaves == 0 || leaves, "null leaves");
+  TKM_REQUIRE(n_consts == 0 || consts32, "null constants");
+  TKM_REQUIRE(n_leaves <= (uint32_t)PEX_MAX_LEAVES && n_ops <= (uint32_t)PEX_MAX_OPS && n_consts <= (uint32_t)PEX_MAX_CONSTS,
+              "expression too large (limits: %d leaves, %d ops, %d constants)", PEX_MAX_LEAVES, PEX_MAX_OPS, PEX_MAX_CONSTS);
+  if (!is_pow2(target_x) || !is_pow2(target_y)) return fail(TKM_ERR_INVALID_ARGUMENT, "Fused polynomial expression domains must be powers of two.");
+  if (ctx->domain_log2 < 0) return fail(TKM_ERR_DOMAIN, "NTT domain is not initialized. Call tkm_ntt_domain_init first.");
+  if (log2_exact(target_x) + log2_exact(target_y) > (uint32_t)ctx->domain_log2)
+    return fail(TKM_ERR_DOMAIN, "NTT domain size too small: initialized size 2^%d but the expression domain is %zu x %zu", ctx->domain_log2, target_x, target_y);
+  // validate the program: operands in range, the stack never underflows or overflows, exactly one value is left
+  int depth = 0;
+  for (uint32_t pc = 0; pc < n_ops; pc++) {
+    const uint32_t code = program[pc] & 0xffu, arg = program[pc] >> 8;
+    switch (code) {
+      case TKM_PEX_LEAF: TKM_REQUIRE(arg < n_leaves && leaves[arg], "op %u: leaf %u out of range", pc, arg); depth++; break;
+      case TKM_PEX_CONST: TKM_REQUIRE(arg < n_consts, "op %u: constant %u out of range", pc, arg); depth++; break;
+      case TKM_PEX_ADD: case TKM_PEX_SUB: case TKM_PEX_MUL: TKM_REQUIRE(depth >= 2, "op %u: stack underflow", pc); depth--; break;
+      case TKM_PEX_SCALE: TKM_REQUIRE(arg < n_consts && depth >= 1, "op %u: bad scale", pc); break;
+      case TKM_PEX_XM1: TKM_REQUIRE(depth >= 1, "op %u: stack underflow", pc); break;
+      default: return fail(TKM_ERR_INVALID_ARGUMENT, "op %u: unknown opcode %u", pc, code);
+    }
+    TKM_REQUIRE(depth <= PEX_STACK, "op %u: expression needs more than %d stack entries", pc, PEX_STACK);
+  }
+  TKM_REQUIRE(depth == 1, "the program leaves %d values on the stack (expected 1)", depth);
+  const size_t n = target_x * target_y;
+  PexProgram pr;
+  memset(&pr, 0, sizeof pr);
+  pr.n_ops = n_ops;
+  memcpy(pr.op, program, n_ops * sizeof(uint32_t));
+  for (uint32_t c = 0; c < n_consts; c++) pr.konst[c] = fr_from_bytes_host(consts32 + 32 * (size_t)c);
+  // one forward transform per distinct leaf (eval_poly_leaf, :459-502): zero-pad to the domain, NTT in place
+  Scratch<Fr> ev[PEX_MAX_LEAVES];
+  for (uint32_t l = 0; l < n_leaves; l++) {
+    const tkm_poly *p = leaves[l];
+    if (p->x_size > target_x || p->y_size > target_y)
+      return fail(TKM_ERR_INVALID_ARGUMENT, "Fused polynomial expression domain is too small for the expression degree.");
+    TKM_TRY(ev[l].alloc(ctx, n));
+    TKM_TRY(poly_reshape_into(ctx, p->d, p->x_size, p->y_size, target_x, target_y, 0, 0, ev[l].p));
+    TKM_TRY(bintt_dev(ctx, ev[l].p, ev[l].p, target_x, target_y, TKM_FORWARD, nullptr, nullptr));
+    pr.leaf[l] = ev[l].p;
+  }
+  tkm_poly *res = nullptr;
+  TKM_TRY(poly_alloc(ctx, target_x, target_y, &res));
+  const uint32_t log_stride = (uint32_t)ctx->domain_log2 - log2_exact(target_x);
+  TKM_CUDA(cudaEventRecord(ctx->pev0, ctx->stream));
+  k_polyexpr<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(res->d, target_x, target_y, pr, ctx->twiddles, log_stride,
+                                                                       (size_t)1 << (ctx->domain_log2 > 0 ? ctx->domain_log2 - 1 : 0));
+  TKM_CUDA(cudaEventRecord(ctx->pev1, ctx->stream));
+  ctx->poly_kernel_timed = true;
+  int32_t st = launch_check(ctx, "k_polyexpr");
+  if (st == TKM_OK) st = bintt_dev(ctx, res->d, res->d, target_x, target_y, TKM_INVERSE, nullptr, nullptr);
+  if (st != TKM_OK) {
+    poly_release(ctx, res);
+    return st;
+  }
+  *out = res;
+  return TKM_OK;
 }
 
 int32_t tkm_poly_add_scalar(tkm_ctx *ctx, tkm_poly *p, const uint8_t s32[32]) {

@@ -209,6 +209,93 @@ static int run_gpu_tests() {
     }
     EXPECT(threw);
   });
+  T("test_poly_expr_fused_matches_coefficients (libs/src/tests.rs:1240-1276)", [&] {
+    ctx.init_ntt_domain_for_size(16);
+    auto make_poly = [&] { return DensePolynomialExt::from_coeffs(ctx, rng.generate_random(4), 2, 2); };
+    auto a = make_poly(), b = make_poly(), c = make_poly(), d = make_poly(), e = make_poly();
+    auto expr = PolyExpr::weighted_sum({
+        {ScalarField::from_u32(7), PolyExpr::mul_x_minus_one(PolyExpr::sub(PolyExpr::mul(PolyExpr::poly(a), PolyExpr::poly(b)),
+                                                                           PolyExpr::mul(PolyExpr::poly(c), PolyExpr::poly(d))))},
+        {ScalarField::from_u32(11), PolyExpr::mul(PolyExpr::sub(PolyExpr::poly(a), PolyExpr::scalar(ScalarField::one())), PolyExpr::poly(e))},
+    });
+    auto coeff_result = expr.evaluate_coeffs(ctx);
+    auto fused_result = expr.evaluate_fused(ctx);
+    for (int k = 0; k < 8; k++) {
+      auto pt = rng.generate_random(2);
+      EXPECT(coeff_result.eval(pt[0], pt[1]) == fused_result.eval(pt[0], pt[1]));
+    }
+    // a larger domain than the degree needs gives the same polynomial; a smaller or non-power-of-two one panics
+    auto wide = expr.evaluate_fused_with_domain(ctx, 8, 4);
+    auto pt = rng.generate_random(2);
+    EXPECT(wide.eval(pt[0], pt[1]) == coeff_result.eval(pt[0], pt[1]));
+    bool threw = false;
+    try {
+      expr.evaluate_fused_with_domain(ctx, 2, 2);
+    } catch (const std::runtime_error &ex) {
+      threw = std::string(ex.what()).find("too small") != std::string::npos;
+    }
+    EXPECT(threw);
+    threw = false;
+    try {
+      expr.evaluate_fused_with_domain(ctx, 6, 4);
+    } catch (const std::runtime_error &ex) {
+      threw = std::string(ex.what()).find("powers of two") != std::string::npos;
+    }
+    EXPECT(threw);
+  });
+  T("poly_comb! as one lincomb pass == chained operators (prove/src/lib.rs:30-38,48-124)", [&] {
+    auto p = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(8 * 4), 8, 4);
+    auto q = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(4 * 16), 4, 16);
+    auto cs = rng.generate_random(3);
+    auto fused = DensePolynomialExt::lincomb({{cs[0], &p, 0, 0}, {cs[1], &q, 0, 0}, {cs[2], &p, 1, 0}, {ScalarField::one(), &q, 0, 1}});
+    auto chained = (p * cs[0]) + (q * cs[1]) + (p.mul_monomial(1, 0) * cs[2]) + q.mul_monomial(0, 1);
+    EXPECT(fused.shape() == chained.shape());
+    EXPECT(fused.copy_coeffs() == chained.copy_coeffs());
+  });
+  T("trait surface: zero / is_zero / eval_x / eval_y / divide_x / += / scalar - poly (bivariate_polynomial/mod.rs:1283-1416)", [&] {
+    auto z = DensePolynomialExt::zero(ctx, 4, 4);
+    EXPECT(z.is_zero());
+    auto p = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(8 * 8), 8, 8);
+    EXPECT(!p.is_zero());
+    auto pt = rng.generate_random(2);
+    EXPECT(p.eval_x(pt[0]).eval(ScalarField::one(), pt[1]) == p.eval(pt[0], pt[1]));
+    EXPECT(p.eval_y(pt[1]).eval(pt[0], ScalarField::one()) == p.eval(pt[0], pt[1]));
+    auto den = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(4), 4, 1);
+    auto qr = p.divide_x(den);
+    EXPECT(((qr.first * den) + qr.second).eval(pt[0], pt[1]) == p.eval(pt[0], pt[1]));
+    DensePolynomialExt acc(p);
+    acc += p;
+    EXPECT(acc.eval(pt[0], pt[1]) == p.eval(pt[0], pt[1]) + p.eval(pt[0], pt[1]));
+    EXPECT((pt[0] - p).eval(pt[0], pt[1]) == pt[0] - p.eval(pt[0], pt[1]));
+    EXPECT(ScalarField::from_hex(pt[0].to_string()) == pt[0]);
+  });
+  T("G1serde ops and sparse encoders (group_structures/mod.rs:127-300,888-947)", [&] {
+    auto ks = rng.generate_random(6);
+    std::vector<G1Affine> tab;
+    for (auto &k : ks) tab.push_back(ctx.g1_mul(generator(), k));
+    EXPECT(g1_add(ctx, tab[0], tab[1]) == ctx.g1_mul(generator(), ks[0] + ks[1]));
+    EXPECT(g1_sub(ctx, tab[0], tab[1]) == ctx.g1_mul(generator(), ks[0] - ks[1]));
+    EXPECT(g1_mul(ctx, tab[2], ks[3]) == ctx.g1_mul(generator(), ks[2] * ks[3]));
+    EXPECT(g1_add(ctx, tab[0], g1_neg(tab[0])) == G1Affine::zero());
+    auto sc = rng.generate_random(4);
+    std::vector<uint32_t> idx = {5, 0, 3, 3};
+    Sigma1 table(ctx, tab.data(), 2, 3);
+    ScalarField exp = sc[0] * ks[5] + sc[1] * ks[0] + sc[2] * ks[3] + sc[3] * ks[3];
+    EXPECT(table.msm_indexed(sc, idx) == ctx.g1_mul(generator(), exp));
+    EXPECT(msm_g1_bases(ctx, {}, {}) == G1Affine::zero());
+    EXPECT(msm_g1_bases(ctx, {tab[1], tab[4]}, {sc[0], sc[1]}) == ctx.g1_mul(generator(), sc[0] * ks[1] + sc[1] * ks[4]));
+  });
+  T("vector_operations (vector_operations/mod.rs:19-141,639-693)", [&] {
+    auto a = rng.generate_random(12), b = rng.generate_random(12);
+    auto m = vector_operations::point_mul_two_vecs(ctx, a, b);
+    auto dv = vector_operations::point_div_two_vecs(ctx, m, b);
+    for (size_t i = 0; i < a.size(); i++) EXPECT(m[i] == a[i] * b[i] && dv[i] == a[i]);
+    auto t = a;
+    vector_operations::transpose_inplace(t, 3, 4);
+    EXPECT(t[1 * 3 + 2] == a[2 * 4 + 1]);
+    auto r = vector_operations::resize(a, 3, 4, 4, 2);
+    EXPECT(r.size() == 8 && r[1 * 2 + 1] == a[1 * 4 + 1] && r[3 * 2] == ScalarField::zero());
+  });
   std::printf("ALL PASSED (%d tests)\n", passed);
   return 0;
 }

@@ -7,8 +7,10 @@
 // backed values, `&`-style operators that never mutate their inputs, and panics mapped to exceptions (every non-zero
 // status throws std::runtime_error carrying tkm_last_error()).  Header-only; link with -ltokamak_b200.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -112,6 +114,34 @@ struct ScalarField {
     std::memcpy(r2.l, R2, 32);
     return mont(mont(*this, o), r2);
   }
+  // ScalarField::from_hex ("0x..." big-endian hex digits, reduced mod r), to_string (the reference prints 0x + 64 digits),
+  // from_bytes_le / to_bytes_le (libs/src/iotools/mod.rs:126-146,1786-1815)
+  static ScalarField from_hex(const std::string &hex) {
+    size_t i = (hex.size() >= 2 && hex[0] == '0' && (hex[1] == 'x' || hex[1] == 'X')) ? 2 : 0;
+    ScalarField r = zero();
+    const ScalarField sixteen = from_u32(16);
+    for (; i < hex.size(); i++) {
+      const char ch = hex[i];
+      int d = (ch >= '0' && ch <= '9') ? ch - '0' : (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : (ch >= 'A' && ch <= 'F') ? ch - 'A' + 10 : -1;
+      if (d < 0) throw std::runtime_error("invalid hex digit in ScalarField::from_hex");
+      r = r * sixteen + from_u32((uint32_t)d);
+    }
+    return r;
+  }
+  std::string to_string() const {
+    static const char *dig = "0123456789abcdef";
+    std::string out = "0x";
+    for (int i = 3; i >= 0; i--)
+      for (int b = 60; b >= 0; b -= 4) out.push_back(dig[(l[i] >> b) & 15]);
+    return out;
+  }
+  static ScalarField from_bytes_le(const uint8_t *b32) {
+    ScalarField r;
+    std::memcpy(r.l, b32, 32);
+    while (geq_r(r.l)) sub_r(r.l);
+    return r;
+  }
+  void to_bytes_le(uint8_t *out32) const { std::memcpy(out32, l, 32); }
   ScalarField pow(uint64_t e) const {
     ScalarField acc = one(), base = *this;
     while (e) {
@@ -309,6 +339,56 @@ class DensePolynomialExt {
     check(tkm_poly_eval(c_->raw(), h_, x.bytes(), y.bytes(), r.bytes()));
     return r;
   }
+  // zero / is_zero / degree (trait :1283-1416)
+  static DensePolynomialExt zero(const Context &c, size_t x_size = 1, size_t y_size = 1) {
+    tkm_poly *h = nullptr;
+    check(tkm_poly_zero(c.raw(), x_size, y_size, &h));
+    return DensePolynomialExt(c, h);
+  }
+  bool is_zero() const { return find_degree().first < 0; }
+  std::pair<int64_t, int64_t> degree() const { return {(int64_t)x_size() - 1, (int64_t)y_size() - 1}; }  // upper bounds, like the reference's fields
+  // += / -= (AddAssign / SubAssign, :532-1281): same union-shape semantics as the binary operators
+  DensePolynomialExt &operator+=(const DensePolynomialExt &o) { return *this = *this + o; }
+  DensePolynomialExt &operator-=(const DensePolynomialExt &o) { return *this = *this - o; }
+  // eval_x / eval_y (:1719-1740): partial evaluations (1 x y_size and x_size x 1)
+  DensePolynomialExt eval_x(const ScalarField &x) const {
+    tkm_poly *h = nullptr;
+    check(tkm_poly_eval_x(c_->raw(), h_, x.bytes(), &h));
+    return DensePolynomialExt(*c_, h);
+  }
+  DensePolynomialExt eval_y(const ScalarField &y) const {
+    tkm_poly *h = nullptr;
+    check(tkm_poly_eval_y(c_->raw(), h_, y.bytes(), &h));
+    return DensePolynomialExt(*c_, h);
+  }
+  // divide_x / divide_y (:1998-2094): (quotient, remainder) of the line-wise long division by a univariate denominator
+  std::pair<DensePolynomialExt, DensePolynomialExt> divide_x(const DensePolynomialExt &denom) const { return divide(denom, 0); }
+  std::pair<DensePolynomialExt, DensePolynomialExt> divide_y(const DensePolynomialExt &denom) const { return divide(denom, 1); }
+  // poly_comb! (prove/src/lib.rs:30-38) and the shifted helpers (:48-124): sum of c * X^sx * Y^sy * p in one pass
+  struct Term {
+    ScalarField c;
+    const DensePolynomialExt *p;
+    uint32_t sx = 0, sy = 0;
+  };
+  static DensePolynomialExt lincomb(const std::vector<Term> &terms) {
+    if (terms.empty()) throw std::runtime_error("empty polynomial combination");
+    std::vector<const tkm_poly *> hs;
+    std::vector<ScalarField> cs;
+    std::vector<uint32_t> sx, sy;
+    for (const Term &t : terms) {
+      hs.push_back(t.p->h_);
+      cs.push_back(t.c);
+      sx.push_back(t.sx);
+      sy.push_back(t.sy);
+    }
+    tkm_poly *h = nullptr;
+    check(tkm_poly_lincomb(terms[0].p->c_->raw(), (uint32_t)terms.size(), hs.data(), cs[0].bytes(), sx.data(), sy.data(), &h));
+    return DensePolynomialExt(*terms[0].p->c_, h);
+  }
+  const Context &context() const { return *c_; }
+  // div_by_vanishing (legacy coset formulation, :2096-2282): the same decomposition P = Q_X (X^c - 1) + Q_Y (Y^d - 1) as
+  // div_by_vanishing_opt (both fix Q_Y's X-degree below c, which makes the pair unique); the prover only calls _opt.
+  std::pair<DensePolynomialExt, DensePolynomialExt> div_by_vanishing(size_t c, size_t d) { return div_by_vanishing_opt(c, d); }
   // div_by_vanishing_opt (:2284-2410): P = Q_X (X^c - 1) + Q_Y (Y^d - 1)
   std::pair<DensePolynomialExt, DensePolynomialExt> div_by_vanishing_opt(size_t c, size_t d) {
     tkm_poly *qx = nullptr, *qy = nullptr;
@@ -320,6 +400,11 @@ class DensePolynomialExt {
   Ruffini div_by_ruffini(const ScalarField &x, const ScalarField &y) const;
 
  private:
+  std::pair<DensePolynomialExt, DensePolynomialExt> divide(const DensePolynomialExt &denom, int y_dir) const {
+    tkm_poly *q = nullptr, *r = nullptr;
+    check(tkm_poly_divide_uni(c_->raw(), h_, denom.h_, y_dir, &q, &r));
+    return {DensePolynomialExt(*c_, q), DensePolynomialExt(*c_, r)};
+  }
   DensePolynomialExt scale(const ScalarField *sx, const ScalarField *sy) const {
     tkm_poly *h = nullptr;
     check(tkm_poly_scale_coeffs(c_->raw(), h_, sx ? sx->bytes() : nullptr, sy ? sy->bytes() : nullptr, &h));
@@ -339,6 +424,257 @@ inline DensePolynomialExt::Ruffini DensePolynomialExt::div_by_ruffini(const Scal
   return Ruffini{DensePolynomialExt(*c_, qx), DensePolynomialExt(*c_, qy), r};
 }
 inline DensePolynomialExt operator*(const ScalarField &s, const DensePolynomialExt &p) { return p * s; }
+inline DensePolynomialExt operator+(const ScalarField &s, const DensePolynomialExt &p) { return p + s; }
+inline DensePolynomialExt operator-(const ScalarField &s, const DensePolynomialExt &p) { return (-p) + s; }
+
+// ---------------------------------------------------------------- PolyExpr (libs/src/bivariate_polynomial/mod.rs:140-260)
+// Expression DAG over borrowed polynomials.  evaluate_coeffs walks it with the coefficient-domain operators;
+// evaluate_fused(_with_domain) compiles it to a postfix program and hands it to tkm_polyexpr_eval: one forward biNTT per
+// distinct leaf (pointer-keyed, like the reference's leaf cache :459-502), ONE pointwise kernel, one inverse biNTT.
+class PolyExpr {
+ public:
+  enum Kind { Poly, Scalar, Add, Sub, Mul, Scale, MulXMinusOne, Sum };
+  static PolyExpr poly(const DensePolynomialExt &p) {
+    PolyExpr e(Poly);
+    e.n_->p = &p;
+    return e;
+  }
+  static PolyExpr scalar(const ScalarField &s) {
+    PolyExpr e(Scalar);
+    e.n_->s = s;
+    return e;
+  }
+  static PolyExpr add(const PolyExpr &l, const PolyExpr &r) { return binary(Add, l, r); }
+  static PolyExpr sub(const PolyExpr &l, const PolyExpr &r) { return binary(Sub, l, r); }
+  static PolyExpr mul(const PolyExpr &l, const PolyExpr &r) { return binary(Mul, l, r); }
+  static PolyExpr scale(const ScalarField &s, const PolyExpr &x) {
+    PolyExpr e(Scale);
+    e.n_->s = s;
+    e.n_->kids = {x.n_};
+    return e;
+  }
+  static PolyExpr mul_x_minus_one(const PolyExpr &x) {
+    PolyExpr e(MulXMinusOne);
+    e.n_->kids = {x.n_};
+    return e;
+  }
+  static PolyExpr weighted_sum(const std::vector<std::pair<ScalarField, PolyExpr>> &terms) {
+    PolyExpr e(Sum);
+    for (const auto &t : terms) e.n_->kids.push_back(scale(t.first, t.second).n_);
+    return e;
+  }
+
+  // evaluate_coeffs (:190-218)
+  DensePolynomialExt evaluate_coeffs(const Context &c) const { return coeffs(*n_, c); }
+  // degree bound (:262-309); (-1, -1) = the zero polynomial
+  std::pair<int64_t, int64_t> degree_bound() const { return bound(*n_); }
+  // evaluate_fused (:220-225) / evaluate_fused_with_domain (:227-260)
+  DensePolynomialExt evaluate_fused(const Context &c) const {
+    const auto d = degree_bound();
+    return evaluate_fused_with_domain(c, domain_size_for_degree(d.first), domain_size_for_degree(d.second));
+  }
+  DensePolynomialExt evaluate_fused_with_domain(const Context &c, size_t target_x_size, size_t target_y_size) const {
+    if ((target_x_size & (target_x_size - 1)) || (target_y_size & (target_y_size - 1)) || !target_x_size || !target_y_size)
+      throw std::runtime_error("Fused polynomial expression domains must be powers of two.");
+    const auto d = degree_bound();
+    if (domain_size_for_degree(d.first) > target_x_size || domain_size_for_degree(d.second) > target_y_size)
+      throw std::runtime_error("Fused polynomial expression domain is too small for the expression degree.");
+    Program pr;
+    emit(*n_, pr);
+    std::vector<const tkm_poly *> hs;
+    for (const DensePolynomialExt *p : pr.leaves) hs.push_back(p->raw());
+    if (pr.consts.empty()) pr.consts.push_back(ScalarField::zero());
+    tkm_poly *h = nullptr;
+    check(tkm_polyexpr_eval(c.raw(), hs.empty() ? nullptr : hs.data(), (uint32_t)hs.size(), pr.ops.data(), (uint32_t)pr.ops.size(), pr.consts[0].bytes(),
+                            (uint32_t)pr.consts.size(), target_x_size, target_y_size, &h));
+    return DensePolynomialExt(c, h);
+  }
+  static size_t domain_size_for_degree(int64_t degree) {  // :438-444
+    if (degree < 0) return 1;
+    size_t n = 1;
+    while (n < (size_t)degree + 1) n <<= 1;
+    return n;
+  }
+
+ private:
+  struct Node {
+    Kind k;
+    const DensePolynomialExt *p = nullptr;
+    ScalarField s = ScalarField::zero();
+    std::vector<std::shared_ptr<Node>> kids;
+  };
+  struct Program {
+    std::vector<const DensePolynomialExt *> leaves;
+    std::vector<ScalarField> consts;
+    std::vector<uint32_t> ops;
+    uint32_t leaf(const DensePolynomialExt *p) {
+      for (size_t i = 0; i < leaves.size(); i++)
+        if (leaves[i] == p) return (uint32_t)i;
+      leaves.push_back(p);
+      return (uint32_t)leaves.size() - 1;
+    }
+    uint32_t konst(const ScalarField &s) {
+      for (size_t i = 0; i < consts.size(); i++)
+        if (consts[i] == s) return (uint32_t)i;
+      consts.push_back(s);
+      return (uint32_t)consts.size() - 1;
+    }
+  };
+  explicit PolyExpr(Kind k) : n_(std::make_shared<Node>()) { n_->k = k; }
+  static PolyExpr binary(Kind k, const PolyExpr &l, const PolyExpr &r) {
+    PolyExpr e(k);
+    e.n_->kids = {l.n_, r.n_};
+    return e;
+  }
+  static void emit(const Node &n, Program &pr) {
+    switch (n.k) {
+      case Poly: pr.ops.push_back(TKM_PEX_LEAF | pr.leaf(n.p) << 8); break;
+      case Scalar: pr.ops.push_back(TKM_PEX_CONST | pr.konst(n.s) << 8); break;
+      case Add: case Sub: case Mul:
+        emit(*n.kids[0], pr);
+        emit(*n.kids[1], pr);
+        pr.ops.push_back(n.k == Add ? TKM_PEX_ADD : n.k == Sub ? TKM_PEX_SUB : TKM_PEX_MUL);
+        break;
+      case Scale:
+        emit(*n.kids[0], pr);
+        if (n.s != ScalarField::one()) pr.ops.push_back(TKM_PEX_SCALE | pr.konst(n.s) << 8);
+        break;
+      case MulXMinusOne:
+        emit(*n.kids[0], pr);
+        pr.ops.push_back(TKM_PEX_XM1);
+        break;
+      case Sum:
+        if (n.kids.empty()) pr.ops.push_back(TKM_PEX_CONST | pr.konst(ScalarField::zero()) << 8);
+        for (size_t i = 0; i < n.kids.size(); i++) {
+          emit(*n.kids[i], pr);
+          if (i) pr.ops.push_back(TKM_PEX_ADD);
+        }
+        break;
+    }
+  }
+  static DensePolynomialExt coeffs(const Node &n, const Context &c) {
+    switch (n.k) {
+      case Poly: return DensePolynomialExt(*n.p);
+      case Scalar: return DensePolynomialExt::from_coeffs(c, {n.s}, 1, 1);
+      case Add: return coeffs(*n.kids[0], c) + coeffs(*n.kids[1], c);
+      case Sub: return coeffs(*n.kids[0], c) - coeffs(*n.kids[1], c);
+      case Mul: return coeffs(*n.kids[0], c) * coeffs(*n.kids[1], c);
+      case Scale: return coeffs(*n.kids[0], c) * n.s;
+      case MulXMinusOne: {
+        DensePolynomialExt p = coeffs(*n.kids[0], c);
+        return p.mul_monomial(1, 0) - p;
+      }
+      case Sum: {
+        if (n.kids.empty()) return DensePolynomialExt::zero(c);
+        DensePolynomialExt acc = coeffs(*n.kids[0], c);
+        for (size_t i = 1; i < n.kids.size(); i++) acc += coeffs(*n.kids[i], c);
+        return acc;
+      }
+    }
+    throw std::logic_error("unreachable");
+  }
+  static std::pair<int64_t, int64_t> bound(const Node &n) {
+    switch (n.k) {
+      case Poly: return n.p->find_degree();
+      case Scalar: return n.s == ScalarField::zero() ? std::make_pair<int64_t, int64_t>(-1, -1) : std::make_pair<int64_t, int64_t>(0, 0);
+      case Add: case Sub: {
+        auto l = bound(*n.kids[0]), r = bound(*n.kids[1]);
+        return {std::max(l.first, r.first), std::max(l.second, r.second)};
+      }
+      case Mul: {
+        auto l = bound(*n.kids[0]), r = bound(*n.kids[1]);
+        if (l.first < 0 || l.second < 0 || r.first < 0 || r.second < 0) return {-1, -1};
+        return {l.first + r.first, l.second + r.second};
+      }
+      case Scale: return n.s == ScalarField::zero() ? std::make_pair<int64_t, int64_t>(-1, -1) : bound(*n.kids[0]);
+      case MulXMinusOne: {
+        auto d = bound(*n.kids[0]);
+        if (d.first < 0 || d.second < 0) return {-1, -1};
+        return {d.first + 1, d.second};
+      }
+      case Sum: {
+        std::pair<int64_t, int64_t> out{-1, -1};
+        for (const auto &k : n.kids) {
+          auto d = bound(*k);
+          out = {std::max(out.first, d.first), std::max(out.second, d.second)};
+        }
+        return out;
+      }
+    }
+    throw std::logic_error("unreachable");
+  }
+  std::shared_ptr<Node> n_;
+};
+
+// ---------------------------------------------------------------- G1serde ops (libs/src/group_structures/mod.rs:888-947)
+inline G1Affine g1_add(const Context &c, const G1Affine &a, const G1Affine &b) {
+  G1Affine r;
+  check(tkm_g1_add(c.raw(), a.b, b.b, r.b));
+  return r;
+}
+inline G1Affine g1_mul(const Context &c, const G1Affine &a, const ScalarField &k) {
+  G1Affine r;
+  check(tkm_g1_mul(c.raw(), a.b, k.bytes(), r.b));
+  return r;
+}
+inline G1Affine g1_neg(const G1Affine &a) {  // (x, -y); the identity stays (0, 0)
+  static const uint64_t Q[6] = {0xb9feffffffffaaabull, 0x1eabfffeb153ffffull, 0x6730d2a0f6b0f624ull, 0x64774b84f38512bfull, 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull};
+  G1Affine r = a;
+  uint64_t y[6];
+  std::memcpy(y, a.b + 48, 48);
+  uint64_t any = 0;
+  for (int i = 0; i < 6; i++) any |= y[i];
+  if (!any) return r;
+  unsigned __int128 borrow = 0;
+  for (int i = 0; i < 6; i++) {
+    unsigned __int128 d = (unsigned __int128)Q[i] - y[i] - borrow;
+    y[i] = (uint64_t)d;
+    borrow = (d >> 64) & 1;
+  }
+  std::memcpy(r.b + 48, y, 48);
+  return r;
+}
+inline G1Affine g1_sub(const Context &c, const G1Affine &a, const G1Affine &b) { return g1_add(c, a, g1_neg(b)); }
+// msm_g1_bases (:127-143): empty input -> identity
+inline G1Affine msm_g1_bases(const Context &c, const std::vector<G1Affine> &bases, const std::vector<ScalarField> &scalars) {
+  if (bases.size() != scalars.size()) throw std::runtime_error("Mismatch between the numbers of bases and scalars");
+  G1Affine r = G1Affine::zero();
+  if (!bases.empty()) check(tkm_msm_g1_host(c.raw(), scalars[0].bytes(), bases[0].b, bases.size(), r.b));
+  return r;
+}
+
+// ---------------------------------------------------------------- vector_operations (libs/src/vector_operations/mod.rs:19-141,639-693)
+namespace vector_operations {
+inline std::vector<ScalarField> pointwise(const Context &c, int32_t op, const std::vector<ScalarField> &a, const std::vector<ScalarField> &b) {
+  if (a.size() != b.size()) throw std::runtime_error("Mismatch of sizes of vectors to be pointwise operated");
+  std::vector<ScalarField> out(a.size());
+  if (!a.empty()) check(tkm_fr_vec_op_host(c.raw(), op, a[0].bytes(), b[0].bytes(), out[0].bytes(), a.size()));
+  return out;
+}
+inline std::vector<ScalarField> point_mul_two_vecs(const Context &c, const std::vector<ScalarField> &a, const std::vector<ScalarField> &b) {
+  return pointwise(c, TKM_OP_MUL, a, b);
+}
+inline std::vector<ScalarField> point_div_two_vecs(const Context &c, const std::vector<ScalarField> &a, const std::vector<ScalarField> &b) {
+  return pointwise(c, TKM_OP_DIV, a, b);
+}
+inline std::vector<ScalarField> point_add_two_vecs(const Context &c, const std::vector<ScalarField> &a, const std::vector<ScalarField> &b) {
+  return pointwise(c, TKM_OP_ADD, a, b);
+}
+// transpose_inplace (:139-141): rows x cols row-major -> cols x rows
+inline void transpose_inplace(std::vector<ScalarField> &v, size_t rows, size_t cols) {
+  std::vector<ScalarField> out(v.size());
+  for (size_t i = 0; i < rows; i++)
+    for (size_t j = 0; j < cols; j++) out[j * rows + i] = v[i * cols + j];
+  v.swap(out);
+}
+// resize (:639-672): copy the overlapping rectangle of a rows x cols matrix into target_rows x target_cols, zero elsewhere
+inline std::vector<ScalarField> resize(const std::vector<ScalarField> &m, size_t rows, size_t cols, size_t target_rows, size_t target_cols) {
+  std::vector<ScalarField> out(target_rows * target_cols, ScalarField::zero());
+  for (size_t i = 0; i < std::min(rows, target_rows); i++)
+    for (size_t j = 0; j < std::min(cols, target_cols); j++) out[i * target_cols + j] = m[i * cols + j];
+  return out;
+}
+}  // namespace vector_operations
 
 // ---------------------------------------------------------------- Sigma1 (xy_powers resident on the device)
 class Sigma1 {
@@ -352,6 +688,30 @@ class Sigma1 {
   }
   Sigma1(const Sigma1 &) = delete;
   Sigma1 &operator=(const Sigma1 &) = delete;
+  // A second resident table (gamma_inv_o_inst, eta_inv_li_o_inter_alpha4_kj, delta_inv_li_o_prv: group_structures/mod.rs:
+  // 361-394) for the sparse encoders; rows x cols like the reference's boxed 2-D arrays.
+  Sigma1(const Context &c, const G1Affine *points, size_t rows, size_t cols) : c_(&c) { check(tkm_crs_upload(c.raw(), points[0].b, rows, cols, &h_)); }
+  // msm_g1_bases over gathered entries of this table (encode_o_pub_fix_common / encode_o_pub_free_common /
+  // encode_statement_common, group_structures/mod.rs:145-300): sum_k scalars[k] * table[idx[k]]
+  G1Affine msm_indexed(const std::vector<ScalarField> &scalars, const std::vector<uint32_t> &idx) const {
+    if (scalars.size() != idx.size()) throw std::runtime_error("Mismatch between the numbers of bases and scalars");
+    G1Affine r = G1Affine::zero();
+    if (scalars.empty()) return r;
+    void *ds = nullptr, *di = nullptr, *dt = nullptr;
+    size_t rows, cols;
+    check(tkm_crs_device_ptr(h_, &dt, &rows, &cols));
+    for (uint32_t i : idx)
+      if (i >= rows * cols) throw std::runtime_error("CRS index out of range");
+    check(tkm_dev_alloc(c_->raw(), scalars.size() * 32, &ds));
+    check(tkm_dev_alloc(c_->raw(), idx.size() * 4, &di));
+    check(tkm_memcpy_h2d(c_->raw(), ds, scalars[0].bytes(), scalars.size() * 32));
+    check(tkm_memcpy_h2d(c_->raw(), di, idx.data(), idx.size() * 4));
+    const int32_t st = tkm_msm_g1_indexed(c_->raw(), ds, 0, dt, di, scalars.size(), r.b);
+    tkm_dev_free(c_->raw(), ds);
+    tkm_dev_free(c_->raw(), di);
+    check(st);
+    return r;
+  }
   // encode_poly(&mut poly): may shrink the polynomial (optimize_size), panics if the CRS is too small
   G1Affine encode_poly(DensePolynomialExt &poly) const {
     G1Affine r;

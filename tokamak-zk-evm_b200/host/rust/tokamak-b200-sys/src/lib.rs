@@ -14,6 +14,14 @@ pub const TKM_OP_ADD: i32 = 0;
 pub const TKM_OP_SUB: i32 = 1;
 pub const TKM_OP_MUL: i32 = 2;
 pub const TKM_OP_DIV: i32 = 3;
+/// Opcodes of the postfix programs `tkm_polyexpr_eval` runs (word = opcode | operand << 8).
+pub const TKM_PEX_LEAF: u32 = 0;
+pub const TKM_PEX_CONST: u32 = 1;
+pub const TKM_PEX_ADD: u32 = 2;
+pub const TKM_PEX_SUB: u32 = 3;
+pub const TKM_PEX_MUL: u32 = 4;
+pub const TKM_PEX_SCALE: u32 = 5;
+pub const TKM_PEX_XM1: u32 = 6;
 
 extern "C" {
     pub fn tkm_last_error() -> *const c_char;
@@ -115,4 +123,10 @@ extern "C" {
     pub fn tkm_event_time_end(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_launch_count(ctx: *mut tkm_ctx, out: *mut u64) -> i32;
     pub fn tkm_microbench(ctx: *mut tkm_ctx, kind: i32, out_ops_per_s: *mut f64) -> i32;
+    pub fn tkm_poly_lincomb(ctx: *mut tkm_ctx, k: u32, polys: *const *const tkm_poly, coeffs32: *const u8, shift_x: *const u32,
+                            shift_y: *const u32, out: *mut *mut tkm_poly) -> i32;
+    pub fn tkm_polyexpr_eval(ctx: *mut tkm_ctx, leaves: *const *const tkm_poly, n_leaves: u32, program: *const u32, n_ops: u32,
+                             consts32: *const u8, n_consts: u32, target_x: usize, target_y: usize, out: *mut *mut tkm_poly) -> i32;
+    pub fn tkm_poly_kernel_time_last(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
+    pub fn tkm_crs_upload_mont(ctx: *mut tkm_ctx, points96_mont: *const u8, rows: usize, cols: usize, out: *mut *mut tkm_crs) -> i32;
 }

@@ -15,6 +15,7 @@ from .ffi import TkmError, check
 R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 FORWARD, INVERSE = 0, 1
 OP_ADD, OP_SUB, OP_MUL, OP_DIV = 0, 1, 2, 3
+PEX_LEAF, PEX_CONST, PEX_ADD, PEX_SUB, PEX_MUL, PEX_SCALE, PEX_XM1 = range(7)  # tkm_polyexpr_eval opcodes
 
 
 def _vp(a):
@@ -408,6 +409,20 @@ class DensePolynomialExt:
         check(self.ctx.lib.tkm_poly_mul_monomial(self.ctx.h, self.h, x_exponent, y_exponent, ctypes.byref(h)))
         return DensePolynomialExt(self.ctx, h)
 
+    @staticmethod
+    def lincomb(terms):
+        """poly_comb! (prove/src/lib.rs:30-38) in one pass: sum of c * X^sx * Y^sy * p over terms (c, p) or (c, p, sx, sy)."""
+        terms = [t if len(t) == 4 else (t[0], t[1], 0, 0) for t in terms]
+        ctx = terms[0][1].ctx
+        k = len(terms)
+        hs = (ctypes.c_void_p * k)(*[t[1].h for t in terms])
+        cs = frs_from_ints([int(t[0]) % R_MOD for t in terms])
+        sx = np.array([t[2] for t in terms], dtype=np.uint32)
+        sy = np.array([t[3] for t in terms], dtype=np.uint32)
+        h = ctypes.c_void_p()
+        check(ctx.lib.tkm_poly_lincomb(ctx.h, k, hs, _vp(cs), _vp(sx), _vp(sy), ctypes.byref(h)))
+        return DensePolynomialExt(ctx, h)
+
     # -- data movement ------------------------------------------------------------------------------
     def copy_coeffs(self):
         x, y = self.shape
@@ -744,102 +759,51 @@ class PolyExpr:
         xd, yd = self.degree_bound()
         if _domain_size_for_degree(xd) > target_x_size or _domain_size_for_degree(yd) > target_y_size:
             raise ValueError("Fused polynomial expression domain is too small for the expression degree.")
-        ev = _EvalDomain(ctx, target_x_size, target_y_size)
-        buf, owned = ev.run(self)
-        if not owned:
-            buf = ev.copy(buf)
-        check(ctx.lib.tkm_bintt(ctx.h, ctypes.c_void_p(buf), ctypes.c_void_p(buf), target_x_size, target_y_size, INVERSE, None, None))
+        leaves, consts, prog = [], [], []
+
+        def leaf(p):
+            for i, q in enumerate(leaves):  # pointer-keyed leaf cache (:459-502): one forward NTT per distinct polynomial
+                if q is p:
+                    return i
+            leaves.append(p)
+            return len(leaves) - 1
+
+        def const(v):
+            if v not in consts:
+                consts.append(v)
+            return consts.index(v)
+
+        def emit(e):
+            k, a = e.kind, e.args
+            if k == "poly":
+                prog.append(PEX_LEAF | leaf(a[0]) << 8)
+            elif k == "scalar":
+                prog.append(PEX_CONST | const(a[0]) << 8)
+            elif k in ("add", "sub", "mul"):
+                emit(a[0])
+                emit(a[1])
+                prog.append({"add": PEX_ADD, "sub": PEX_SUB, "mul": PEX_MUL}[k])
+            elif k == "scale":
+                emit(a[1])
+                if a[0] != 1:
+                    prog.append(PEX_SCALE | const(a[0]) << 8)
+            elif k == "xm1":
+                emit(a[0])
+                prog.append(PEX_XM1)
+            elif k == "sum":
+                if not a[0]:
+                    prog.append(PEX_CONST | const(0) << 8)
+                for n_, t in enumerate(a[0]):
+                    emit(t)
+                    if n_:
+                        prog.append(PEX_ADD)
+            else:
+                raise ValueError(k)
+
+        emit(self)
+        hs = (ctypes.c_void_p * max(1, len(leaves)))(*[q.h for q in leaves])
+        cs = frs_from_ints(consts or [0])
+        pr = np.array(prog, dtype=np.uint32)
         h = ctypes.c_void_p()
-        check(ctx.lib.tkm_poly_from_device(ctx.h, ctypes.c_void_p(buf), target_x_size, target_y_size, ctypes.byref(h)))
-        ev.release(buf)
-        ev.close()
+        check(ctx.lib.tkm_polyexpr_eval(ctx.h, hs, len(leaves), _vp(pr), len(prog), _vp(cs), len(consts), target_x_size, target_y_size, ctypes.byref(h)))
         return DensePolynomialExt(ctx, h)
-
-
-class _EvalDomain:
-    """Device buffers of x*y evaluations with a per-leaf cache; every node returns (device pointer, owned)."""
-
-    def __init__(self, ctx, x, y):
-        self.ctx, self.x, self.y, self.n = ctx, x, y, x * y
-        self.cache = {}
-        self.free = []
-
-    def alloc(self):
-        return self.free.pop() if self.free else self.ctx.dev_alloc(self.n * 32)
-
-    def release(self, ptr):
-        self.free.append(ptr)
-
-    def copy(self, src):
-        dst = self.alloc()
-        one = frs_from_ints([1])
-        check(self.ctx.lib.tkm_fr_vec_scale(self.ctx.h, _vp(one), ctypes.c_void_p(src), ctypes.c_void_p(dst), self.n))
-        return dst
-
-    def close(self):
-        for p in list(self.cache.values()) + self.free:
-            self.ctx.dev_free(p)
-        self.cache, self.free = {}, []
-
-    def _binary(self, op, l, r):
-        lib, h = self.ctx.lib, self.ctx.h
-        (pl, ol), (pr, orr) = self.run(l), self.run(r)
-        out = pl if ol else (pr if orr and op != OP_SUB else self.alloc())
-        check(lib.tkm_fr_vec_op(h, op, ctypes.c_void_p(pl), ctypes.c_void_p(pr), ctypes.c_void_p(out), self.n))
-        for p, o in ((pl, ol), (pr, orr)):
-            if o and p != out:
-                self.release(p)
-        return out, True
-
-    def run(self, e):
-        lib, h, n = self.ctx.lib, self.ctx.h, self.n
-        k, a = e.kind, e.args
-        if k == "poly":
-            key = id(a[0])
-            if key not in self.cache:  # eval_poly_leaf (:459-502): resize + forward NTT once per distinct leaf
-                q = a[0].clone()
-                q.resize(self.x, self.y)
-                if q.shape != (self.x, self.y):
-                    raise ValueError("leaf polynomial larger than the evaluation domain")
-                check(lib.tkm_poly_ntt_inplace(h, q.h, FORWARD, None, None))
-                buf = self.alloc()
-                one = frs_from_ints([1])
-                check(lib.tkm_fr_vec_scale(h, _vp(one), ctypes.c_void_p(q.device_ptr()), ctypes.c_void_p(buf), n))
-                q.close()
-                self.cache[key] = buf
-            return self.cache[key], False
-        if k == "scalar":
-            buf = self.alloc()
-            s = frs_from_ints([a[0]])
-            check(lib.tkm_fr_vec_fill(h, _vp(s), ctypes.c_void_p(buf), n))
-            return buf, True
-        if k == "add":
-            return self._binary(OP_ADD, a[0], a[1])
-        if k == "sub":
-            return self._binary(OP_SUB, a[0], a[1])
-        if k == "mul":
-            return self._binary(OP_MUL, a[0], a[1])
-        if k == "scale":
-            p, o = self.run(a[1])
-            if a[0] == 1:
-                return p, o
-            out = p if o else self.alloc()
-            s = frs_from_ints([a[0]])
-            check(lib.tkm_fr_vec_scale(h, _vp(s), ctypes.c_void_p(p), ctypes.c_void_p(out), n))
-            return out, True
-        if k == "xm1":
-            p, o = self.run(a[0])
-            out = p if o else self.alloc()
-            check(lib.tkm_fr_mul_x_minus_one(h, ctypes.c_void_p(p), ctypes.c_void_p(out), self.x, self.y))
-            return out, True
-        if k == "sum":
-            acc = self.alloc()
-            z = frs_from_ints([0])
-            check(lib.tkm_fr_vec_fill(h, _vp(z), ctypes.c_void_p(acc), n))
-            for t in a[0]:
-                p, o = self.run(t)
-                check(lib.tkm_fr_vec_op(h, OP_ADD, ctypes.c_void_p(acc), ctypes.c_void_p(p), ctypes.c_void_p(acc), n))
-                if o:
-                    self.release(p)
-            return acc, True
-        raise ValueError(k)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "tkm_g1_mul": [c_void_p, c_void_p, c_void_p, c_void_p],
     "tkm_g1_sum": [c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_crs_upload": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
+    "tkm_crs_upload_mont": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_crs_from_device": [c_void_p, c_void_p, c_size_t, c_size_t, c_int32, P(c_void_p)],
     "tkm_crs_precompute": [c_void_p, c_void_p, c_uint32],
     "tkm_crs_free": [c_void_p, c_void_p],
@@ -76,6 +77,9 @@ SIGNATURES = {
     "tkm_poly_optimize_size": [c_void_p, c_void_p],
     "tkm_poly_mul_monomial": [c_void_p, c_void_p, c_size_t, c_size_t, P(c_void_p)],
     "tkm_poly_axpby": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)],
+    "tkm_poly_lincomb": [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)],
+    "tkm_polyexpr_eval": [c_void_p, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_uint32, c_size_t, c_size_t, P(c_void_p)],
+    "tkm_poly_kernel_time_last": [c_void_p, P(ctypes.c_float)],
     "tkm_poly_add_scalar": [c_void_p, c_void_p, c_void_p],
     "tkm_poly_mul": [c_void_p, c_void_p, c_void_p, P(c_void_p)],
     "tkm_poly_scale_coeffs": [c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)],

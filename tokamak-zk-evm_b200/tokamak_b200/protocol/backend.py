@@ -53,6 +53,14 @@ class GpuTable:
         self.ctx.dev_free(tmp)
         return out
 
+    def mont_bytes_host(self):
+        """The table exactly as it sits on the device: x || y, 48-byte little-endian Montgomery coordinates -- the
+        `ffjs-g1-affine-96` encoding of the TZBWASM1 CRS container (protocol/crs_io.py)."""
+        n = self.rows * self.cols
+        out = np.empty((n, 12), dtype=np.uint64)
+        self.ctx.d2h(out, self.device_ptr())
+        return out
+
     def close(self):
         if self.h:
             self.ctx.lib.tkm_crs_free(self.ctx.h, self.h)
@@ -132,6 +140,16 @@ class GpuBackend:
         pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
         h = ctypes.c_void_p()
         check(self.ctx.lib.tkm_crs_upload(self.ctx.h, _vp(pts), rows, cols, ctypes.byref(h)))
+        return GpuTable(self.ctx, h, rows, cols)
+
+    def table_from_mont_bytes(self, data, rows, cols):
+        """Upload points that are already in the device layout (Montgomery little-endian, e.g. a TZBWASM1 CRS section read
+        through a memory map): one H2D copy, no conversion."""
+        arr = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        if arr.nbytes != rows * cols * 96:
+            raise ValueError("table size mismatch")
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.tkm_crs_upload_mont(self.ctx.h, _vp(arr), rows, cols, ctypes.byref(h)))
         return GpuTable(self.ctx, h, rows, cols)
 
     def commit(self, table, poly):

@@ -49,41 +49,43 @@ class Mixer:
         return Mixer(r(0), r(1), r(2), r(3), [r(4), r(5), r(6), 0], [r(7), r(8), r(9), 0], [r(10), r(11)], [r(12), r(13)], r(14), r(15), r(16))
 
 
-def comb(*terms):
-    """poly_comb! (prove/src/lib.rs:30-38): sum_k c_k * p_k."""
-    c, p = terms[0]
-    acc = p * (c % R_MOD)
-    for c, p in terms[1:]:
-        acc = acc + p * (c % R_MOD)
+def _lincomb(terms):
+    """sum of c * X^sx * Y^sy * p over terms (c, p, sx, sy): one fused pass where the backend's polynomial type offers
+    `lincomb` (tkm_poly_lincomb on the device), else the reference's chain of scalings, shifts and additions."""
+    p0 = terms[0][1]
+    if hasattr(type(p0), "lincomb"):
+        return type(p0).lincomb([(c % R_MOD, p, sx, sy) for c, p, sx, sy in terms])
+    acc = None
+    for c, p, sx, sy in terms:
+        t = (p.mul_monomial(sx, sy) if (sx or sy) else p) * (c % R_MOD)
+        acc = t if acc is None else acc + t
     return acc
 
 
+def comb(*terms):
+    """poly_comb! (prove/src/lib.rs:30-38): sum_k c_k * p_k."""
+    return _lincomb([(c, p, 0, 0) for c, p in terms])
+
+
 def mul_by_x_minus_one(p):
-    return p.mul_monomial(1, 0) - p
+    return _lincomb([(1, p, 1, 0), (R_MOD - 1, p, 0, 0)])
 
 
 def mul_by_one_minus_x(p):
-    return p - p.mul_monomial(1, 0)
+    return _lincomb([(1, p, 0, 0), (R_MOD - 1, p, 1, 0)])
 
 
 def mul_by_linear_x(p, c):
-    return p * c[0] + p.mul_monomial(1, 0) * c[1]
+    return _lincomb([(c[0], p, 0, 0), (c[1], p, 1, 0)])
 
 
 def mul_by_linear_y(p, c):
-    return p * c[0] + p.mul_monomial(0, 1) * c[1]
+    return _lincomb([(c[0], p, 0, 0), (c[1], p, 0, 1)])
 
 
 def mul_by_term9(p, rB_X, rB_Y, t_mi_eval, t_smax_eval):
     const = (t_mi_eval * rB_X[0] + t_smax_eval * rB_Y[0]) % R_MOD
-    return p * const + p.mul_monomial(1, 0) * (t_mi_eval * rB_X[1] % R_MOD) + p.mul_monomial(0, 1) * (t_smax_eval * rB_Y[1] % R_MOD)
-
-
-def _pow2(v):
-    r = 1
-    while r < v:
-        r <<= 1
-    return r
+    return _lincomb([(const, p, 0, 0), (t_mi_eval * rB_X[1] % R_MOD, p, 1, 0), (t_smax_eval * rB_Y[1] % R_MOD, p, 0, 1)])
 
 
 class Timings:
