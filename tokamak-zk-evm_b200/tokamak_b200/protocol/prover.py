@@ -88,6 +88,13 @@ def mul_by_term9(p, rB_X, rB_Y, t_mi_eval, t_smax_eval):
     return _lincomb([(const, p, 0, 0), (t_mi_eval * rB_X[1] % R_MOD, p, 1, 0), (t_smax_eval * rB_Y[1] % R_MOD, p, 0, 1)])
 
 
+def _pow2(v):
+    r = 1
+    while r < v:
+        r <<= 1
+    return r
+
+
 class Timings:
     def __init__(self):
         self.spans = {}
