@@ -290,6 +290,10 @@ int32_t tkm_event_time_end(tkm_ctx *ctx, float *out_ms);
 /* Duration (CUDA events on the context stream) of the most recent dominant-kernel launch: k_accumulate of the last MSM,
  * or all k_ntt_pass launches of the last (bi)NTT.  Used by bench.py for the per-kernel roofline. */
 int32_t tkm_kernel_time_last(tkm_ctx *ctx, float *out_ms);
+/* Work accounting of the most recent MSM accumulation pass: the number L of affine pair-tree levels it ran (0 = chained
+ * XYZZ additions only) and the entry counts n_0 .. n_L of the levels (n_l - n_{l+1} affine additions at level l; the
+ * n_L remaining entries go through XYZZ mixed additions).  bench.py's roofline counts the issued multiplications with it. */
+int32_t tkm_msm_tree_stats(tkm_ctx *ctx, uint32_t *out_levels, uint64_t out_counts[9]);
 /* The same for the fused expression kernel of the most recent tkm_polyexpr_eval (bench.py's poly_engine GB/s). */
 int32_t tkm_poly_kernel_time_last(tkm_ctx *ctx, float *out_ms);
 /* Kernel launches issued by this library on this context since creation. */

@@ -745,7 +745,7 @@ def test_poly_expr_fused_matches_coefficients(ctx, T):
 
 
 def test_polyexpr_program_entry_point(ctx, T):
-    """tkm_polyexpr_eval: the prover's p_comb shape (prove/src/lib.rs:2110-2146) on a 64 x 32 domain against the coefficient-
+    """tkm_polyexpr_eval: the prover's p_comb shape (prove/src/lib.rs:2110-2146) on a 128 x 64 domain against the coefficient-
     domain operators, shared leaves transformed once, constant-only / scale-by-one programs, and the reference's panics."""
     E = T.PolyExpr
     sx, sy = 32, 16
@@ -757,21 +757,22 @@ def test_polyexpr_program_entry_point(ctx, T):
     p3 = E.mul(E.poly(K0), E.sub(rg, E.mul(E.poly(r2), E.poly(f))))
     expr = E.weighted_sum([(1, p1), (kappa, p2), (kappa * kappa % P.R_MOD, p3)])
     l0 = ctx.launch_count()
-    fused = expr.evaluate_fused_with_domain(64, 32)
+    fused = expr.evaluate_fused_with_domain(128, 64)  # degree (31 + 62, 15 + 30): K0 * (r g - ..) is a triple product
     launches = ctx.launch_count() - l0
-    # 7 distinct leaves (r, g, f used more than once): 7 x (pad + forward biNTT) + ONE expression kernel + one inverse biNTT
-    assert launches <= 7 * 4 + 1 + 3, launches
+    # 11 leaf occurrences (degree bound: one find_degree each) but 7 distinct leaves (r, g, f are shared): 7 x (pad + two
+    # NTT passes) + ONE expression kernel + the two passes of the inverse biNTT -- not one pass per DAG node
+    assert launches <= 11 + 7 * 3 + 1 + 2, launches
     ref = expr.evaluate_coeffs()
-    ref.resize(64, 32)
-    assert fused.shape == (64, 32)
+    ref.resize(128, 64)
+    assert fused.shape == (128, 64)
     assert np.array_equal(fused.copy_coeffs(), ref.copy_coeffs())
     assert to_ints(E.scalar(5).evaluate_fused_with_domain(2, 2).copy_coeffs()) == [5, 0, 0, 0]
     assert np.array_equal(E.scale(1, E.poly(r)).evaluate_fused_with_domain(sx, sy).copy_coeffs(), r.copy_coeffs())
     assert to_ints(E.weighted_sum([]).evaluate_fused_with_domain(1, 1).copy_coeffs()) == [0]
     with pytest.raises(ValueError):
-        expr.evaluate_fused_with_domain(32, 32)  # too small for the degree
+        expr.evaluate_fused_with_domain(64, 64)  # too small for the degree
     with pytest.raises(ValueError):
-        expr.evaluate_fused_with_domain(48, 32)  # not a power of two
+        expr.evaluate_fused_with_domain(192, 64)  # not a power of two
     # raw entry point: malformed programs are rejected, not executed
     import ctypes
     hs = (ctypes.c_void_p * 1)(r.h)

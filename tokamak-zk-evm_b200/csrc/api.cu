@@ -190,6 +190,8 @@ int32_t tkm_ctx_create(int32_t device_ordinal, tkm_ctx **out) {
   TKM_CUDA(cudaEventCreate(&ctx->ev1));
   TKM_CUDA(cudaEventCreate(&ctx->kev0));
   TKM_CUDA(cudaEventCreate(&ctx->kev1));
+  TKM_CUDA(cudaMallocHost((void **)&ctx->tree_counts, 16 * sizeof(uint32_t)));
+  memset(ctx->tree_counts, 0, 16 * sizeof(uint32_t));
   TKM_CUDA(cudaEventCreate(&ctx->pev0));
   TKM_CUDA(cudaEventCreate(&ctx->pev1));
   // keep freed scratch in the stream-ordered pool instead of returning it to the driver
@@ -216,6 +218,7 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->kev0) cudaEventDestroy(ctx->kev0);
   if (ctx->kev1) cudaEventDestroy(ctx->kev1);
+  if (ctx->tree_counts) cudaFreeHost(ctx->tree_counts);
   if (ctx->pev0) cudaEventDestroy(ctx->pev0);
   if (ctx->pev1) cudaEventDestroy(ctx->pev1);
   if (ctx->side_stream) {
@@ -827,6 +830,14 @@ int32_t tkm_kernel_time_last(tkm_ctx *ctx, float *out_ms) {
   TKM_REQUIRE(ctx->kernel_timed, "no dominant-kernel launch has been timed on this context yet");
   TKM_CUDA(cudaEventSynchronize(ctx->kev1));
   TKM_CUDA(cudaEventElapsedTime(out_ms, ctx->kev0, ctx->kev1));
+  return TKM_OK;
+}
+int32_t tkm_msm_tree_stats(tkm_ctx *ctx, uint32_t *out_levels, uint64_t out_counts[9]) {
+  API_BEGIN
+  TKM_REQUIRE(out_levels && out_counts, "null out pointer");
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out_levels = ctx->tree_levels;
+  for (uint32_t l = 0; l < 9; l++) out_counts[l] = l <= ctx->tree_levels ? ctx->tree_counts[l] : 0;
   return TKM_OK;
 }
 int32_t tkm_poly_kernel_time_last(tkm_ctx *ctx, float *out_ms) {

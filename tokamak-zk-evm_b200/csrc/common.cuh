@@ -77,6 +77,9 @@ struct tkm_ctx {
   // are cached here and not in process-wide statics: a second context on another GPU must get its own shared-memory opt-in)
   bool ntt_attr_set[4] = {false, false, false, false};
   int acc_occ = 0, bits_occ = 0;
+  // entry counts of the affine pair tree's levels in the most recent MSM accumulation pass (pinned; written by async copies)
+  uint32_t *tree_counts = nullptr;  // [9]
+  uint32_t tree_levels = 0;
 };
 
 struct tkm_poly {

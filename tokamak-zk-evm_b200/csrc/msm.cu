@@ -153,6 +153,355 @@ __device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *src) {
   return p;
 }
 
+// ---------------------------------------------------------------- 3a. affine pair tree with batched inversion
+// The additions of one bucket form a chain acc += P in k_accumulate (XYZZ mixed additions, 10 products each).  They are
+// associative, so the same sum can be taken as a binary tree: level l pairs the entries (2t, 2t+1) of every bucket's run
+// of the sorted list and replaces them by their AFFINE sum -- lambda = (y2 - y1)/(x2 - x1), x3 = lambda^2 - x1 - x2,
+// y3 = lambda (x1 - x3) - y1: 2 products + 1 squaring + one inversion.  All additions of a level are independent, so
+// their denominators are inverted together with Montgomery's trick (3 products each): 5 products + 1 squaring per
+// addition instead of 10, and the trick's single inversion per batch is amortised over millions of additions by a
+// second batch level (k_tree_fwd2 / k_tree_inv / k_tree_bwd2).  Run-aligned pairing keeps every level a compact sorted
+// list: bucket b holds m_l(b) = ceil(count(b) / 2^l) entries at offset off_l[b] (exclusive scans of m_l, all levels
+// computed up front from the bucket counts), element j of level l+1 with t = j - off_{l+1}[b] is
+// in_l[off_l[b] + 2t] (+ in_l[off_l[b] + 2t + 1] when 2t + 1 < m_l(b)).  After L levels the short remaining runs go
+// through the chunked XYZZ accumulation below, which also absorbs any skew (hot buckets).  Exceptional pairs (P = Q:
+// tangent slope with denominator 2y; P = -Q: identity, kept as (0, 0); identity operands) are exact.
+// Thread t of T handles elements j = s*T + t, s < TREE_B: consecutive lanes touch consecutive elements (coalesced),
+// and the prefix-product chain of a thread runs over its strided set.
+constexpr uint32_t TREE_MAX_LEVELS = 8;
+constexpr int TREE_THREADS = 128;
+constexpr int TREE2_LEAVES = 256;        // thread products per block of the second batch level (a product tree in shared memory)
+constexpr int TREE3_LEAVES = 512;        // block products the single top block can take
+constexpr uint32_t TREE_MAX_T = TREE2_LEAVES * TREE2_LEAVES * TREE3_LEAVES;  // first-level threads two block tiers + the top block can serve
+
+struct TreeLevel {
+  // input of the level: level 0 reads the sorted digit list and gathers bases, deeper levels read the previous SoA output
+  const uint32_t *vals;      // level 0: base index | sign << 31 per sorted entry
+  const G1Affine *bases;     // level 0
+  const Fq *in_x, *in_y;     // level >= 1
+  const uint32_t *off_in;    // off_l[b], b <= nbuckets
+  const uint32_t *off_out;   // off_{l+1}[b]
+  const uint32_t *off_next;  // off_{l+2}[b] or null (no further level): keys of the next level are written by the apply pass
+  const uint32_t *keys_out;  // bucket of every output element
+  uint32_t *keys_next;
+  Fq *out_x, *out_y;
+  Fq *pref;                  // prefix products, one per output element
+  Fq *tot;                   // product of every thread's denominators
+  const Fq *inv_tot;         // their inverses (second batch level)
+  uint32_t nbuckets;
+  uint32_t T;                // threads of the first batch level (stride of the element assignment)
+  uint32_t B;                // elements per thread (steps of its prefix-product chain)
+  uint32_t level0;
+};
+
+struct TreePair {
+  G1Affine p1, p2;
+  uint32_t kind;  // 0: copy p1, 1: copy p2, 2: identity, 3: chord (d = x2 - x1), 4: tangent (d = 2 y1)
+  uint32_t b, tprime;
+};
+
+__device__ __forceinline__ Fq ldg_fq(const Fq *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+  Fq a;
+  a.v[0] = r0.x; a.v[1] = r0.y; a.v[2] = r0.z; a.v[3] = r0.w;
+  a.v[4] = r1.x; a.v[5] = r1.y; a.v[6] = r1.z; a.v[7] = r1.w;
+  a.v[8] = r2.x; a.v[9] = r2.y; a.v[10] = r2.z; a.v[11] = r2.w;
+  return a;
+}
+__device__ __forceinline__ void st_fq(Fq *p, const Fq &a) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  q[2] = make_uint4(a.v[8], a.v[9], a.v[10], a.v[11]);
+}
+
+// Operands of output element j and the case it falls in.  WITH_Y = false loads only what the denominator needs (the y
+// coordinates are fetched on demand in the rare cases that need them).
+template <bool WITH_Y>
+__device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePair &pr, Fq &d) {
+  const uint32_t b = L.keys_out[j];
+  const uint32_t o_in = L.off_in[b], m = L.off_in[b + 1] - o_in;
+  const uint32_t tp = j - L.off_out[b];
+  const uint32_t i = o_in + 2 * tp;
+  const bool partner = 2 * tp + 1 < m;
+  pr.b = b;
+  pr.tprime = tp;
+  if (L.level0) {
+    const uint32_t v1 = L.vals[i];
+    const G1Affine *q1 = L.bases + (v1 & 0x7fffffffu);
+    if (WITH_Y) {
+      pr.p1 = ldg_affine(q1);
+      if (v1 >> 31) pr.p1.y = pr.p1.y.neg();
+    } else {
+      pr.p1.x = ldg_fq(&q1->x);
+    }
+    if (partner) {
+      const uint32_t v2 = L.vals[i + 1];
+      const G1Affine *q2 = L.bases + (v2 & 0x7fffffffu);
+      if (WITH_Y) {
+        pr.p2 = ldg_affine(q2);
+        if (v2 >> 31) pr.p2.y = pr.p2.y.neg();
+      } else {
+        pr.p2.x = ldg_fq(&q2->x);
+      }
+    }
+  } else {
+    pr.p1.x = ldg_fq(L.in_x + i);
+    if (WITH_Y) pr.p1.y = ldg_fq(L.in_y + i);
+    if (partner) {
+      pr.p2.x = ldg_fq(L.in_x + i + 1);
+      if (WITH_Y) pr.p2.y = ldg_fq(L.in_y + i + 1);
+    }
+  }
+  d = Fq::one();
+  if (!partner) {
+    pr.kind = 0;
+    return;
+  }
+  const bool x_equal = pr.p1.x == pr.p2.x;
+  if (!x_equal && !pr.p1.x.is_zero() && !pr.p2.x.is_zero()) {  // the common case: no coordinate is needed beyond x
+    pr.kind = 3;
+    d = pr.p2.x - pr.p1.x;
+    return;
+  }
+  // rare: an operand may be the identity (0, 0), or the points share their x
+  if (!WITH_Y) {
+    if (L.level0) {
+      const uint32_t v1 = L.vals[i], v2 = L.vals[i + 1];
+      pr.p1.y = ldg_fq(&L.bases[v1 & 0x7fffffffu].y);
+      pr.p2.y = ldg_fq(&L.bases[v2 & 0x7fffffffu].y);
+      if (v1 >> 31) pr.p1.y = pr.p1.y.neg();
+      if (v2 >> 31) pr.p2.y = pr.p2.y.neg();
+    } else {
+      pr.p1.y = ldg_fq(L.in_y + i);
+      pr.p2.y = ldg_fq(L.in_y + i + 1);
+    }
+  }
+  if (pr.p1.is_identity()) {
+    pr.kind = 1;
+  } else if (pr.p2.is_identity()) {
+    pr.kind = 0;
+  } else if (!x_equal) {
+    pr.kind = 3;
+    d = pr.p2.x - pr.p1.x;
+  } else if (pr.p1.y == pr.p2.y && !pr.p1.y.is_zero()) {
+    pr.kind = 4;
+    d = pr.p1.y.dbl();
+  } else {
+    pr.kind = 2;  // P + (-P)
+  }
+}
+
+__global__ void __launch_bounds__(TREE_THREADS) k_tree_fwd(const __grid_constant__ TreeLevel L) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L.T) return;
+  const uint32_t n = L.off_out[L.nbuckets];
+  Fq acc = Fq::one();
+  for (uint32_t s = 0; s < L.B; s++) {
+    const uint64_t j = (uint64_t)s * L.T + t;
+    if (j >= n) break;
+    TreePair pr;
+    Fq d;
+    tree_load<false>(L, (uint32_t)j, pr, d);
+    st_fq(L.pref + j, acc);
+    if (pr.kind >= 3) acc = acc * d;
+  }
+  st_fq(L.tot + t, acc);
+}
+
+// Second batch level over the T thread products: a product tree per block of TREE2_LEAVES in shared memory (log depth: a
+// few product latencies instead of a serial chain), the block roots reduced the same way by ONE top block, whose single
+// thread-0 inversion (binary extended Euclid) is the only inversion of the whole level; the inverses flow back down the
+// same trees.  tree[LEAVES + i] = leaf i, tree[k] = tree[2k] * tree[2k+1]; going down, a node's slot is overwritten by its
+// inverse: inv(left) = inv(node) * right, inv(right) = inv(node) * left.
+template <int LEAVES>
+__device__ __forceinline__ void tree_up(Fq *tree, int tid) {
+  for (int w = LEAVES / 2; w >= 1; w >>= 1) {
+    __syncthreads();
+    if (tid < w) tree[w + tid] = tree[2 * (w + tid)] * tree[2 * (w + tid) + 1];
+  }
+  __syncthreads();
+}
+template <int LEAVES>
+__device__ __forceinline__ void tree_down(Fq *tree, int tid) {  // tree[1] holds the inverse of the root product on entry
+  for (int w = 1; w < LEAVES; w <<= 1) {
+    __syncthreads();
+    if (tid < w) {
+      const Fq iv = tree[w + tid], l = tree[2 * (w + tid)], r = tree[2 * (w + tid) + 1];
+      tree[2 * (w + tid)] = iv * r;
+      tree[2 * (w + tid) + 1] = iv * l;
+    }
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(TREE2_LEAVES) k_tree_l2_up(const Fq *__restrict__ tot, uint32_t T, Fq *__restrict__ blk) {
+  __shared__ Fq tree[2 * TREE2_LEAVES];
+  const int tid = threadIdx.x;
+  const uint32_t v = blockIdx.x * TREE2_LEAVES + tid;
+  tree[TREE2_LEAVES + tid] = v < T ? ldg_fq(tot + v) : Fq::one();
+  tree_up<TREE2_LEAVES>(tree, tid);
+  if (tid == 0) st_fq(blk + blockIdx.x, tree[1]);
+}
+__global__ void __launch_bounds__(TREE3_LEAVES) k_tree_l3(Fq *__restrict__ blk, uint32_t nblk) {  // in place: products -> inverses
+  __shared__ Fq tree[2 * TREE3_LEAVES];
+  const int tid = threadIdx.x;
+  tree[TREE3_LEAVES + tid] = (uint32_t)tid < nblk ? blk[tid] : Fq::one();
+  tree_up<TREE3_LEAVES>(tree, tid);
+  if (tid == 0) tree[1] = tree[1].inv_bgcd();
+  tree_down<TREE3_LEAVES>(tree, tid);
+  if ((uint32_t)tid < nblk) st_fq(blk + tid, tree[TREE3_LEAVES + tid]);
+}
+// (inv_tot may alias tot: a block reads its own segment before the first barrier and writes it after the last)
+__global__ void __launch_bounds__(TREE2_LEAVES) k_tree_l2_down(const Fq *tot, const Fq *blk_inv, uint32_t T, Fq *inv_tot) {
+  __shared__ Fq tree[2 * TREE2_LEAVES];
+  const int tid = threadIdx.x;
+  const uint32_t v = blockIdx.x * TREE2_LEAVES + tid;
+  tree[TREE2_LEAVES + tid] = v < T ? tot[v] : Fq::one();
+  tree_up<TREE2_LEAVES>(tree, tid);
+  if (tid == 0) tree[1] = blk_inv[blockIdx.x];
+  tree_down<TREE2_LEAVES>(tree, tid);
+  if (v < T) st_fq(inv_tot + v, tree[TREE2_LEAVES + tid]);
+}
+
+__global__ void __launch_bounds__(TREE_THREADS) k_tree_apply(const __grid_constant__ TreeLevel L) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L.T) return;
+  const uint32_t n = L.off_out[L.nbuckets];
+  uint32_t cnt = 0;
+  while (cnt < L.B && (uint64_t)cnt * L.T + t < n) cnt++;
+  if (!cnt) return;
+  Fq run = ldg_fq(L.inv_tot + t);
+  for (uint32_t s = cnt; s-- > 0;) {
+    const uint32_t j = (uint32_t)((uint64_t)s * L.T + t);
+    TreePair pr;
+    Fq d;
+    tree_load<true>(L, j, pr, d);
+    G1Affine r;
+    if (pr.kind >= 3) {
+      const Fq dinv = run * ldg_fq(L.pref + j);
+      run = run * d;
+      Fq num;
+      if (pr.kind == 3) {
+        num = pr.p2.y - pr.p1.y;
+      } else {
+        const Fq xx = pr.p1.x.sqr();
+        num = xx.dbl() + xx;
+      }
+      const Fq lam = num * dinv;
+      r.x = lam.sqr() - pr.p1.x - pr.p2.x;
+      r.y = lam * (pr.p1.x - r.x) - pr.p1.y;
+    } else if (pr.kind == 0) {
+      r = pr.p1;
+    } else if (pr.kind == 1) {
+      r = pr.p2;
+    } else {
+      r = G1Affine::identity();
+    }
+    st_fq(L.out_x + j, r.x);
+    st_fq(L.out_y + j, r.y);
+    if (L.off_next && !(pr.tprime & 1)) L.keys_next[L.off_next[pr.b] + (pr.tprime >> 1)] = pr.b;
+  }
+}
+
+// Bucket counts of the sorted key list (run boundaries), then all levels' offsets in one three-phase scan:
+// off[l][b] = sum_{b' < b} ceil(count(b') / 2^l), b <= nbuckets.
+__global__ void __launch_bounds__(256) k_run_bounds(const uint32_t *__restrict__ keys, size_t M, uint32_t nbuckets, uint32_t *__restrict__ start,
+                                                    uint32_t *__restrict__ end) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t k = keys[i];
+    if (k >= nbuckets) continue;  // zero digits (trash key, sorted last)
+    if (i == 0 || keys[i - 1] != k) start[k] = (uint32_t)i;
+    if (i + 1 == M || keys[i + 1] != k) end[k] = (uint32_t)i + 1;
+  }
+}
+constexpr uint32_t SCAN_ITEMS = 16, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+__device__ __forceinline__ uint32_t tree_len(uint32_t cnt, uint32_t l) { return (cnt + (1u << l) - 1) >> l; }
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t *__restrict__ start, const uint32_t *__restrict__ end, uint32_t nbuckets,
+                                                                uint32_t levels, uint32_t ntiles, uint32_t *__restrict__ tile_sums) {
+  __shared__ uint32_t sh[SCAN_THREADS / 32];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  for (uint32_t l = 0; l < levels; l++) {
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
+      const uint32_t b = base + k;
+      if (b < nbuckets) sum += tree_len(end[b] - start[b], l);
+    }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (uint32_t w = 0; w < SCAN_THREADS / 32; w++) tot += sh[w];
+      tile_sums[l * ntiles + blockIdx.x] = tot;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t *__restrict__ tile_sums, uint32_t ntiles, uint32_t levels) {
+  // one block per level; exclusive scan of the tile sums in place (ntiles is a few thousand)
+  __shared__ uint32_t sh[1024];
+  const uint32_t l = blockIdx.x;
+  if (l >= levels) return;
+  uint32_t *a = tile_sums + l * ntiles;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < ntiles ? a[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+      const uint32_t add = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < ntiles) a[i] = carry + sh[threadIdx.x] - v;
+    carry += sh[1023];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t *__restrict__ start, const uint32_t *__restrict__ end, uint32_t nbuckets,
+                                                            uint32_t levels, uint32_t ntiles, const uint32_t *__restrict__ tile_sums,
+                                                            uint32_t *__restrict__ off /* [levels][nbuckets + 1] */) {
+  __shared__ uint32_t sh[SCAN_THREADS];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  for (uint32_t l = 0; l < levels; l++) {
+    uint32_t v[SCAN_ITEMS], sum = 0;
+    for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
+      const uint32_t b = base + k;
+      v[k] = b < nbuckets ? tree_len(end[b] - start[b], l) : 0;
+      sum += v[k];
+    }
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < SCAN_THREADS; d <<= 1) {
+      const uint32_t add = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    uint32_t run = tile_sums[l * ntiles + blockIdx.x] + sh[threadIdx.x] - sum;
+    uint32_t *o = off + (size_t)l * (nbuckets + 1);
+    for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
+      const uint32_t b = base + k;
+      if (b <= nbuckets) o[b] = run;  // index nbuckets receives the total
+      run += v[k];
+    }
+    __syncthreads();
+  }
+}
+// keys of level 1: every even-position entry of a level-0 run names its bucket at off_1[b] + t/2
+__global__ void __launch_bounds__(256) k_tree_keys1(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off0, const uint32_t *__restrict__ off1,
+                                                    uint32_t nbuckets, uint32_t *__restrict__ keys1) {
+  const size_t n0 = off0[nbuckets];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n0; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t b = keys[i];
+    const uint32_t t = (uint32_t)i - off0[b];
+    if (!(t & 1)) keys1[off1[b] + (t >> 1)] = b;
+  }
+}
+
 constexpr int ACC_THREADS = 128;
 // Resident CTAs per SM the accumulation kernel is compiled for (register cap 168 at 3).  Overridable for the occupancy
 // probe of scripts/ubench (a mixed-addition stream alone is 3 % faster at 2 CTAs/SM with 206 registers).
@@ -160,29 +509,45 @@ constexpr int ACC_THREADS = 128;
 #define TKM_ACC_MIN_BLOCKS 3
 #endif
 
+// DIRECT = false: entry i is the base vals[i] (sign in bit 31) gathered from `bases`.  DIRECT = true: entry i is the affine
+// point (px[i], py[i]) left by the pair tree, and the list length is read from *n_ptr (the launch is sized for its bound).
+template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, TKM_ACC_MIN_BLOCKS) k_accumulate(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                            size_t M, uint32_t chunk, const G1Affine *__restrict__ bases,
+                                                           const Fq *__restrict__ px, const Fq *__restrict__ py, const uint32_t *__restrict__ n_ptr,
                                                            uint32_t invalid_key, G1Xyzz *__restrict__ buckets,
                                                            uint32_t *__restrict__ pkeys, G1Xyzz *__restrict__ ppts,
                                                            size_t nthreads) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= nthreads) return;
+  if (DIRECT) M = *n_ptr;
   size_t start = t * chunk, end = start + chunk;
   if (end > M) end = M;
+  if (start >= M) {  // beyond the actual list (DIRECT: the launch covers the upper bound): two padding entries
+    pkeys[2 * t] = invalid_key;
+    pkeys[2 * t + 1] = invalid_key;
+    store_xyzz(ppts + 2 * t, G1Xyzz::identity());
+    store_xyzz(ppts + 2 * t + 1, G1Xyzz::identity());
+    return;
+  }
+  auto fetch = [&](size_t i, uint32_t v) {
+    if (DIRECT) return G1Affine{ldg_fq(px + i), ldg_fq(py + i)};
+    return ldg_affine(bases + (v & 0x7fffffffu));
+  };
   uint32_t cur = keys[start];
   G1Xyzz acc = G1Xyzz::identity();
   bool first_run = true;
   // software pipeline: the next base is in flight while the current addition runs
-  uint32_t nk = cur, nv = vals[start];
-  G1Affine npt = (nk != invalid_key) ? ldg_affine(bases + (nv & 0x7fffffffu)) : G1Affine::identity();
+  uint32_t nk = cur, nv = DIRECT ? 0u : vals[start];
+  G1Affine npt = (nk != invalid_key) ? fetch(start, nv) : G1Affine::identity();
   for (size_t i = start; i < end; i++) {
     uint32_t k = nk, v = nv;
     G1Affine pt = npt;
     if (k == invalid_key && cur == invalid_key) break;  // sorted last: nothing but zero digits from here on
     if (i + 1 < end) {
       nk = keys[i + 1];
-      nv = vals[i + 1];
-      if (nk != invalid_key) npt = ldg_affine(bases + (nv & 0x7fffffffu));
+      nv = DIRECT ? 0u : vals[i + 1];
+      if (nk != invalid_key) npt = fetch(i + 1, nv);
     }
     if (k != cur) {
       if (first_run) {
@@ -551,22 +916,148 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
                                            ctx->stream));
   ctx->launches += 4;  // cub's histogram + onesweep passes (approximate; they are library launches)
 
+  // ---- affine pair tree (see "3a"): L levels of run-aligned pairwise affine additions with batched inversion, when the
+  // buckets are deep enough to pay for the per-level fixed cost
+  uint32_t L = 0;
+  {
+    const double avg = (double)M / (double)m.nbuckets;  // entries per bucket
+    if (avg >= 16.0 && M >= ((size_t)1 << 24)) {  // below ~16 M entries (2^20 points) the levels' fixed cost (one inversion latency each) eats the saving
+      while ((8u << (L + 1)) <= avg && L < TREE_MAX_LEVELS) L++;  // leaves runs of 8..16 entries for the XYZZ pass (measured best at 2^22)
+    }
+    if (const char *e = getenv("TKM_MSM_TREE_LEVELS")) {  // developer knob (0 = chained XYZZ additions only)
+      const uint32_t v = (uint32_t)atoi(e);
+      L = v <= TREE_MAX_LEVELS ? v : TREE_MAX_LEVELS;
+    }
+  }
+  Scratch<uint32_t> t_start, t_end, t_off, t_tiles, t_keys[2];
+  Scratch<Fq> t_x[2], t_y[2], t_pref, t_tot, t_invtot, t_tot2, t_tot3;
+  const uint32_t nb = m.nbuckets;
+  auto bound = [&](uint32_t l) { return (size_t)((M + ((size_t)1 << l) - 1) >> l) + nb; };  // >= entries of level l
+  TKM_CUDA(cudaEventRecord(ctx->kev0, ctx->stream));
+  if (L > 0) {
+    if (bound(1) + nb >= 0xffffffffull) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM too large for the 32-bit element indices of the pair tree");
+    const uint32_t levels = L + 1;
+    TKM_TRY(t_start.alloc(ctx, nb));
+    TKM_TRY(t_end.alloc(ctx, nb));
+    TKM_TRY(t_off.alloc(ctx, (size_t)levels * (nb + 1)));
+    const uint32_t ntiles = (nb + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    TKM_TRY(t_tiles.alloc(ctx, (size_t)levels * ntiles));
+    TKM_CUDA(cudaMemsetAsync(t_start.p, 0, (size_t)nb * 4, ctx->stream));
+    TKM_CUDA(cudaMemsetAsync(t_end.p, 0, (size_t)nb * 4, ctx->stream));
+    k_run_bounds<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, M, nb, t_start.p, t_end.p);
+    TKM_TRY(launch_check(ctx, "k_run_bounds"));
+    k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(t_start.p, t_end.p, nb, levels, ntiles, t_tiles.p);
+    TKM_TRY(launch_check(ctx, "k_scan_tile_sums"));
+    k_scan_tiles<<<levels, 1024, 0, ctx->stream>>>(t_tiles.p, ntiles, levels);
+    TKM_TRY(launch_check(ctx, "k_scan_tiles"));
+    k_scan_write<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(t_start.p, t_end.p, nb, levels, ntiles, t_tiles.p, t_off.p);
+    TKM_TRY(launch_check(ctx, "k_scan_write"));
+    for (int side = 0; side < 2; side++) {
+      const size_t cap = bound(1 + side);
+      if (side == 1 && L < 2) break;
+      TKM_TRY(t_x[side].alloc(ctx, cap));
+      TKM_TRY(t_y[side].alloc(ctx, cap));
+      TKM_TRY(t_keys[side].alloc(ctx, cap));
+    }
+    // threads per level: about eight resident waves (4 CTAs of 128 per SM) so that blocks are balanced dynamically
+    static const uint32_t tree_waves = getenv("TKM_MSM_TREE_WAVES") ? (uint32_t)atoi(getenv("TKM_MSM_TREE_WAVES")) : 8;  // developer knob
+    auto pick_T = [&](size_t cap_elems, uint32_t *B_out) {
+      size_t target = (size_t)ctx->sm_count * 4 * TREE_THREADS * (tree_waves ? tree_waves : 1);
+      if (target > TREE_MAX_T) target = TREE_MAX_T;
+      size_t B = (cap_elems + target - 1) / target;
+      if (B < 8) B = 8;
+      *B_out = (uint32_t)B;
+      return (cap_elems + B - 1) / B;
+    };
+    size_t T1 = 0;  // the largest thread count of any level (the rounding of B makes it non-monotonic in the level)
+    for (uint32_t l = 0; l < L; l++) {
+      uint32_t Bl;
+      const size_t Tl = pick_T(bound(l + 1), &Bl);
+      if (Tl > T1) T1 = Tl;
+    }
+    TKM_TRY(t_pref.alloc(ctx, bound(1)));
+    TKM_TRY(t_tot.alloc(ctx, T1));
+    TKM_TRY(t_invtot.alloc(ctx, T1));
+    TKM_TRY(t_tot2.alloc(ctx, (T1 + TREE2_LEAVES - 1) / TREE2_LEAVES));
+    TKM_TRY(t_tot3.alloc(ctx, (T1 + TREE2_LEAVES * TREE2_LEAVES - 1) / (TREE2_LEAVES * TREE2_LEAVES)));
+    auto off = [&](uint32_t l) { return t_off.p + (size_t)l * (nb + 1); };
+    k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, t_keys[0].p);
+    TKM_TRY(launch_check(ctx, "k_tree_keys1"));
+    for (uint32_t l = 0; l < L; l++) {
+      const int o = l & 1, i = o ^ 1;  // level l+1 lands in side o; level l (l >= 1) sits in side i
+      TreeLevel tl;
+      memset(&tl, 0, sizeof tl);
+      tl.level0 = l == 0;
+      tl.vals = vals_s.p;
+      tl.bases = in.bases;
+      tl.in_x = l ? t_x[i].p : nullptr;
+      tl.in_y = l ? t_y[i].p : nullptr;
+      tl.off_in = off(l);
+      tl.off_out = off(l + 1);
+      tl.off_next = l + 2 <= L ? off(l + 2) : nullptr;
+      tl.keys_out = t_keys[o].p;
+      tl.keys_next = t_keys[i].p;
+      tl.out_x = t_x[o].p;
+      tl.out_y = t_y[o].p;
+      tl.pref = t_pref.p;
+      tl.tot = t_tot.p;
+      tl.inv_tot = t_invtot.p;
+      tl.nbuckets = nb;
+      uint32_t B;
+      const size_t T = pick_T(bound(l + 1), &B);
+      const uint32_t nblk = (uint32_t)((T + TREE2_LEAVES - 1) / TREE2_LEAVES);
+      tl.T = (uint32_t)T;
+      tl.B = B;
+      const unsigned g1 = (unsigned)((T + TREE_THREADS - 1) / TREE_THREADS);
+      k_tree_fwd<<<g1, TREE_THREADS, 0, ctx->stream>>>(tl);
+      TKM_TRY(launch_check(ctx, "k_tree_fwd"));
+      // second batch level: products of 256 thread products per block, then (when there are more than 512 of those) a
+      // second block tier, the top block with the level's only inversion, and back down
+      k_tree_l2_up<<<nblk, TREE2_LEAVES, 0, ctx->stream>>>(t_tot.p, (uint32_t)T, t_tot2.p);
+      TKM_TRY(launch_check(ctx, "k_tree_l2_up"));
+      if (nblk <= (uint32_t)TREE3_LEAVES) {
+        k_tree_l3<<<1, TREE3_LEAVES, 0, ctx->stream>>>(t_tot2.p, nblk);
+        TKM_TRY(launch_check(ctx, "k_tree_l3"));
+      } else {
+        const uint32_t nblk2 = (nblk + TREE2_LEAVES - 1) / TREE2_LEAVES;
+        k_tree_l2_up<<<nblk2, TREE2_LEAVES, 0, ctx->stream>>>(t_tot2.p, nblk, t_tot3.p);
+        TKM_TRY(launch_check(ctx, "k_tree_l2_up"));
+        k_tree_l3<<<1, TREE3_LEAVES, 0, ctx->stream>>>(t_tot3.p, nblk2);
+        TKM_TRY(launch_check(ctx, "k_tree_l3"));
+        k_tree_l2_down<<<nblk2, TREE2_LEAVES, 0, ctx->stream>>>(t_tot2.p, t_tot3.p, nblk, t_tot2.p);
+        TKM_TRY(launch_check(ctx, "k_tree_l2_down"));
+      }
+      k_tree_l2_down<<<nblk, TREE2_LEAVES, 0, ctx->stream>>>(t_tot.p, t_tot2.p, (uint32_t)T, t_invtot.p);
+      TKM_TRY(launch_check(ctx, "k_tree_l2_down"));
+      k_tree_apply<<<g1, TREE_THREADS, 0, ctx->stream>>>(tl);
+      TKM_TRY(launch_check(ctx, "k_tree_apply"));
+    }
+    // per-level entry counts for bench.py's work accounting (read back lazily by tkm_msm_tree_stats)
+    ctx->tree_levels = L;
+    for (uint32_t l = 0; l <= L; l++)
+      TKM_CUDA(cudaMemcpyAsync(ctx->tree_counts + l, off(l) + nb, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    ctx->tree_levels = 0;
+  }
+  const int fin = (L & 1) ? 0 : 1;  // side holding level L (L >= 1)
+  const size_t Macc = L ? bound(L) : M;
+
   // Chunk length.  Every thread does the same amount of work (one chunk), so the launch runs in lock-step waves of
   // `cap` resident threads: pick the number of waves for chunks of at most ~256 entries (2 partial-list entries per chunk:
   // longer chunks shrink the segmented-reduction levels), then size the chunk so that the waves are full.
   int &occ = ctx->acc_occ;  // per context = per device
   if (!occ) {
-    TKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate, ACC_THREADS, 0));
+    TKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accumulate<false>, ACC_THREADS, 0));
     if (occ < 1) occ = 1;
   }
   const size_t cap = (size_t)ctx->sm_count * occ * ACC_THREADS;
   uint32_t target = 256;
   if (const char *e = getenv("TKM_MSM_CHUNK")) target = (uint32_t)atoi(e);  // developer knob
   if (target < 8) target = 8;
-  const size_t waves = (M + cap * target - 1) / (cap * target);
-  uint32_t chunk = (uint32_t)((M + waves * cap - 1) / (waves * cap));
+  const size_t waves = (Macc + cap * target - 1) / (cap * target);
+  uint32_t chunk = (uint32_t)((Macc + waves * cap - 1) / (waves * cap));
   if (chunk < 8) chunk = 8;
-  const size_t T = (M + chunk - 1) / chunk;
+  const size_t T = (Macc + chunk - 1) / chunk;
   size_t P = 2 * T;
   Scratch<uint32_t> pk_a, pk_b;
   Scratch<G1Xyzz> pp_a, pp_b;
@@ -576,8 +1067,12 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   TKM_TRY(pk_b.alloc(ctx, P2));
   TKM_TRY(pp_b.alloc(ctx, P2));
   const unsigned acc_grid = (unsigned)((T + ACC_THREADS - 1) / ACC_THREADS);
-  TKM_CUDA(cudaEventRecord(ctx->kev0, ctx->stream));
-  k_accumulate<<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(keys_s.p, vals_s.p, M, chunk, in.bases, invalid, buckets, pk_a.p, pp_a.p, T);
+  if (L)
+    k_accumulate<true><<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(t_keys[fin].p, nullptr, Macc, chunk, nullptr, t_x[fin].p, t_y[fin].p,
+                                                                   t_off.p + (size_t)L * (nb + 1) + nb, invalid, buckets, pk_a.p, pp_a.p, T);
+  else
+    k_accumulate<false><<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(keys_s.p, vals_s.p, M, chunk, in.bases, nullptr, nullptr, nullptr, invalid, buckets,
+                                                                    pk_a.p, pp_a.p, T);
   TKM_CUDA(cudaEventRecord(ctx->kev1, ctx->stream));
   ctx->kernel_timed = true;
   TKM_TRY(launch_check(ctx, "k_accumulate"));

@@ -129,4 +129,5 @@ extern "C" {
                              consts32: *const u8, n_consts: u32, target_x: usize, target_y: usize, out: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_kernel_time_last(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_crs_upload_mont(ctx: *mut tkm_ctx, points96_mont: *const u8, rows: usize, cols: usize, out: *mut *mut tkm_crs) -> i32;
+    pub fn tkm_msm_tree_stats(ctx: *mut tkm_ctx, out_levels: *mut u32, out_counts: *mut u64) -> i32;
 }

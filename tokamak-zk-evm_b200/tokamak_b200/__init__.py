@@ -104,6 +104,18 @@ class Context:
         check(self.lib.tkm_kernel_time_last(self.h, ctypes.byref(ms)))
         return float(ms.value)
 
+    def poly_kernel_time_last(self):
+        ms = ctypes.c_float()
+        check(self.lib.tkm_poly_kernel_time_last(self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def msm_tree_stats(self):
+        """(L, [n_0 .. n_L]): affine pair-tree levels of the last MSM accumulation pass and their entry counts."""
+        lv = ctypes.c_uint32()
+        cnt = np.zeros(9, dtype=np.uint64)
+        check(self.lib.tkm_msm_tree_stats(self.h, ctypes.byref(lv), _vp(cnt)))
+        return int(lv.value), [int(c) for c in cnt[:lv.value + 1]]
+
     def microbench(self, kind):
         v = ctypes.c_double()
         check(self.lib.tkm_microbench(self.h, kind, ctypes.byref(v)))

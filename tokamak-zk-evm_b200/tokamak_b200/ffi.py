@@ -79,6 +79,7 @@ SIGNATURES = {
     "tkm_poly_axpby": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)],
     "tkm_poly_lincomb": [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)],
     "tkm_polyexpr_eval": [c_void_p, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_uint32, c_size_t, c_size_t, P(c_void_p)],
+    "tkm_msm_tree_stats": [c_void_p, P(c_uint32), c_void_p],
     "tkm_poly_kernel_time_last": [c_void_p, P(ctypes.c_float)],
     "tkm_poly_add_scalar": [c_void_p, c_void_p, c_void_p],
     "tkm_poly_mul": [c_void_p, c_void_p, c_void_p, P(c_void_p)],
