@@ -29,6 +29,18 @@ NTT_X, NTT_Y = 16384, 512
 NTT_BUTTERFLIES = NTT_X * NTT_Y * ((14 - 2) / 2 + (9 - 2) / 2 + 0.5)  # 83.9 M products per transform
 FR_MUL_WIDE_IMADS = 112  # Fr Montgomery product: 64 a*b + 48 reduction wide IMADs (r's two low limbs need no multiplier)
 WIDE_PER_MADD = 6 * 288 + 2 * 222 + 432  # XYZZ mixed addition: 6 products + 2 dedicated squarings + the fused two-product Y3
+WIDE_PER_AFFINE_ADD = 5 * 288 + 222      # affine pair-tree addition: 3 products of Montgomery's trick + lambda, lambda^2, lambda*(x1 - x3)
+
+
+def accumulation_work(ctx, entries_fallback):
+    """Issued wide IMADs of the last MSM's accumulation phase from the library's own counters (tkm_msm_tree_stats): affine
+    additions of the pair-tree levels (n_0 - n_L) plus XYZZ mixed additions of the n_L entries left for the chained pass."""
+    L, counts = ctx.msm_tree_stats()
+    if L == 0:
+        n0 = counts[0] if counts and counts[0] else entries_fallback
+        return n0 * WIDE_PER_MADD, {"tree_levels": 0, "mixed_additions": n0}
+    tree_adds = counts[0] - counts[L]
+    return tree_adds * WIDE_PER_AFFINE_ADD + counts[L] * WIDE_PER_MADD, {"tree_levels": L, "entries_per_level": counts, "affine_additions": tree_adds, "mixed_additions": counts[L]}
 METRIC = "BLS12-381 G1 MSM throughput at 2^22 points"
 UNIT = "Mpts/s"
 G1_GEN = (
@@ -386,19 +398,21 @@ def main():
                     acc_ms.append(ctx.kernel_time_last())
                 acc_ms = float(np.mean(acc_ms))
                 adds = n * W
-                # wide IMADs the kernel actually issues per mixed addition: 6 general products x 288 (144 a*b + 144 reduction)
-                # + 2 dedicated squarings x 222 (78 + 144) + the fused two-product Y3 (Fq::dot2: 288 + one reduction of 144);
-                # the nominal count of SURVEY 8d is 10 x 288 = 2880
-                wide_per_add = WIDE_PER_MADD
-                ach = adds * wide_per_add / (acc_ms * 1e-3)
+                # wide IMADs the accumulation phase actually issues, from the library's per-level entry counts: affine pair-tree
+                # additions x 1662 (5 products x 288 + 1 squaring x 222) + the chained XYZZ mixed additions of the remaining
+                # entries x 2604 (6 x 288 + 2 x 222 + the fused two-product Y3 x 432); SURVEY 8d's nominal count is 10 x 288 per addition
+                work, detail = accumulation_work(ctx, adds)
+                ach = work / (acc_ms * 1e-3)
                 peak = max(imad_wide, imad_wide_x)
                 line["roofline"] = {"bound": "int32", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T(32x32+64 IMAD.WIDE)/s", "frac": ach / peak,
                                     "traffic": NCU_TRAFFIC["k_accumulate"], "traffic_unit": "GB per launch (dram read+write, ncu --set full capture in profiles/)",
-                                    "algorithmic_gb": adds * 104 / 1e9, "kernel": "k_accumulate", "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_res,
-                                    "note": "MSM is integer-pipe bound (SURVEY.md 8d; the schema's hbm/tensor bounds do not describe it): "
-                                            "N*W mixed additions x 2604 issued wide IMADs (6 products x 288 + 2 squarings x 222 + one fused two-product Y3 x 432) per launch / k_accumulate's event-timed duration; "
-                                            "peak = best measured IMAD.WIDE.U32 stream on this GPU (64-bit-addend or carry-chain form)",
-                                    "whole_msm_frac": adds * wide_per_add / (ms_res * 1e-3) / peak,
+                                    "algorithmic_gb": adds * 104 / 1e9, "kernel": "accumulation phase: k_tree_fwd/k_tree_apply per level + k_accumulate", "kernel_ms": acc_ms,
+                                    "kernel_share_of_step": acc_ms / ms_res, "work": detail,
+                                    "note": "MSM is integer-pipe bound (SURVEY.md 8d; the schema's hbm/tensor bounds do not describe it): issued wide IMADs of the "
+                                            "bucket accumulation (affine pair-tree additions x 1662 + chained XYZZ mixed additions x 2604, counts from tkm_msm_tree_stats) "
+                                            "/ the phase's event-timed duration; peak = best measured IMAD.WIDE.U32 stream on this GPU (64-bit-addend or carry-chain form)",
+                                    "whole_msm_frac": work / (ms_res * 1e-3) / peak,
+                                    "useful_work_frac_vs_xyzz_only": adds * WIDE_PER_MADD / (acc_ms * 1e-3) / peak,
                                     # the schema's HBM view of the same kernel, for completeness: 104 algorithmic bytes per addition
                                     "hbm_view": {"bound": "hbm", "achieved": adds * 104 / (acc_ms * 1e-3) / 1e9, "peak": measured_peaks()[0], "unit": "GB/s",
                                                  "frac": adds * 104 / (acc_ms * 1e-3) / 1e9 / measured_peaks()[0]},
@@ -495,6 +509,7 @@ def main():
             step_strong()
         ms_strong, _, clocks_s, rs = timed(step_strong, max(3, min(args.steps, 10)))
         acc_s = ctx.kernel_time_last()
+        work_s, detail_s = accumulation_work(ctx, ns * msm_windows(ns)[1])  # this rank's counts; ranks differ by well under 1 %
         if world > 1:
             tt = torch.tensor([acc_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -506,12 +521,12 @@ def main():
             assert np.array_equal(rs, exp_s), f"2^{LOG_S} MSM over {world} rank(s) differs from (sum s_i k_i)*G"
             c_s, W_s = msm_windows(ns)
             peak_s = line.get("roofline", {}).get("peak")
-            work = ns * W_s * WIDE_PER_MADD
+            work = work_s
             line["msm_2p24_strong"] = {
                 "metric": "one 2^24-point G1 MSM, point ranges over N GPUs", "log2_points_total": LOG_S, "ranks": world, "points_per_rank": ns,
                 "ms": ms_strong, "value": (1 << LOG_S) / ms_strong / 1e3, "unit": UNIT, "scaling": "strong", "window_bits": c_s, "windows": W_s,
                 "checked": "combined result == (sum s_i k_i)*G over all ranks (known discrete logs)",
-                "roofline": {"bound": "int32", "kernel": "k_accumulate", "kernel_ms_max_over_ranks": acc_s, "achieved": work / (acc_s * 1e-3) / 1e12,
+                "roofline": {"bound": "int32", "kernel": "accumulation phase (pair tree + k_accumulate)", "kernel_ms_max_over_ranks": acc_s, "work": detail_s, "achieved": work / (acc_s * 1e-3) / 1e12,
                              "peak": peak_s, "unit": "T(32x32+64 IMAD.WIDE)/s per GPU", "frac": (work / (acc_s * 1e-3) / 1e12 / peak_s) if peak_s else None,
                              "whole_msm_frac": (work / (ms_strong * 1e-3) / 1e12 / peak_s) if peak_s else None},
                 "clocks": clocks_s}

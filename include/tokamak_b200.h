@@ -272,6 +272,27 @@ int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t o
 int32_t tkm_poly_commit_begin(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, int32_t *out_ticket);
 int32_t tkm_commit_end(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]);
 
+/* ---- multi-GPU (the reference pins device 0, libs/src/utils/mod.rs:90-96, so this is new surface) --------
+ * One context per GPU -- one process per GPU, or several contexts in one process.  NCCL (over NVLink/NVSwitch) is the
+ * plumbing and is loaded at run time; single-GPU use needs none of this.  Bootstrap like ncclCommInitRank: rank 0 obtains
+ * an id, hands it to every rank out of band (MPI, a file, torch.distributed, ...), and every rank calls tkm_comm_init
+ * (collective).  The sharded entry points are collective too: every rank of the communicator must call them. */
+#define TKM_COMM_ID_BYTES 128
+int32_t tkm_comm_unique_id(uint8_t out_id[TKM_COMM_ID_BYTES]);
+int32_t tkm_comm_init(tkm_ctx *ctx, const uint8_t id[TKM_COMM_ID_BYTES], int32_t rank, int32_t world);
+int32_t tkm_comm_destroy(tkm_ctx *ctx);
+int32_t tkm_comm_rank(tkm_ctx *ctx, int32_t *out_rank, int32_t *out_world);
+/* msm::msm over a point range per GPU: every rank passes its slice (device-resident, like tkm_msm_g1); the 96-byte partial
+ * sums are all-gathered (the only collective) and summed, and every rank receives the total. */
+int32_t tkm_msm_g1_sharded(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, const void *dev_bases_mont, size_t n_local,
+                           uint8_t out96[96]);
+/* _biNTT of an x_size x y_size polynomial sharded by rows.  Forward: dev_in = this rank's rows [x/G][y] (Montgomery form),
+ * dev_out = its column shard of the evaluations [x][y/G] (entry (k, l) is the value at (w_x^k, w_y^(rank*y/G + l))); local
+ * Y pass, one all-to-all of (x/G) x (y/G) tiles, local X pass.  Inverse: dev_in = column shard, dev_out = row shard of the
+ * coefficients.  Both buffers hold x*y/G elements and must not alias; the call is asynchronous on the context stream. */
+int32_t tkm_bintt_sharded(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t x_size, size_t y_size, int32_t dir,
+                          const uint8_t *coset_x32, const uint8_t *coset_y32);
+
 /* ---- host-side data loader (no device work) -------------------------------------------------------
  * Every "0x..." string of a JSON text, in file order, as 32-byte canonical little-endian scalars reduced mod r:
  * the HexString -> ScalarField::from_hex parsing of placementVariables.json / instance.json

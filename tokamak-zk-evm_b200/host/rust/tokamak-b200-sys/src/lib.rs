@@ -10,6 +10,7 @@ use std::os::raw::{c_char, c_void};
 
 pub const TKM_FORWARD: i32 = 0;
 pub const TKM_INVERSE: i32 = 1;
+pub const TKM_COMM_ID_BYTES: usize = 128;
 pub const TKM_OP_ADD: i32 = 0;
 pub const TKM_OP_SUB: i32 = 1;
 pub const TKM_OP_MUL: i32 = 2;
@@ -130,4 +131,12 @@ extern "C" {
     pub fn tkm_poly_kernel_time_last(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_crs_upload_mont(ctx: *mut tkm_ctx, points96_mont: *const u8, rows: usize, cols: usize, out: *mut *mut tkm_crs) -> i32;
     pub fn tkm_msm_tree_stats(ctx: *mut tkm_ctx, out_levels: *mut u32, out_counts: *mut u64) -> i32;
+    pub fn tkm_comm_unique_id(out_id: *mut u8) -> i32;
+    pub fn tkm_comm_init(ctx: *mut tkm_ctx, id: *const u8, rank: i32, world: i32) -> i32;
+    pub fn tkm_comm_destroy(ctx: *mut tkm_ctx) -> i32;
+    pub fn tkm_comm_rank(ctx: *mut tkm_ctx, out_rank: *mut i32, out_world: *mut i32) -> i32;
+    pub fn tkm_msm_g1_sharded(ctx: *mut tkm_ctx, dev_scalars: *const c_void, scalars_mont: i32, dev_bases_mont: *const c_void, n_local: usize,
+                              out96: *mut u8) -> i32;
+    pub fn tkm_bintt_sharded(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize, dir: i32,
+                             coset_x32: *const u8, coset_y32: *const u8) -> i32;
 }

@@ -93,6 +93,12 @@ SIGNATURES = {
     "tkm_poly_commit": [c_void_p, c_void_p, c_void_p, c_void_p],
     "tkm_poly_commit_begin": [c_void_p, c_void_p, c_void_p, P(c_int32)],
     "tkm_commit_end": [c_void_p, c_int32, c_void_p],
+    "tkm_comm_unique_id": [c_void_p],
+    "tkm_comm_init": [c_void_p, c_void_p, c_int32, c_int32],
+    "tkm_comm_destroy": [c_void_p],
+    "tkm_comm_rank": [c_void_p, P(c_int32), P(c_int32)],
+    "tkm_msm_g1_sharded": [c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p],
+    "tkm_bintt_sharded": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p, c_void_p],
     "tkm_host_parse_hex_scalars": [ctypes.c_char_p, c_size_t, c_void_p, c_size_t, P(c_size_t)],
     "tkm_host_parse_r1cs": [ctypes.c_char_p, c_size_t, P(c_uint32), P(c_uint32), P(c_size_t), c_void_p, c_void_p, c_void_p],
     "tkm_event_time_begin": [c_void_p],
