@@ -462,6 +462,82 @@ def main():
                                             "api": "tkm_bintt_host (replaces _biNTT with HostSlice in/out)"}
             ctx.dev_free(d_poly)
 
+        if rank == 0:
+            # ---- polynomial-engine kernels (HBM-bound: a few field operations per 32-byte element): achieved GB/s of each against
+            # the measured HBM peak.  Event-timed over the C-ABI call on device-resident polynomials at the prover's shapes;
+            # algorithmic bytes = operands read once + result written once.
+            hbm_p, _ = measured_peaks()
+            px, py = 8192, 512
+            npts = px * py
+            ctx.init_ntt_domain_for_size(NTT_X * NTT_Y)
+            mk = lambda seed, x_, y_: T.DensePolynomialExt.from_coeffs(ctx, random_scalars(seed, x_ * y_), x_, y_)
+            pa, pb, pc = mk(7001, px, py), mk(7002, px, py), mk(7003, px, py)
+            sc = [0x1234567 + (1 << 200), 0x7654321 + (1 << 199), 0xABCDEF + (1 << 198)]
+            eng = {}
+
+            fr_mul_peak = line.get("microbench", {}).get("fr_mul_per_s")
+
+            def timed_op(name, fn, bytes_moved, reps=5, note=None, muls_per_elem=0, elems=0):
+                fn()
+                ctx.sync()
+                l0_ = ctx.launch_count()
+                ctx.time_begin()
+                for _ in range(reps):
+                    keep = fn()
+                ms_ = ctx.time_end() / reps
+                eng[name] = {"ms": ms_, "algorithmic_gb": bytes_moved / 1e9, "achieved_gbs": bytes_moved / (ms_ * 1e-3) / 1e9,
+                             "frac_of_hbm": bytes_moved / (ms_ * 1e-3) / 1e9 / hbm_p, "launches": (ctx.launch_count() - l0_) // reps}
+                if muls_per_elem and fr_mul_peak:  # kernels with several products per element are bound by the Fr multiplier, not HBM
+                    eng[name]["fr_mul_frac"] = muls_per_elem * elems / (ms_ * 1e-3) / fr_mul_peak
+                    eng[name]["bound"] = "Fr multiplier (int32 pipe)" if eng[name]["fr_mul_frac"] > eng[name]["frac_of_hbm"] else "hbm"
+                if note:
+                    eng[name]["note"] = note
+                del keep
+
+            timed_op("k_lincomb (poly_comb!, 3 terms 8192x512)", lambda: T.DensePolynomialExt.lincomb([(sc[0], pa), (sc[1], pb), (sc[2], pc)]), 4 * npts * 32,
+                     muls_per_elem=3, elems=npts)
+            timed_op("k_lincomb (shifted helper: c0 p + c1 X p)", lambda: T.DensePolynomialExt.lincomb([(sc[0], pa, 0, 0), (sc[1], pa, 1, 0)]), (1 + 2) * npts * 32,
+                     note="one operand read (twice, second time from L2), result 16384x512", muls_per_elem=2, elems=npts)
+            timed_op("k_axpby (p + q)", lambda: pa + pb, 3 * npts * 32)
+            timed_op("k_scale_coeffs (scale_coeffs_x)", lambda: pa.scale_coeffs_x(sc[0]), 2 * npts * 32, muls_per_elem=1, elems=npts)
+            timed_op("k_row_dot/k_col_dot (eval at a point)", lambda: pa.eval(sc[0], sc[1]), npts * 32)
+            timed_op("k_vanish_qy/_qx (div_by_vanishing_opt c=4096 d=256)", lambda: pa.clone().div_by_vanishing_opt(4096, 256), (1 + 2 + 1 + 1) * npts * 32,
+                     note="includes the clone (the reference's &mut self): read+write clone, read, write Q_X, Q_Y/B traffic ~ N")
+            timed_op("k_ruffini_x/_y (div_by_ruffini)", lambda: pa.div_by_ruffini(sc[0], sc[1]), 2 * npts * 32)
+            d_t0, d_t1 = ctx.dev_alloc(npts * 32), ctx.dev_alloc(npts * 32)
+            T.check(lib.tkm_fr_vec_fill(h, T.fr_bytes(5)[1], d_t0, npts))
+            timed_op("k_transpose (4096 x 1024)", lambda: ctx.transpose_dev(d_t0, d_t1, 4096, 1024), 2 * npts * 32)
+            timed_op("k_vec_op (pointwise mul)", lambda: T.check(lib.tkm_fr_vec_op(h, 2, d_t0, d_t1, d_t1, npts)), 3 * npts * 32)
+            ctx.dev_free(d_t0)
+            ctx.dev_free(d_t1)
+            # the fused expression kernel on prove2's p_comb (7 leaves, domain 16384 x 512): kernel-only time from its own events
+            m_i, s_mx = 4096, 256
+            lv = [mk(7100 + k, m_i, s_mx // 2) for k in range(7)]  # triple products must fit the 16384 x 512 domain
+            r_, g_, f_, r1_, r2_, KL_, K0_ = lv
+            E = T.PolyExpr
+            rg = E.mul(E.poly(r_), E.poly(g_))
+            expr = E.weighted_sum([(1, E.mul(E.sub(E.poly(r_), E.scalar(1)), E.poly(KL_))),
+                                   (sc[0], E.mul_x_minus_one(E.sub(rg, E.mul(E.poly(r1_), E.poly(f_))))),
+                                   (sc[1], E.mul(E.poly(K0_), E.sub(rg, E.mul(E.poly(r2_), E.poly(f_)))))])
+            for _ in range(2):
+                res_ = expr.evaluate_fused_with_domain(NTT_X, NTT_Y)
+            ctx.sync()
+            t0_ = time.perf_counter()
+            res_ = expr.evaluate_fused_with_domain(NTT_X, NTT_Y)
+            ctx.sync()
+            whole_ms = (time.perf_counter() - t0_) * 1e3
+            kms_ = ctx.poly_kernel_time_last()
+            bytes_ = (7 + 1) * NTT_X * NTT_Y * 32
+            eng["k_polyexpr (p_comb, 7 leaves, 16384x512)"] = {"ms": kms_, "algorithmic_gb": bytes_ / 1e9, "achieved_gbs": bytes_ / (kms_ * 1e-3) / 1e9,
+                                                              "frac_of_hbm": bytes_ / (kms_ * 1e-3) / 1e9 / hbm_p, "launches": 1,
+                                                              "whole_evaluate_fused_ms": whole_ms, "bound": "Fr multiplier (int32 pipe)",
+                                                              "fr_mul_frac": (8 * NTT_X * NTT_Y / (kms_ * 1e-3) / fr_mul_peak) if fr_mul_peak else None,
+                                                              "note": "8 Fr products + 6 additions per element next to 256 B of traffic: the pointwise DAG of "
+                                                                      "PolyExpr::evaluate_on_domain as ONE kernel (the reference: ~12 passes with a fresh 256 MiB vector each); "
+                                                                      "whole call = 7 leaf pads + 7 forward biNTTs + this kernel + 1 inverse biNTT"}
+            del res_, lv, pa, pb, pc
+            line["poly_engine"] = {"peak_gbs": hbm_p, "kernels": eng}
+
         if rank == 0 and world == 1:
             # ---- CPU baseline beside it (N=1 only): the oracle port on the host cores, bounded sample, also the bit-exact check
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -37,3 +37,42 @@ pub fn msm_g1_bases(scalars: &[ScalarField], bases: &[G1serde]) -> G1serde {
     check(unsafe { sys::tkm_msm_g1_host(ctx(), scalars.as_ptr() as *const u8, bases.as_ptr() as *const u8, scalars.len(), out.0.as_mut_ptr()) });
     out
 }
+
+/// A second resident table for the sparse encoders (gamma_inv_o_inst, eta_inv_li_o_inter_alpha4_kj, delta_inv_li_o_prv;
+/// group_structures/mod.rs:361-394), rows x cols like the reference's boxed 2-D arrays, uploaded once from the archive.
+pub struct G1Table {
+    h: *mut sys::tkm_crs,
+    pub rows: usize,
+    pub cols: usize,
+}
+impl Drop for G1Table {
+    fn drop(&mut self) { unsafe { sys::tkm_crs_free(ctx(), self.h) }; }
+}
+impl G1Table {
+    pub fn upload(points: &[G1serde], rows: usize, cols: usize) -> Self {
+        assert_eq!(points.len(), rows * cols);
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::tkm_crs_upload(ctx(), points.as_ptr() as *const u8, rows, cols, &mut h) });
+        Self { h, rows, cols }
+    }
+    /// msm_g1_bases over gathered entries (encode_o_pub_fix_common / encode_o_pub_free_common / encode_statement_common,
+    /// :145-300): sum_k scalars[k] * table[idx[k]]; empty input gives the identity (:131-133).
+    pub fn msm_indexed(&self, scalars: &[ScalarField], idx: &[u32]) -> G1serde {
+        if scalars.len() != idx.len() { panic!("Mismatch between the numbers of bases and scalars"); }
+        let mut out = G1serde::zero();
+        if scalars.is_empty() { return out; }
+        unsafe {
+            let (mut ds, mut di, mut dt) = (std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut());
+            check(sys::tkm_crs_device_ptr(self.h, &mut dt, std::ptr::null_mut(), std::ptr::null_mut()));
+            check(sys::tkm_dev_alloc(ctx(), scalars.len() * 32, &mut ds));
+            check(sys::tkm_dev_alloc(ctx(), idx.len() * 4, &mut di));
+            check(sys::tkm_memcpy_h2d(ctx(), ds, scalars.as_ptr() as *const _, scalars.len() * 32));
+            check(sys::tkm_memcpy_h2d(ctx(), di, idx.as_ptr() as *const _, idx.len() * 4));
+            let st = sys::tkm_msm_g1_indexed(ctx(), ds, 0, dt, di, scalars.len(), out.0.as_mut_ptr());
+            sys::tkm_dev_free(ctx(), ds);
+            sys::tkm_dev_free(ctx(), di);
+            check(st);
+        }
+        out
+    }
+}
