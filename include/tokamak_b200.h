@@ -93,6 +93,13 @@ int32_t tkm_fr_suffix_product(tkm_ctx *ctx, const void *dev_in, void *dev_out, s
 int32_t tkm_fr_vec_reduce(tkm_ctx *ctx, int32_t op, const void *dev_a, const void *dev_b, size_t n, uint8_t out32[32]);
 /* outer_product_two_vecs (vector_operations/mod.rs:551-600): out[i*cols + j] = col[i] * row[j]. */
 int32_t tkm_fr_outer_product(tkm_ctx *ctx, const void *dev_col, const void *dev_row, void *dev_out, size_t rows, size_t cols);
+/* out[k] = base^k, k < n, in Montgomery form on the device (the power vectors behind scale_coeffs, the vanishing and
+ * permutation tables; resize_monomial_vec / extend_monomial_vec, vector_operations/mod.rs:674-693). */
+int32_t tkm_fr_powers(tkm_ctx *ctx, const uint8_t base32[32], void *dev_out, size_t n);
+/* dst[dst_idx[k]] = table[src_idx[k]] for k < n (u32 indices on the device, range-checked): the sparse overrides of the
+ * permutation evaluation tables s0, s1 (Permutation::to_poly, libs/src/iotools/mod.rs:419-455) without a host round trip. */
+int32_t tkm_fr_scatter_from_table(tkm_ctx *ctx, void *dev_dst, size_t dst_len, const void *dev_dst_idx, const void *dev_table, size_t table_len,
+                                  const void *dev_src_idx, size_t n);
 /* VecOps::transpose (vector_operations/mod.rs:139,168): rows x cols -> cols x rows, out != in. */
 int32_t tkm_fr_transpose(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t rows, size_t cols);
 /* Host-buffer forms of the same ops (HostSlice in, HostSlice out; canonical bytes). */

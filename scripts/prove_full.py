@@ -24,6 +24,14 @@ def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: 
     t = time.perf_counter()
     params, infos, r1cs = S.make_library(spec)
     pl, perm, inst = S.synthesize(params, infos, r1cs, small_value_fraction=0.5)
+    if be.name == "b200":
+        # the in-memory synthesizer output holds every placement's variables as an array of canonical limbs -- exactly what the
+        # library's native loader (tkm_host_parse_hex_scalars) returns for placementVariables.json -- not as Python integers
+        import numpy as np
+        from tokamak_b200.protocol import formats as F0
+
+        for p_ in pl:
+            p_.variables = F0.ScalarArray(np.frombuffer(b"".join(v.to_bytes(32, "little") for v in p_.variables), dtype=np.uint64).reshape(-1, 4))
     t_synth = time.perf_counter() - t
     log("synthetic circuit ready", t_synth)
     t = time.perf_counter()

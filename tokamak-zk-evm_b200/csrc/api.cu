@@ -8,6 +8,7 @@ namespace tkm {
 Fr root_of_unity_host(uint32_t log_n);
 int32_t domain_init(tkm_ctx *ctx, uint32_t log2_size);
 int32_t domain_release(tkm_ctx *ctx);
+int32_t fill_powers_public(tkm_ctx *ctx, Fr *out, const Fr &base, const Fr &scale, size_t count);
 
 // ---- single-point helpers (G1serde ops, group_structures/mod.rs:895-947) and fixed-base batch mul
 __global__ void k_g1_add_single(const G1Affine *a, const G1Affine *b, uint32_t *out_canonical) {
@@ -78,6 +79,18 @@ __global__ void __launch_bounds__(128) k_fixed_base_mul(const G1Affine *__restri
     r.y = r.y.from_mont();
     out_canonical[i] = r;
   }
+}
+
+__global__ void __launch_bounds__(256) k_check_indices(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, size_t n, size_t a_lim, size_t b_lim,
+                                                       uint32_t *__restrict__ bad) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    if (a[k] >= a_lim || b[k] >= b_lim) *bad = 1;
+}
+// dst[dst_idx[k]] = table[src_idx[k]]: the sparse overrides of an otherwise regular evaluation table
+// (Permutation::to_poly, libs/src/iotools/mod.rs:419-455).
+__global__ void __launch_bounds__(256) k_scatter_from_table(Fr *__restrict__ dst, const uint32_t *__restrict__ dst_idx, const Fr *__restrict__ table,
+                                                            const uint32_t *__restrict__ src_idx, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[dst_idx[k]] = table[src_idx[k]];
 }
 
 // ---- micro-benchmarks: dependent-free integer streams and field-op rates (ops/s over the whole GPU)
@@ -348,6 +361,31 @@ int32_t tkm_fr_vec_reduce(tkm_ctx *ctx, int32_t op, const void *a, const void *b
   TKM_TRY(vec_reduce(ctx, op, (const Fr *)a, (const Fr *)b, n, &r));
   fr_to_bytes_host(r, out32);
   return TKM_OK;
+}
+int32_t tkm_fr_powers(tkm_ctx *ctx, const uint8_t base32[32], void *dev_out, size_t n) {
+  API_BEGIN
+  TKM_REQUIRE(base32 && (dev_out || n == 0), "null argument");
+  if (n == 0) return TKM_OK;
+  return fill_powers_public(ctx, (Fr *)dev_out, fr_from_bytes_host(base32), Fr::one(), n);
+}
+int32_t tkm_fr_scatter_from_table(tkm_ctx *ctx, void *dev_dst, size_t dst_len, const void *dev_dst_idx, const void *dev_table, size_t table_len,
+                                  const void *dev_src_idx, size_t n) {
+  API_BEGIN
+  if (n == 0) return TKM_OK;
+  TKM_REQUIRE(dev_dst && dev_dst_idx && dev_table && dev_src_idx, "null argument");
+  // the index arrays live on the device: bounds are checked there before the scatter
+  Scratch<uint32_t> bad;
+  TKM_TRY(bad.alloc(ctx, 1));
+  TKM_CUDA(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
+  k_check_indices<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>((const uint32_t *)dev_dst_idx, (const uint32_t *)dev_src_idx, n, dst_len, table_len, bad.p);
+  TKM_TRY(launch_check(ctx, "k_check_indices"));
+  uint32_t h_bad = 0;
+  TKM_CUDA(cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  TKM_REQUIRE(!h_bad, "scatter index out of range");
+  k_scatter_from_table<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>((Fr *)dev_dst, (const uint32_t *)dev_dst_idx, (const Fr *)dev_table,
+                                                                                (const uint32_t *)dev_src_idx, n);
+  return launch_check(ctx, "k_scatter_from_table");
 }
 int32_t tkm_fr_outer_product(tkm_ctx *ctx, const void *col, const void *row, void *out, size_t rows, size_t cols) {
   API_BEGIN
@@ -626,6 +664,8 @@ int32_t tkm_crs_precompute(tkm_ctx *ctx, tkm_crs *crs, uint32_t window_bits) {
     TKM_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(crs->pre);
     crs->pre = nullptr;
+    if (crs->xpad) cudaFree(crs->xpad);
+    crs->xpad = nullptr;
   }
   TKM_TRY(crs_precompute(ctx, crs->d, crs->rows * crs->cols, window_bits, &crs->pre, &crs->pre_W));
   crs->pre_c = window_bits;
@@ -636,6 +676,7 @@ int32_t tkm_crs_free(tkm_ctx *ctx, tkm_crs *crs) {
   if (!crs) return TKM_OK;
   cudaStreamSynchronize(ctx->stream);
   if (crs->pre) cudaFree(crs->pre);
+  if (crs->xpad) cudaFree(crs->xpad);
   if (crs->owned && crs->d) cudaFree(crs->d);
   delete crs;
   return TKM_OK;

@@ -96,6 +96,10 @@ struct tkm_crs {
   bool owned = true;
   tkm::G1Affine *pre = nullptr;  // optional fixed-base tables [pre_W][rows*cols]: 2^(pre_c*w) * P
   uint32_t pre_c = 0, pre_W = 0;
+  // x coordinates alone in 64-byte slots (same index space as d, or as pre when tables exist): what the forward pass of the
+  // MSM's affine pair tree gathers.  Built on the first commitment against this CRS.
+  uint4 *xpad = nullptr;
+  bool xpad_for_pre = false;
 };
 
 namespace tkm {
@@ -179,7 +183,9 @@ struct MsmInput {
   const uint32_t *idx;  // optional gather indices into bases (rows must be 1)
   uint32_t pre_c = 0;       // fixed-base tables: window bits the tables were built for (0 = plain bases)
   uint32_t pre_stride = 0;  // fixed-base tables: points per table (table w starts at bases + w*pre_stride)
+  const uint4 *xpad = nullptr;  // optional: 64-byte x slots over the same index space as bases (see tkm_crs::xpad)
 };
+int32_t msm_build_xpad(tkm_ctx *ctx, const G1Affine *bases, size_t row_stride, size_t rows, size_t cols, uint32_t tables, size_t table_stride, uint4 *xpad);
 int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c, G1Affine **out_table, uint32_t *out_W);
 int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]);
 int32_t msm_run_async(tkm_ctx *ctx, const MsmInput &in, int32_t *out_ticket);

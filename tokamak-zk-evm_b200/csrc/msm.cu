@@ -178,6 +178,7 @@ struct TreeLevel {
   // input of the level: level 0 reads the sorted digit list and gathers bases, deeper levels read the previous SoA output
   const uint32_t *vals;      // level 0: base index | sign << 31 per sorted entry
   const G1Affine *bases;     // level 0
+  const uint4 *xpad;         // level 0, forward pass: the bases' x coordinates alone, one 64-byte slot each (one DRAM granule per gather)
   const Fq *in_x, *in_y;     // level >= 1
   const uint32_t *off_in;    // off_l[b], b <= nbuckets
   const uint32_t *off_out;   // off_{l+1}[b]
@@ -234,7 +235,7 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
       pr.p1 = ldg_affine(q1);
       if (v1 >> 31) pr.p1.y = pr.p1.y.neg();
     } else {
-      pr.p1.x = ldg_fq(&q1->x);
+      pr.p1.x = L.xpad ? ldg_fq(reinterpret_cast<const Fq *>(L.xpad + 4 * (size_t)(v1 & 0x7fffffffu))) : ldg_fq(&q1->x);
     }
     if (partner) {
       const uint32_t v2 = L.vals[i + 1];
@@ -243,7 +244,7 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
         pr.p2 = ldg_affine(q2);
         if (v2 >> 31) pr.p2.y = pr.p2.y.neg();
       } else {
-        pr.p2.x = ldg_fq(&q2->x);
+        pr.p2.x = L.xpad ? ldg_fq(reinterpret_cast<const Fq *>(L.xpad + 4 * (size_t)(v2 & 0x7fffffffu))) : ldg_fq(&q2->x);
       }
     }
   } else {
@@ -290,6 +291,23 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
     d = pr.p1.y.dbl();
   } else {
     pr.kind = 2;  // P + (-P)
+  }
+}
+
+// x coordinates of the bases an MSM touches, one 64-byte slot per base: the forward pass of level 0 gathers only x, and from
+// the 96-byte (x, y) entries a 48-byte x costs one or two 64-byte DRAM granules plus the neighbouring sector.
+__global__ void __launch_bounds__(256) k_tree_xpad(const G1Affine *__restrict__ bases, size_t row_stride, uint32_t rows, uint32_t cols, const uint32_t *__restrict__ gather,
+                                                   uint32_t tables, uint32_t table_stride, uint4 *__restrict__ xpad) {
+  // addresses the same index space as k_decompose's base indices: i*row_stride + j (or gather[k]) + w*table_stride
+  const size_t n = (size_t)rows * cols;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n * tables; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = e % n, w = e / n;
+    const size_t idx = (gather ? gather[k] : (k / cols) * row_stride + (k % cols)) + w * table_stride;
+    const uint4 *q = reinterpret_cast<const uint4 *>(&bases[idx].x);
+    uint4 *o = xpad + 4 * idx;
+    o[0] = __ldg(q);
+    o[1] = __ldg(q + 1);
+    o[2] = __ldg(q + 2);
   }
 }
 
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(TREE2_LEAVES) k_tree_l2_down(const Fq *tot, co
   if (v < T) st_fq(inv_tot + v, tree[TREE2_LEAVES + tid]);
 }
 
-__global__ void __launch_bounds__(TREE_THREADS) k_tree_apply(const __grid_constant__ TreeLevel L) {
+__global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_apply(const __grid_constant__ TreeLevel L) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L.T) return;
   const uint32_t n = L.off_out[L.nbuckets];
@@ -882,6 +900,13 @@ int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c,
   return TKM_OK;
 }
 
+int32_t msm_build_xpad(tkm_ctx *ctx, const G1Affine *bases, size_t row_stride, size_t rows, size_t cols, uint32_t tables, size_t table_stride, uint4 *xpad) {
+  if (rows * cols == 0) return TKM_OK;
+  k_tree_xpad<<<grid_for(rows * cols * tables, 256, ctx->sm_count), 256, 0, ctx->stream>>>(bases, row_stride, (uint32_t)rows, (uint32_t)cols, nullptr, tables,
+                                                                                         (uint32_t)table_stride, xpad);
+  return launch_check(ctx, "k_tree_xpad");
+}
+
 int32_t g1_to_mont_dev(tkm_ctx *ctx, const G1Affine *in, G1Affine *out, size_t n) {
   if (n == 0) return TKM_OK;
   k_g1_to_mont<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, n);
@@ -931,6 +956,8 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   }
   Scratch<uint32_t> t_start, t_end, t_off, t_tiles, t_keys[2];
   Scratch<Fq> t_x[2], t_y[2], t_pref, t_tot, t_invtot, t_tot2, t_tot3;
+  Scratch<uint4> t_xpad;
+  const uint4 *xpad = in.xpad;
   const uint32_t nb = m.nbuckets;
   auto bound = [&](uint32_t l) { return (size_t)((M + ((size_t)1 << l) - 1) >> l) + nb; };  // >= entries of level l
   TKM_CUDA(cudaEventRecord(ctx->kev0, ctx->stream));
@@ -980,6 +1007,12 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
     TKM_TRY(t_invtot.alloc(ctx, T1));
     TKM_TRY(t_tot2.alloc(ctx, (T1 + TREE2_LEAVES - 1) / TREE2_LEAVES));
     TKM_TRY(t_tot3.alloc(ctx, (T1 + TREE2_LEAVES * TREE2_LEAVES - 1) / (TREE2_LEAVES * TREE2_LEAVES)));
+    if (!xpad && !in.idx && !in.pre_c) {  // plain bases (dense or a strided rectangle): a per-call x table pays for itself over the windows
+      const size_t span = (in.rows - 1) * in.base_row_stride + in.cols;
+      TKM_TRY(t_xpad.alloc(ctx, span * 4));
+      TKM_TRY(msm_build_xpad(ctx, in.bases, in.base_row_stride, in.rows, in.cols, 1, 0, t_xpad.p));
+      xpad = t_xpad.p;
+    }
     auto off = [&](uint32_t l) { return t_off.p + (size_t)l * (nb + 1); };
     k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, t_keys[0].p);
     TKM_TRY(launch_check(ctx, "k_tree_keys1"));
@@ -990,6 +1023,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
       tl.level0 = l == 0;
       tl.vals = vals_s.p;
       tl.bases = in.bases;
+      tl.xpad = xpad;
       tl.in_x = l ? t_x[i].p : nullptr;
       tl.in_y = l ? t_y[i].p : nullptr;
       tl.off_in = off(l);

@@ -1066,6 +1066,28 @@ static int32_t commit_input(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, MsmIn
     in->pre_c = crs->pre_c;
     in->pre_stride = (uint32_t)(crs->rows * crs->cols);
   }
+  // the CRS's x-only table for the pair tree's forward pass: built once per CRS (and again if tables appear or vanish)
+  tkm_crs *mc = const_cast<tkm_crs *>(crs);
+  const bool want_pre = crs->pre != nullptr;
+  if (tx * ty >= ((size_t)1 << 20)) {  // only commitments large enough to run the tree need it
+    if (mc->xpad && mc->xpad_for_pre != want_pre) {
+      TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(mc->xpad);
+      mc->xpad = nullptr;
+    }
+    if (!mc->xpad) {
+      const size_t n_all = crs->rows * crs->cols, tables = want_pre ? crs->pre_W : 1;
+      if (cudaMalloc((void **)&mc->xpad, n_all * tables * 64) == cudaSuccess) {
+        int32_t st = msm_build_xpad(ctx, in->bases, crs->cols, crs->rows, crs->cols, (uint32_t)tables, n_all, mc->xpad);
+        if (st != TKM_OK) return st;
+        mc->xpad_for_pre = want_pre;
+      } else {
+        cudaGetLastError();  // not enough memory for the optional table: the tree falls back to gathering x from the points
+        mc->xpad = nullptr;
+      }
+    }
+    in->xpad = mc->xpad;
+  }
   return TKM_OK;
 }
 

@@ -139,4 +139,7 @@ extern "C" {
                               out96: *mut u8) -> i32;
     pub fn tkm_bintt_sharded(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize, dir: i32,
                              coset_x32: *const u8, coset_y32: *const u8) -> i32;
+    pub fn tkm_fr_powers(ctx: *mut tkm_ctx, base32: *const u8, dev_out: *mut c_void, n: usize) -> i32;
+    pub fn tkm_fr_scatter_from_table(ctx: *mut tkm_ctx, dev_dst: *mut c_void, dst_len: usize, dev_dst_idx: *const c_void, dev_table: *const c_void,
+                                     table_len: usize, dev_src_idx: *const c_void, n: usize) -> i32;
 }

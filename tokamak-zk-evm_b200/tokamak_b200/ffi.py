@@ -38,6 +38,8 @@ SIGNATURES = {
     "tkm_fr_transpose": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t],
     "tkm_fr_vec_reduce": [c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_fr_outer_product": [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t],
+    "tkm_fr_powers": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "tkm_fr_scatter_from_table": [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t],
     "tkm_fr_suffix_product": [c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_bintt": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p, c_void_p],
     "tkm_bintt_host": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p, c_void_p],

@@ -214,6 +214,50 @@ class GpuBackend:
         expr = E.weighted_sum([(1, p1), (kappa0 % R_MOD, p2), (kappa0 * kappa0 % R_MOD, p3)])
         return expr.evaluate_fused_with_domain(x_size, y_size, self.ctx)
 
+    # ---- the permutation polynomials s0, s1
+    def permutation_polys(self, permutation, m_i, s_max, omega_m_i, omega_s_max):
+        """Permutation::to_poly (libs/src/iotools/mod.rs:419-455) on the device: the identity tables w_x^row and w_y^col as
+        outer products of power vectors, the listed (row, col) -> (X, Y) entries scattered over them, one inverse biNTT each.
+        Nothing of size m_i * s_max is built on the host."""
+        ctx, lib = self.ctx, self.ctx.lib
+        n = m_i * s_max
+        from .. import fr_bytes
+
+        d_xp, d_yp = ctx.dev_alloc(m_i * 32), ctx.dev_alloc(s_max * 32)
+        d_one = ctx.dev_alloc(max(m_i, s_max) * 32)
+        check(lib.tkm_fr_powers(ctx.h, fr_bytes(omega_m_i)[1], d_xp, m_i))
+        check(lib.tkm_fr_powers(ctx.h, fr_bytes(omega_s_max)[1], d_yp, s_max))
+        check(lib.tkm_fr_vec_fill(ctx.h, fr_bytes(1)[1], d_one, max(m_i, s_max)))
+        d_s0, d_s1 = ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 32)
+        check(lib.tkm_fr_outer_product(ctx.h, d_xp, d_one, d_s0, m_i, s_max))
+        check(lib.tkm_fr_outer_product(ctx.h, d_one, d_yp, d_s1, m_i, s_max))
+        if len(permutation):
+            e = np.array([(p.row, p.col, p.X, p.Y) for p in permutation], dtype=np.int64)
+            if e[:, 0].max() >= m_i or e[:, 2].max() >= m_i or e[:, 1].max() >= s_max or e[:, 3].max() >= s_max or e.min() < 0:
+                raise ValueError("permutation entry out of range")
+            idx = e[:, 0] * s_max + e[:, 1]
+            _, last = np.unique(idx[::-1], return_index=True)  # a later entry for the same (row, col) overrides an earlier one
+            keep = len(idx) - 1 - last
+            k = len(keep)
+            d_idx, d_sx, d_sy = ctx.dev_alloc(k * 4), ctx.dev_alloc(k * 4), ctx.dev_alloc(k * 4)
+            ctx.h2d(d_idx, np.ascontiguousarray(idx[keep], dtype=np.uint32))
+            ctx.h2d(d_sx, np.ascontiguousarray(e[keep, 2], dtype=np.uint32))
+            ctx.h2d(d_sy, np.ascontiguousarray(e[keep, 3], dtype=np.uint32))
+            check(lib.tkm_fr_scatter_from_table(ctx.h, d_s0, n, d_idx, d_xp, m_i, d_sx, k))
+            check(lib.tkm_fr_scatter_from_table(ctx.h, d_s1, n, d_idx, d_yp, s_max, d_sy, k))
+            for p_ in (d_idx, d_sx, d_sy):
+                ctx.dev_free(p_)
+        out = []
+        for d in (d_s0, d_s1):
+            h = ctypes.c_void_p()
+            check(lib.tkm_poly_from_device(ctx.h, d, m_i, s_max, ctypes.byref(h)))
+            q = DensePolynomialExt(ctx, h)
+            check(lib.tkm_poly_ntt_inplace(ctx.h, q.h, 1, None, None))
+            out.append(q)
+        for p_ in (d_xp, d_yp, d_one, d_s0, d_s1):
+            ctx.dev_free(p_)
+        return out[0], out[1]
+
     # ---- prove1's recursion polynomial
     def recursion_poly(self, f, g, m_i, s_max):
         """r(X,Y) from the polynomials f, g without leaving the device (prove/src/lib.rs:1835-1880): evaluate both on the

@@ -139,9 +139,12 @@ class Prover:
         self.t_mi = self._vanishing_x(m_i)
         self.t_smax = self._vanishing_y(s_max)
         self.omega_m_i, self.omega_s_max = root_of_unity(m_i), root_of_unity(s_max)
-        s0_ev, s1_ev = qap.permutation_evals(permutation, m_i, s_max, self.omega_m_i, self.omega_s_max)
-        self.s0XY = backend.from_rou_evals(s0_ev, m_i, s_max)
-        self.s1XY = backend.from_rou_evals(s1_ev, m_i, s_max)
+        if hasattr(backend, "permutation_polys"):  # built on the device: no m_I x s_max table on the host
+            self.s0XY, self.s1XY = backend.permutation_polys(permutation, m_i, s_max, self.omega_m_i, self.omega_s_max)
+        else:
+            s0_ev, s1_ev = qap.permutation_evals(permutation, m_i, s_max, self.omega_m_i, self.omega_s_max)
+            self.s0XY = backend.from_rou_evals(s0_ev, m_i, s_max)
+            self.s1XY = backend.from_rou_evals(s1_ev, m_i, s_max)
         self.q = [None] * 4  # q0 (Q_AX part), q1, q2 (Q_CX part), q3
         self.cache = {}
         self.t.add("init.build.instance", time.perf_counter() - t1)
