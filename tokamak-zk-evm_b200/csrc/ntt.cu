@@ -89,6 +89,15 @@ constexpr uint32_t NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of tile data
 constexpr uint32_t NTT_MAX_LOGL = 10;
 constexpr uint32_t NTT_THREADS = 256;
 
+// Shared-memory index of tile element i.  Tiles whose batch lanes walk `outer` (C = 2 columns per 512-point row) are
+// accessed with power-of-two strides in the last butterfly stages and in the bit-reversed store; XOR-ing the folded
+// higher index bits into bits 1-2 spreads every such 8-lane group over the 8 bank groups of 16 bytes (a bijection within
+// each aligned block of 8 elements).  Tiles with C >= 8 keep the identity: their fastest index is the batch lane.
+template <bool SWZ>
+__device__ __forceinline__ uint32_t sidx(uint32_t i) {
+  if (!SWZ) return i;
+  return i ^ ((((i >> 3) ^ (i >> 5) ^ (i >> 7) ^ (i >> 9)) & 3u) << 1);
+}
 __device__ __forceinline__ Fr lds_fr(const uint4 *lo, const uint4 *hi, uint32_t i) {
   Fr r;
   uint4 a = lo[i], b = hi[i];
@@ -109,11 +118,13 @@ __device__ __forceinline__ Fr ldg_fr(const Fr *p) {
   return r;
 }
 
-template <bool INVERSE>
+template <bool INVERSE, bool SWZ>
 __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
   extern __shared__ uint4 smem[];
   const uint32_t L = 1u << p.logL, C = 1u << p.logC, TILE = L * C;
-  uint4 *d_lo = smem, *d_hi = smem + TILE, *t_lo = smem + 2 * TILE, *t_hi = t_lo + L;
+  // the two 128-bit planes sit one 16-byte slot apart modulo the 128-byte bank row (SWZ: lanes alternate between them)
+  uint4 *d_lo = smem, *d_hi = smem + TILE + (SWZ ? 1 : 0), *t_lo = smem + 2 * TILE + (SWZ ? 8 : 0), *t_hi = t_lo + L;
+#define DI(i) sidx<SWZ>(i)
   const uint32_t tid = threadIdx.x;
   const uint64_t n = 1ull << p.logn;
   const uint32_t n1 = 1u << p.logn1, n2 = 1u << p.logn2;
@@ -159,16 +170,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
       else { l = e & (L - 1); c = e >> p.logL; }
       uint64_t addr = base + (uint64_t)(l * pos_mul + pos_add) * pos_stride + (uint64_t)c * c_stride;
       uint4 v = gin[2 * addr + half];
-      (half ? d_hi : d_lo)[l * C + c] = v;
+      (half ? d_hi : d_lo)[DI(l * C + c)] = v;
     }
   }
   __syncthreads();
   if (p.pre) {
     for (uint32_t e = tid; e < TILE; e += NTT_THREADS) {
       uint32_t l = e >> p.logC;
-      Fr x = lds_fr(d_lo, d_hi, e);
+      Fr x = lds_fr(d_lo, d_hi, DI(e));
       Fr s = ldg_fr(p.pre + (l * pos_mul + pos_add));
-      sts_fr(d_lo, d_hi, e, x * s);
+      sts_fr(d_lo, d_hi, DI(e), x * s);
     }
     __syncthreads();
   }
@@ -187,13 +198,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
       uint32_t j = bidx & (h - 1);
       uint32_t l0 = ((bidx >> logh) << (logh + 1)) + j;
       uint32_t i0 = l0 * C + c, i1 = i0 + h * C;
-      Fr a = lds_fr(d_lo, d_hi, i0);
-      Fr b = lds_fr(d_lo, d_hi, i1);
+      Fr a = lds_fr(d_lo, d_hi, DI(i0));
+      Fr b = lds_fr(d_lo, d_hi, DI(i1));
       Fr tw = lds_fr(t_lo, t_hi, j);  // stage 0 twiddles start at offset 0
       Fr sm = a + b;
       Fr df = INVERSE ? (b - a) : (a - b);
-      sts_fr(d_lo, d_hi, i0, sm);
-      sts_fr(d_lo, d_hi, i1, df * tw);
+      sts_fr(d_lo, d_hi, DI(i0), sm);
+      sts_fr(d_lo, d_hi, DI(i1), df * tw);
     }
     __syncthreads();
     u = 1;
@@ -206,17 +217,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
       const uint32_t j = q & (h2 - 1);
       const uint32_t l0 = ((q >> logh2) << (logh + 1)) + j;
       const uint32_t i0 = l0 * C + c, i1 = i0 + h2 * C, i2 = i0 + h * C, i3 = i2 + h2 * C;
-      Fr x0 = lds_fr(d_lo, d_hi, i0), x2 = lds_fr(d_lo, d_hi, i2);
+      Fr x0 = lds_fr(d_lo, d_hi, DI(i0)), x2 = lds_fr(d_lo, d_hi, DI(i2));
       Fr a0 = x0 + x2;
       Fr a2 = (INVERSE ? (x2 - x0) : (x0 - x2)) * lds_fr(t_lo, t_hi, toff0 + j);
-      Fr x1 = lds_fr(d_lo, d_hi, i1), x3 = lds_fr(d_lo, d_hi, i3);
+      Fr x1 = lds_fr(d_lo, d_hi, DI(i1)), x3 = lds_fr(d_lo, d_hi, DI(i3));
       Fr a1 = x1 + x3;
       Fr a3 = (INVERSE ? (x3 - x1) : (x1 - x3)) * lds_fr(t_lo, t_hi, toff0 + j + h2);
       const Fr tw1 = lds_fr(t_lo, t_hi, toff1 + j);
-      sts_fr(d_lo, d_hi, i0, a0 + a1);
-      sts_fr(d_lo, d_hi, i1, (INVERSE ? (a1 - a0) : (a0 - a1)) * tw1);
-      sts_fr(d_lo, d_hi, i2, a2 + a3);
-      sts_fr(d_lo, d_hi, i3, (INVERSE ? (a3 - a2) : (a2 - a3)) * tw1);
+      sts_fr(d_lo, d_hi, DI(i0), a0 + a1);
+      sts_fr(d_lo, d_hi, DI(i1), (INVERSE ? (a1 - a0) : (a0 - a1)) * tw1);
+      sts_fr(d_lo, d_hi, DI(i2), a2 + a3);
+      sts_fr(d_lo, d_hi, DI(i3), (INVERSE ? (a3 - a2) : (a2 - a3)) * tw1);
     }
     __syncthreads();
   }
@@ -225,14 +236,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
     for (uint32_t w = tid; w < (TILE >> 2); w += NTT_THREADS) {
       uint32_t c = w & (C - 1), q = w >> p.logC;
       uint32_t i0 = (q << 2) * C + c, i1 = i0 + C, i2 = i1 + C, i3 = i2 + C;
-      Fr x0 = lds_fr(d_lo, d_hi, i0), x1 = lds_fr(d_lo, d_hi, i1), x2 = lds_fr(d_lo, d_hi, i2), x3 = lds_fr(d_lo, d_hi, i3);
+      Fr x0 = lds_fr(d_lo, d_hi, DI(i0)), x1 = lds_fr(d_lo, d_hi, DI(i1)), x2 = lds_fr(d_lo, d_hi, DI(i2)), x3 = lds_fr(d_lo, d_hi, DI(i3));
       Fr y0 = x0 + x2, y1 = x1 + x3;
       Fr y2 = x0 - x2;
       Fr y3 = (INVERSE ? (x3 - x1) : (x1 - x3)) * w4;
-      sts_fr(d_lo, d_hi, i0, y0 + y1);
-      sts_fr(d_lo, d_hi, i1, y0 - y1);
-      sts_fr(d_lo, d_hi, i2, y2 + y3);
-      sts_fr(d_lo, d_hi, i3, y2 - y3);
+      sts_fr(d_lo, d_hi, DI(i0), y0 + y1);
+      sts_fr(d_lo, d_hi, DI(i1), y0 - y1);
+      sts_fr(d_lo, d_hi, DI(i2), y2 + y3);
+      sts_fr(d_lo, d_hi, DI(i3), y2 - y3);
     }
     __syncthreads();
   }
@@ -242,10 +253,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
     for (uint32_t e = tid; e < TILE; e += NTT_THREADS) {
       uint32_t l = e >> p.logC;
       uint32_t k2 = (p.logL == 0) ? 0 : (__brev(l) >> (32 - p.logL));
-      Fr x = lds_fr(d_lo, d_hi, e);
+      Fr x = lds_fr(d_lo, d_hi, DI(e));
       if (p.post) x = x * ldg_fr(p.post + ((uint64_t)k2 * n1 + brev_g));
       if (p.has_post_scalar) x = x * p.post_scalar;
-      sts_fr(d_lo, d_hi, e, x);
+      sts_fr(d_lo, d_hi, DI(e), x);
     }
     __syncthreads();
   }
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
         l = (p.logL == 0) ? 0 : (__brev(k) >> (32 - p.logL));
         pos = (uint64_t)k * n1 + brev_g;
       }
-      const uint4 v = (half ? d_hi : d_lo)[l * C + c];
+      const uint4 v = (half ? d_hi : d_lo)[DI(l * C + c)];
       if (p.sc_on) {
         const uint64_t a_loc = pos & ((1ull << p.sc_logblk) - 1);
         uint4 *gp = reinterpret_cast<uint4 *>(p.sc_peer[pos >> p.sc_logblk]);
@@ -279,26 +290,33 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
   }
 }
 
+#undef DI
+
 static int32_t launch_pass(tkm_ctx *ctx, const NttPass &p, bool inverse) {
   const uint32_t L = 1u << p.logL, C = 1u << p.logC;
-  size_t smem = (size_t)(2 * L * C + 2 * L) * sizeof(uint4);
+  // Swizzled tiles remove the shared-memory bank conflicts of the row-batched (C = 2) pass -- measured on B200: the
+  // 16384 x 512 transform takes 1.875 ms with them against 1.858 ms without (the index arithmetic costs more ALU issue slots
+  // than the conflicts cost LSU cycles; the kernel is bound by the integer pipes).  Opt-in for profiling.
+  static const bool swz_on = getenv("TKM_NTT_SWIZZLE") != nullptr;
+  const bool swz = swz_on && !p.batch_inner && C < 8 && L >= 16;
+  size_t smem = (size_t)(2 * L * C + 2 * L + (swz ? 16 : 0)) * sizeof(uint4);
   bool *attr_set = ctx->ntt_attr_set;  // per context = per device (cudaFuncSetAttribute applies to the current device only)
-  if (!attr_set[inverse ? 1 : 0]) {
-    size_t max_smem = (size_t)(2 * (1u << NTT_TILE_LOG) + 2 * (1u << NTT_MAX_LOGL)) * sizeof(uint4);
-    if (inverse)
-      TKM_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    else
-      TKM_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    attr_set[inverse ? 1 : 0] = true;
+  const int variant = (inverse ? 1 : 0) + (swz ? 2 : 0);
+  if (!attr_set[variant]) {
+    size_t max_smem = (size_t)(2 * (1u << NTT_TILE_LOG) + 2 * (1u << NTT_MAX_LOGL) + 16) * sizeof(uint4);
+    const void *fn = variant == 0 ? (const void *)k_ntt_pass<false, false> : variant == 1 ? (const void *)k_ntt_pass<true, false>
+                     : variant == 2 ? (const void *)k_ntt_pass<false, true> : (const void *)k_ntt_pass<true, true>;
+    TKM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    attr_set[variant] = true;
   }
   const uint64_t batch_total = p.batch_inner ? p.inner : p.outer;
   const uint64_t G = (p.pass == 1) ? (1ull << p.logn2) : (1ull << p.logn1);
   const uint64_t tiles = (batch_total >> p.logC) * G * (p.batch_inner ? p.outer : 1);
   if (tiles == 0 || tiles > 0x7fffffffull) return fail(TKM_ERR_INVALID_ARGUMENT, "NTT tile count out of range");
-  if (inverse)
-    k_ntt_pass<true><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
-  else
-    k_ntt_pass<false><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
+  if (variant == 0) k_ntt_pass<false, false><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
+  else if (variant == 1) k_ntt_pass<true, false><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
+  else if (variant == 2) k_ntt_pass<false, true><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
+  else k_ntt_pass<true, true><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
   return launch_check(ctx, "k_ntt_pass");
 }
 
