@@ -992,7 +992,8 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
       size_t target = (size_t)ctx->sm_count * 4 * TREE_THREADS * (tree_waves ? tree_waves : 1);
       if (target > TREE_MAX_T) target = TREE_MAX_T;
       size_t B = (cap_elems + target - 1) / target;
-      if (B < 8) B = 8;
+      static const uint32_t min_b = getenv("TKM_MSM_TREE_MIN_B") ? (uint32_t)atoi(getenv("TKM_MSM_TREE_MIN_B")) : 32;  // developer knob
+      if (B < min_b) B = min_b;  // small levels: fewer, longer chains keep the second batch level (its cost grows with T) small
       *B_out = (uint32_t)B;
       return (cap_elems + B - 1) / B;
     };
