@@ -150,6 +150,36 @@ class ClockSampler:
                 "source": f"NVML, in-process thread, {int(self.PERIOD_S * 1000)} ms period"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned staging buffers of the e2e leg are
+    allocated on that node: eight ranks copying 512 MiB each through one remote node's memory controller is what limited the
+    N = 8 e2e line in round 1.  Best effort: returns the node, or None when the topology cannot be read."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU path, restated (oracle/oracle.c: bucket-method MSM on all host threads).
@@ -245,6 +275,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation: first touch places the staging buffers
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
@@ -367,7 +398,7 @@ def main():
         "data": "synthetic",
         "config": bench_config(args.log_n, world),
         "checks": {"msm_timed_result": f"combined result of the timed steps == (sum over {world} rank(s) of sum_i s_i k_i)*G (known discrete logs; CPU oracle as checker, outside the timed region)"},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "numa_node_rank0": numa,
         "ms_per_step_host_clock": {"min": min(timed.last_per_step), "max": max(timed.last_per_step), "all": [round(x, 3) for x in timed.last_per_step]},
     }
 
