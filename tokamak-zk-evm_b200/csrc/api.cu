@@ -232,6 +232,12 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
   if (ctx->kev0) cudaEventDestroy(ctx->kev0);
   if (ctx->kev1) cudaEventDestroy(ctx->kev1);
   if (ctx->tree_counts) cudaFreeHost(ctx->tree_counts);
+  if (ctx->tree_stream) {
+    cudaStreamSynchronize(ctx->tree_stream);
+    cudaStreamDestroy(ctx->tree_stream);
+    cudaEventDestroy(ctx->tree_fork);
+    cudaEventDestroy(ctx->tree_join);
+  }
   if (ctx->pev0) cudaEventDestroy(ctx->pev0);
   if (ctx->pev1) cudaEventDestroy(ctx->pev1);
   if (ctx->side_stream) {

@@ -80,6 +80,9 @@ struct tkm_ctx {
   // entry counts of the affine pair tree's levels in the most recent MSM accumulation pass (pinned; written by async copies)
   uint32_t *tree_counts = nullptr;  // [9]
   uint32_t tree_levels = 0;
+  // second stream of the MSM pair tree (the two halves of the bucket range run concurrently), created on first use
+  cudaStream_t tree_stream = nullptr;
+  cudaEvent_t tree_fork = nullptr, tree_join = nullptr;
   // multi-GPU: the NCCL communicator this context belongs to (comm.cu); null = single GPU
   void *comm = nullptr;
   int32_t comm_rank = 0, comm_world = 1;

@@ -190,8 +190,8 @@ struct TreeLevel {
   Fq *tot;                   // product of every thread's denominators
   const Fq *inv_tot;         // their inverses (second batch level)
   uint32_t nbuckets;
+  uint32_t b_lo, b_hi;       // this launch handles the elements of buckets [b_lo, b_hi): positions [off_out[b_lo], off_out[b_hi]) of the level
   uint32_t T;                // threads of the first batch level (stride of the element assignment)
-  uint32_t B;                // elements per thread (steps of its prefix-product chain)
   uint32_t level0;
 };
 
@@ -314,10 +314,11 @@ __global__ void __launch_bounds__(256) k_tree_xpad(const G1Affine *__restrict__ 
 __global__ void __launch_bounds__(TREE_THREADS) k_tree_fwd(const __grid_constant__ TreeLevel L) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L.T) return;
-  const uint32_t n = L.off_out[L.nbuckets];
+  const uint32_t j0 = L.off_out[L.b_lo], n = L.off_out[L.b_hi];
+  const uint32_t B = (n - j0 + L.T - 1) / L.T;  // chain length from the actual element count: T is sized for the expected share of the bucket range
   Fq acc = Fq::one();
-  for (uint32_t s = 0; s < L.B; s++) {
-    const uint64_t j = (uint64_t)s * L.T + t;
+  for (uint32_t s = 0; s < B; s++) {
+    const uint64_t j = (uint64_t)j0 + (uint64_t)s * L.T + t;
     if (j >= n) break;
     TreePair pr;
     Fq d;
@@ -385,13 +386,14 @@ __global__ void __launch_bounds__(TREE2_LEAVES) k_tree_l2_down(const Fq *tot, co
 __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_apply(const __grid_constant__ TreeLevel L) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L.T) return;
-  const uint32_t n = L.off_out[L.nbuckets];
-  uint32_t cnt = 0;
-  while (cnt < L.B && (uint64_t)cnt * L.T + t < n) cnt++;
+  const uint32_t j0 = L.off_out[L.b_lo], n = L.off_out[L.b_hi];
+  const uint32_t B = (n - j0 + L.T - 1) / L.T;
+  uint32_t cnt = B;
+  while (cnt && (uint64_t)j0 + (uint64_t)(cnt - 1) * L.T + t >= n) cnt--;
   if (!cnt) return;
   Fq run = ldg_fq(L.inv_tot + t);
   for (uint32_t s = cnt; s-- > 0;) {
-    const uint32_t j = (uint32_t)((uint64_t)s * L.T + t);
+    const uint32_t j = (uint32_t)((uint64_t)j0 + (uint64_t)s * L.T + t);
     TreePair pr;
     Fq d;
     tree_load<true>(L, j, pr, d);
@@ -509,14 +511,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t *__r
     __syncthreads();
   }
 }
-// keys of level 1: every even-position entry of a level-0 run names its bucket at off_1[b] + t/2
+// keys of level 1: every even-position entry of a level-0 run names its bucket at off_1[b] + t/2 (buckets >= split go to the
+// second half's buffer)
 __global__ void __launch_bounds__(256) k_tree_keys1(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off0, const uint32_t *__restrict__ off1,
-                                                    uint32_t nbuckets, uint32_t *__restrict__ keys1) {
+                                                    uint32_t nbuckets, uint32_t split, uint32_t *__restrict__ keys1_lo, uint32_t *__restrict__ keys1_hi) {
   const size_t n0 = off0[nbuckets];
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n0; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t b = keys[i];
     const uint32_t t = (uint32_t)i - off0[b];
-    if (!(t & 1)) keys1[off1[b] + (t >> 1)] = b;
+    if (!(t & 1)) (b < split ? keys1_lo : keys1_hi)[off1[b] + (t >> 1)] = b;
+  }
+}
+// the second half's final level, copied next to the first half's (positions [off[split], off[nbuckets]) are its own)
+__global__ void __launch_bounds__(256) k_tree_merge(const uint32_t *__restrict__ off, uint32_t split, uint32_t nbuckets, const uint4 *__restrict__ sx,
+                                                    const uint4 *__restrict__ sy, const uint32_t *__restrict__ sk, uint4 *__restrict__ dx, uint4 *__restrict__ dy,
+                                                    uint32_t *__restrict__ dk) {
+  const size_t j0 = off[split], j1 = off[nbuckets];
+  for (size_t e = (size_t)3 * j0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)3 * j1; e += (size_t)gridDim.x * blockDim.x) {
+    dx[e] = sx[e];
+    dy[e] = sy[e];
+    if (e % 3 == 0) dk[e / 3] = sk[e / 3];
   }
 }
 
@@ -954,8 +968,8 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
       L = v <= TREE_MAX_LEVELS ? v : TREE_MAX_LEVELS;
     }
   }
-  Scratch<uint32_t> t_start, t_end, t_off, t_tiles, t_keys[2];
-  Scratch<Fq> t_x[2], t_y[2], t_pref, t_tot, t_invtot, t_tot2, t_tot3;
+  Scratch<uint32_t> t_start, t_end, t_off, t_tiles, t_keys[2][2];  // [part][side]
+  Scratch<Fq> t_x[2][2], t_y[2][2], t_pref[2], t_tot, t_invtot, t_tot2, t_tot3;
   Scratch<uint4> t_xpad;
   const uint4 *xpad = in.xpad;
   const uint32_t nb = m.nbuckets;
@@ -979,12 +993,22 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
     TKM_TRY(launch_check(ctx, "k_scan_tiles"));
     k_scan_write<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(t_start.p, t_end.p, nb, levels, ntiles, t_tiles.p, t_off.p);
     TKM_TRY(launch_check(ctx, "k_scan_write"));
-    for (int side = 0; side < 2; side++) {
-      const size_t cap = bound(1 + side);
-      if (side == 1 && L < 2) break;
-      TKM_TRY(t_x[side].alloc(ctx, cap));
-      TKM_TRY(t_y[side].alloc(ctx, cap));
-      TKM_TRY(t_keys[side].alloc(ctx, cap));
+    // The levels of two halves of the bucket range are independent, so they run on two streams: while one half sits in
+    // the latency-bound second batch level (a handful of small kernels and ONE inversion per level), the other half's
+    // forward/apply kernels keep the SMs busy.  Each half has its own level buffers (a half running ahead must not overwrite
+    // what the other still reads), sized for ALL entries: thread counts assume an even split, the chain length is derived on
+    // the device from the actual count, so a skewed split only shifts time, never correctness.
+    static const bool tree_one_stream = getenv("TKM_MSM_TREE_ONE_STREAM") != nullptr;  // developer knob
+    const uint32_t parts = (!tree_one_stream && nb >= 2 && M >= ((size_t)1 << 22)) ? 2 : 1;
+    for (uint32_t part = 0; part < parts; part++) {
+      for (int side = 0; side < 2; side++) {
+        const size_t cap = bound(1 + side);
+        if (side == 1 && L < 2) break;
+        TKM_TRY(t_x[part][side].alloc(ctx, cap));
+        TKM_TRY(t_y[part][side].alloc(ctx, cap));
+        TKM_TRY(t_keys[part][side].alloc(ctx, cap));
+      }
+      TKM_TRY(t_pref[part].alloc(ctx, bound(1)));
     }
     // threads per level: about eight resident waves (4 CTAs of 128 per SM) so that blocks are balanced dynamically
     static const uint32_t tree_waves = getenv("TKM_MSM_TREE_WAVES") ? (uint32_t)atoi(getenv("TKM_MSM_TREE_WAVES")) : 8;  // developer knob
@@ -1000,14 +1024,14 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
     size_t T1 = 0;  // the largest thread count of any level (the rounding of B makes it non-monotonic in the level)
     for (uint32_t l = 0; l < L; l++) {
       uint32_t Bl;
-      const size_t Tl = pick_T(bound(l + 1), &Bl);
+      const size_t Tl = pick_T((bound(l + 1) + parts - 1) / parts, &Bl);
       if (Tl > T1) T1 = Tl;
     }
-    TKM_TRY(t_pref.alloc(ctx, bound(1)));
-    TKM_TRY(t_tot.alloc(ctx, T1));
-    TKM_TRY(t_invtot.alloc(ctx, T1));
-    TKM_TRY(t_tot2.alloc(ctx, (T1 + TREE2_LEAVES - 1) / TREE2_LEAVES));
-    TKM_TRY(t_tot3.alloc(ctx, (T1 + TREE2_LEAVES * TREE2_LEAVES - 1) / (TREE2_LEAVES * TREE2_LEAVES)));
+    const size_t n2 = (T1 + TREE2_LEAVES - 1) / TREE2_LEAVES, n3 = (n2 + TREE2_LEAVES - 1) / TREE2_LEAVES;
+    TKM_TRY(t_tot.alloc(ctx, T1 * parts));
+    TKM_TRY(t_invtot.alloc(ctx, T1 * parts));
+    TKM_TRY(t_tot2.alloc(ctx, n2 * parts));
+    TKM_TRY(t_tot3.alloc(ctx, n3 * parts));
     if (!xpad && !in.idx && !in.pre_c) {  // plain bases (dense or a strided rectangle): a per-call x table pays for itself over the windows
       const size_t span = (in.rows - 1) * in.base_row_stride + in.cols;
       TKM_TRY(t_xpad.alloc(ctx, span * 4));
@@ -1015,57 +1039,82 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
       xpad = t_xpad.p;
     }
     auto off = [&](uint32_t l) { return t_off.p + (size_t)l * (nb + 1); };
-    k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, t_keys[0].p);
+    k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, parts == 2 ? nb / 2 : nb, t_keys[0][0].p,
+                                                                           t_keys[parts - 1][0].p);
     TKM_TRY(launch_check(ctx, "k_tree_keys1"));
+    if (parts == 2) {
+      if (!ctx->tree_stream) {
+        TKM_CUDA(cudaStreamCreateWithFlags(&ctx->tree_stream, cudaStreamNonBlocking));
+        TKM_CUDA(cudaEventCreateWithFlags(&ctx->tree_fork, cudaEventDisableTiming));
+        TKM_CUDA(cudaEventCreateWithFlags(&ctx->tree_join, cudaEventDisableTiming));
+      }
+      TKM_CUDA(cudaEventRecord(ctx->tree_fork, ctx->stream));
+      TKM_CUDA(cudaStreamWaitEvent(ctx->tree_stream, ctx->tree_fork, 0));
+    }
     for (uint32_t l = 0; l < L; l++) {
       const int o = l & 1, i = o ^ 1;  // level l+1 lands in side o; level l (l >= 1) sits in side i
-      TreeLevel tl;
-      memset(&tl, 0, sizeof tl);
-      tl.level0 = l == 0;
-      tl.vals = vals_s.p;
-      tl.bases = in.bases;
-      tl.xpad = xpad;
-      tl.in_x = l ? t_x[i].p : nullptr;
-      tl.in_y = l ? t_y[i].p : nullptr;
-      tl.off_in = off(l);
-      tl.off_out = off(l + 1);
-      tl.off_next = l + 2 <= L ? off(l + 2) : nullptr;
-      tl.keys_out = t_keys[o].p;
-      tl.keys_next = t_keys[i].p;
-      tl.out_x = t_x[o].p;
-      tl.out_y = t_y[o].p;
-      tl.pref = t_pref.p;
-      tl.tot = t_tot.p;
-      tl.inv_tot = t_invtot.p;
-      tl.nbuckets = nb;
-      uint32_t B;
-      const size_t T = pick_T(bound(l + 1), &B);
-      const uint32_t nblk = (uint32_t)((T + TREE2_LEAVES - 1) / TREE2_LEAVES);
-      tl.T = (uint32_t)T;
-      tl.B = B;
-      const unsigned g1 = (unsigned)((T + TREE_THREADS - 1) / TREE_THREADS);
-      k_tree_fwd<<<g1, TREE_THREADS, 0, ctx->stream>>>(tl);
-      TKM_TRY(launch_check(ctx, "k_tree_fwd"));
-      // second batch level: products of 256 thread products per block, then (when there are more than 512 of those) a
-      // second block tier, the top block with the level's only inversion, and back down
-      k_tree_l2_up<<<nblk, TREE2_LEAVES, 0, ctx->stream>>>(t_tot.p, (uint32_t)T, t_tot2.p);
-      TKM_TRY(launch_check(ctx, "k_tree_l2_up"));
-      if (nblk <= (uint32_t)TREE3_LEAVES) {
-        k_tree_l3<<<1, TREE3_LEAVES, 0, ctx->stream>>>(t_tot2.p, nblk);
-        TKM_TRY(launch_check(ctx, "k_tree_l3"));
-      } else {
-        const uint32_t nblk2 = (nblk + TREE2_LEAVES - 1) / TREE2_LEAVES;
-        k_tree_l2_up<<<nblk2, TREE2_LEAVES, 0, ctx->stream>>>(t_tot2.p, nblk, t_tot3.p);
+      for (uint32_t part = 0; part < parts; part++) {
+        cudaStream_t st = part ? ctx->tree_stream : ctx->stream;
+        TreeLevel tl;
+        memset(&tl, 0, sizeof tl);
+        tl.level0 = l == 0;
+        tl.vals = vals_s.p;
+        tl.bases = in.bases;
+        tl.xpad = xpad;
+        tl.in_x = l ? t_x[part][i].p : nullptr;
+        tl.in_y = l ? t_y[part][i].p : nullptr;
+        tl.off_in = off(l);
+        tl.off_out = off(l + 1);
+        tl.off_next = l + 2 <= L ? off(l + 2) : nullptr;
+        tl.keys_out = t_keys[part][o].p;
+        tl.keys_next = t_keys[part][i].p;
+        tl.out_x = t_x[part][o].p;
+        tl.out_y = t_y[part][o].p;
+        tl.pref = t_pref[part].p;
+        Fq *tot = t_tot.p + (size_t)part * T1, *invtot = t_invtot.p + (size_t)part * T1, *tot2 = t_tot2.p + (size_t)part * n2, *tot3 = t_tot3.p + (size_t)part * n3;
+        tl.tot = tot;
+        tl.inv_tot = invtot;
+        tl.nbuckets = nb;
+        tl.b_lo = part ? nb / 2 : 0;
+        tl.b_hi = (parts == 2 && part == 0) ? nb / 2 : nb;
+        uint32_t B;
+        const size_t T = pick_T((bound(l + 1) + parts - 1) / parts, &B);
+        const uint32_t nblk = (uint32_t)((T + TREE2_LEAVES - 1) / TREE2_LEAVES);
+        tl.T = (uint32_t)T;
+        const unsigned g1 = (unsigned)((T + TREE_THREADS - 1) / TREE_THREADS);
+        // (staggering the halves with an event -- second half's forward pass after the first half's -- was measured: 22.38 ms
+        // against 22.19 ms unstaggered at 2^22, so the streams are left to interleave freely)
+        k_tree_fwd<<<g1, TREE_THREADS, 0, st>>>(tl);
+        TKM_TRY(launch_check(ctx, "k_tree_fwd"));
+        // second batch level: products of 256 thread products per block, then (when there are more than 512 of those) a
+        // second block tier, the top block with the level's only inversion, and back down
+        k_tree_l2_up<<<nblk, TREE2_LEAVES, 0, st>>>(tot, (uint32_t)T, tot2);
         TKM_TRY(launch_check(ctx, "k_tree_l2_up"));
-        k_tree_l3<<<1, TREE3_LEAVES, 0, ctx->stream>>>(t_tot3.p, nblk2);
-        TKM_TRY(launch_check(ctx, "k_tree_l3"));
-        k_tree_l2_down<<<nblk2, TREE2_LEAVES, 0, ctx->stream>>>(t_tot2.p, t_tot3.p, nblk, t_tot2.p);
+        if (nblk <= (uint32_t)TREE3_LEAVES) {
+          k_tree_l3<<<1, TREE3_LEAVES, 0, st>>>(tot2, nblk);
+          TKM_TRY(launch_check(ctx, "k_tree_l3"));
+        } else {
+          const uint32_t nblk2 = (nblk + TREE2_LEAVES - 1) / TREE2_LEAVES;
+          k_tree_l2_up<<<nblk2, TREE2_LEAVES, 0, st>>>(tot2, nblk, tot3);
+          TKM_TRY(launch_check(ctx, "k_tree_l2_up"));
+          k_tree_l3<<<1, TREE3_LEAVES, 0, st>>>(tot3, nblk2);
+          TKM_TRY(launch_check(ctx, "k_tree_l3"));
+          k_tree_l2_down<<<nblk2, TREE2_LEAVES, 0, st>>>(tot2, tot3, nblk, tot2);
+          TKM_TRY(launch_check(ctx, "k_tree_l2_down"));
+        }
+        k_tree_l2_down<<<nblk, TREE2_LEAVES, 0, st>>>(tot, tot2, (uint32_t)T, invtot);
         TKM_TRY(launch_check(ctx, "k_tree_l2_down"));
+        k_tree_apply<<<g1, TREE_THREADS, 0, st>>>(tl);
+        TKM_TRY(launch_check(ctx, "k_tree_apply"));
       }
-      k_tree_l2_down<<<nblk, TREE2_LEAVES, 0, ctx->stream>>>(t_tot.p, t_tot2.p, (uint32_t)T, t_invtot.p);
-      TKM_TRY(launch_check(ctx, "k_tree_l2_down"));
-      k_tree_apply<<<g1, TREE_THREADS, 0, ctx->stream>>>(tl);
-      TKM_TRY(launch_check(ctx, "k_tree_apply"));
+    }
+    if (parts == 2) {
+      TKM_CUDA(cudaEventRecord(ctx->tree_join, ctx->tree_stream));
+      TKM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->tree_join, 0));
+      const int f = (L & 1) ? 0 : 1;
+      k_tree_merge<<<grid_for(bound(L) * 3 / 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(off(L), nb / 2, nb, (const uint4 *)t_x[1][f].p, (const uint4 *)t_y[1][f].p,
+                                                                                           t_keys[1][f].p, (uint4 *)t_x[0][f].p, (uint4 *)t_y[0][f].p, t_keys[0][f].p);
+      TKM_TRY(launch_check(ctx, "k_tree_merge"));
     }
     // per-level entry counts for bench.py's work accounting (read back lazily by tkm_msm_tree_stats)
     ctx->tree_levels = L;
@@ -1103,7 +1152,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   TKM_TRY(pp_b.alloc(ctx, P2));
   const unsigned acc_grid = (unsigned)((T + ACC_THREADS - 1) / ACC_THREADS);
   if (L)
-    k_accumulate<true><<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(t_keys[fin].p, nullptr, Macc, chunk, nullptr, t_x[fin].p, t_y[fin].p,
+    k_accumulate<true><<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(t_keys[0][fin].p, nullptr, Macc, chunk, nullptr, t_x[0][fin].p, t_y[0][fin].p,
                                                                    t_off.p + (size_t)L * (nb + 1) + nb, invalid, buckets, pk_a.p, pp_a.p, T);
   else
     k_accumulate<false><<<acc_grid, ACC_THREADS, 0, ctx->stream>>>(keys_s.p, vals_s.p, M, chunk, in.bases, nullptr, nullptr, nullptr, invalid, buckets,
