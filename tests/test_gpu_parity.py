@@ -766,9 +766,9 @@ def test_polyexpr_program_entry_point(ctx, T):
     ref.resize(128, 64)
     assert fused.shape == (128, 64)
     assert np.array_equal(fused.copy_coeffs(), ref.copy_coeffs())
-    assert to_ints(E.scalar(5).evaluate_fused_with_domain(2, 2).copy_coeffs()) == [5, 0, 0, 0]
+    assert to_ints(E.scalar(5).evaluate_fused_with_domain(2, 2, ctx).copy_coeffs()) == [5, 0, 0, 0]
     assert np.array_equal(E.scale(1, E.poly(r)).evaluate_fused_with_domain(sx, sy).copy_coeffs(), r.copy_coeffs())
-    assert to_ints(E.weighted_sum([]).evaluate_fused_with_domain(1, 1).copy_coeffs()) == [0]
+    assert to_ints(E.weighted_sum([]).evaluate_fused_with_domain(1, 1, ctx).copy_coeffs()) == [0]
     with pytest.raises(ValueError):
         expr.evaluate_fused_with_domain(64, 64)  # too small for the degree
     with pytest.raises(ValueError):

@@ -185,6 +185,8 @@ struct TreeLevel {
   const uint32_t *off_next;  // off_{l+2}[b] or null (no further level): keys of the next level are written by the apply pass
   const uint32_t *keys_out;  // bucket of every output element
   uint32_t *keys_next;
+  const uint32_t *src_out;   // per output element: input index of its first operand | (has a partner) << 31
+  uint32_t *src_next;
   Fq *out_x, *out_y;
   Fq *pref;                  // prefix products, one per output element
   Fq *tot;                   // product of every thread's denominators
@@ -198,7 +200,6 @@ struct TreeLevel {
 struct TreePair {
   G1Affine p1, p2;
   uint32_t kind;  // 0: copy p1, 1: copy p2, 2: identity, 3: chord (d = x2 - x1), 4: tangent (d = 2 y1)
-  uint32_t b, tprime;
 };
 
 __device__ __forceinline__ Fq ldg_fq(const Fq *p) {
@@ -220,16 +221,14 @@ __device__ __forceinline__ void st_fq(Fq *p, const Fq &a) {
 // Operands of output element j and the case it falls in.  WITH_Y = false loads only what the denominator needs (the y
 // coordinates are fetched on demand in the rare cases that need them).
 template <bool WITH_Y>
-__device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePair &pr, Fq &d) {
-  const uint32_t b = L.keys_out[j];
-  const uint32_t o_in = L.off_in[b], m = L.off_in[b + 1] - o_in;
-  const uint32_t tp = j - L.off_out[b];
-  const uint32_t i = o_in + 2 * tp;
-  const bool partner = 2 * tp + 1 < m;
-  pr.b = b;
-  pr.tprime = tp;
+__device__ __forceinline__ void tree_classify(const TreeLevel &L, uint32_t i, bool partner, uint32_t v1, uint32_t v2, TreePair &pr, Fq &d);
+
+// Operands of one output element (input entries i and, when it has a partner, i + 1; v1, v2 = their digit-list values at
+// level 0) and the case it falls in.  WITH_Y = false loads only what the denominator needs (the y coordinates are fetched on
+// demand in the rare cases that need them).
+template <bool WITH_Y>
+__device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t i, bool partner, uint32_t v1, uint32_t v2, TreePair &pr, Fq &d) {
   if (L.level0) {
-    const uint32_t v1 = L.vals[i];
     const G1Affine *q1 = L.bases + (v1 & 0x7fffffffu);
     if (WITH_Y) {
       pr.p1 = ldg_affine(q1);
@@ -238,7 +237,6 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
       pr.p1.x = L.xpad ? ldg_fq(reinterpret_cast<const Fq *>(L.xpad + 4 * (size_t)(v1 & 0x7fffffffu))) : ldg_fq(&q1->x);
     }
     if (partner) {
-      const uint32_t v2 = L.vals[i + 1];
       const G1Affine *q2 = L.bases + (v2 & 0x7fffffffu);
       if (WITH_Y) {
         pr.p2 = ldg_affine(q2);
@@ -255,6 +253,11 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
       if (WITH_Y) pr.p2.y = ldg_fq(L.in_y + i + 1);
     }
   }
+  tree_classify<WITH_Y>(L, i, partner, v1, v2, pr, d);
+}
+
+template <bool WITH_Y>
+__device__ __forceinline__ void tree_classify(const TreeLevel &L, uint32_t i, bool partner, uint32_t v1, uint32_t v2, TreePair &pr, Fq &d) {
   d = Fq::one();
   if (!partner) {
     pr.kind = 0;
@@ -269,7 +272,6 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
   // rare: an operand may be the identity (0, 0), or the points share their x
   if (!WITH_Y) {
     if (L.level0) {
-      const uint32_t v1 = L.vals[i], v2 = L.vals[i + 1];
       pr.p1.y = ldg_fq(&L.bases[v1 & 0x7fffffffu].y);
       pr.p2.y = ldg_fq(&L.bases[v2 & 0x7fffffffu].y);
       if (v1 >> 31) pr.p1.y = pr.p1.y.neg();
@@ -292,6 +294,51 @@ __device__ __forceinline__ void tree_load(const TreeLevel &L, uint32_t j, TreePa
   } else {
     pr.kind = 2;  // P + (-P)
   }
+}
+
+#ifndef TKM_TREE_PREFETCH
+#define TKM_TREE_PREFETCH 0
+#endif
+// (Measured on B200: explicit L2 prefetches of the next element's operands make the tree SLOWER -- 2^22: 22.5 ms with them
+// against 21.9 ms without, 2^24: 84.6 against 79.5 -- the line-granular prefetch over-fetches around the 96-byte points and
+// the passes are already limited by DRAM traffic at level 0.  Kept behind a build knob.)
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#if TKM_TREE_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+// Software pipeline of a thread's chain: the element's source descriptor (src: input index | partner << 31, written when the
+// level's keys were) is loaded three elements ahead, its digit values (level 0) two ahead, and the operands it names are
+// prefetched into L2 one element ahead -- the dependent gathers key -> index -> value -> point never stall the chain.
+struct TreeFetch {
+  uint32_t src[3];   // descriptors of the next three elements of the chain
+  uint32_t v[2][2];  // level 0: digit values of the next two elements
+};
+template <bool WITH_Y>
+__device__ __forceinline__ void tree_prefetch(const TreeLevel &L, uint32_t src, uint32_t v1, uint32_t v2, const Fq *pref_next) {
+  const uint32_t i = src & 0x7fffffffu;
+  const bool partner = src >> 31;
+  if (L.level0) {
+    if (WITH_Y || !L.xpad) {
+      const char *q1 = reinterpret_cast<const char *>(L.bases + (v1 & 0x7fffffffu));
+      prefetch_l2(q1);
+      if (partner) {
+        const char *q2 = reinterpret_cast<const char *>(L.bases + (v2 & 0x7fffffffu));
+        prefetch_l2(q2);
+      }
+    } else {
+      prefetch_l2(L.xpad + 4 * (size_t)(v1 & 0x7fffffffu));
+      if (partner) prefetch_l2(L.xpad + 4 * (size_t)(v2 & 0x7fffffffu));
+    }
+  } else {
+    const char *qx = reinterpret_cast<const char *>(L.in_x + i);
+    prefetch_l2(qx);
+    if (WITH_Y) prefetch_l2(reinterpret_cast<const char *>(L.in_y + i));
+  }
+  if (pref_next) prefetch_l2(pref_next);
 }
 
 // x coordinates of the bases an MSM touches, one 64-byte slot per base: the forward pass of level 0 gathers only x, and from
@@ -317,14 +364,35 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree_fwd(const __grid_constant
   const uint32_t j0 = L.off_out[L.b_lo], n = L.off_out[L.b_hi];
   const uint32_t B = (n - j0 + L.T - 1) / L.T;  // chain length from the actual element count: T is sized for the expected share of the bucket range
   Fq acc = Fq::one();
+  auto pos = [&](uint32_t s) { return (uint64_t)j0 + (uint64_t)s * L.T + t; };  // element s of this thread's chain
+  auto live = [&](uint32_t s) { return s < B && pos(s) < n; };
+  auto load_vals = [&](uint32_t src, uint32_t *v) {
+    if (!L.level0) return;
+    const uint32_t i = src & 0x7fffffffu;
+    v[0] = L.vals[i];
+    v[1] = (src >> 31) ? L.vals[i + 1] : 0u;
+  };
+  // prime the pipeline: descriptors two elements ahead, digit values one ahead (loading the operands themselves one element
+  // ahead into registers was measured too: 118 registers, no gain)
+  uint32_t sc = live(0) ? L.src_out[pos(0)] : 0, s1 = live(1) ? L.src_out[pos(1)] : 0, s2 = live(2) ? L.src_out[pos(2)] : 0;
+  uint32_t vc[2] = {0, 0}, v1[2] = {0, 0};
+  if (live(0)) load_vals(sc, vc);
+  if (live(1)) load_vals(s1, v1);
   for (uint32_t s = 0; s < B; s++) {
-    const uint64_t j = (uint64_t)j0 + (uint64_t)s * L.T + t;
+    const uint64_t j = pos(s);
     if (j >= n) break;
+    if (live(s + 1)) tree_prefetch<false>(L, s1, v1[0], v1[1], nullptr);  // (compiled out unless TKM_TREE_PREFETCH)
+    uint32_t v2[2] = {0, 0};
+    if (live(s + 2)) load_vals(s2, v2);                                    // digit values two ahead
+    const uint32_t s3 = live(s + 3) ? L.src_out[pos(s + 3)] : 0;           // descriptor three ahead
     TreePair pr;
     Fq d;
-    tree_load<false>(L, (uint32_t)j, pr, d);
+    tree_load<false>(L, sc & 0x7fffffffu, sc >> 31, vc[0], vc[1], pr, d);
     st_fq(L.pref + j, acc);
     if (pr.kind >= 3) acc = acc * d;
+    sc = s1; s1 = s2; s2 = s3;
+    vc[0] = v1[0]; vc[1] = v1[1];
+    v1[0] = v2[0]; v1[1] = v2[1];
   }
   st_fq(L.tot + t, acc);
 }
@@ -392,11 +460,28 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_apply(const __grid_con
   while (cnt && (uint64_t)j0 + (uint64_t)(cnt - 1) * L.T + t >= n) cnt--;
   if (!cnt) return;
   Fq run = ldg_fq(L.inv_tot + t);
-  for (uint32_t s = cnt; s-- > 0;) {
-    const uint32_t j = (uint32_t)((uint64_t)j0 + (uint64_t)s * L.T + t);
+  // the chain runs backwards: element cnt-1 first.  k counts elements already consumed; element index s = cnt - 1 - k.
+  auto pos = [&](uint32_t k) { return (uint32_t)((uint64_t)j0 + (uint64_t)(cnt - 1 - k) * L.T + t); };
+  auto live = [&](uint32_t k) { return k < cnt; };
+  auto load_vals = [&](uint32_t src, uint32_t *v) {
+    if (!L.level0) return;
+    const uint32_t i = src & 0x7fffffffu;
+    v[0] = L.vals[i];
+    v[1] = (src >> 31) ? L.vals[i + 1] : 0u;
+  };
+  uint32_t sc = L.src_out[pos(0)], s1 = live(1) ? L.src_out[pos(1)] : 0, s2 = live(2) ? L.src_out[pos(2)] : 0;
+  uint32_t vc[2] = {0, 0}, v1[2] = {0, 0};
+  load_vals(sc, vc);
+  if (live(1)) load_vals(s1, v1);
+  for (uint32_t k = 0; k < cnt; k++) {
+    const uint32_t j = pos(k);
+    if (live(k + 1)) tree_prefetch<true>(L, s1, v1[0], v1[1], L.pref + pos(k + 1));
+    uint32_t v2[2] = {0, 0};
+    if (live(k + 2)) load_vals(s2, v2);
+    const uint32_t s3 = live(k + 3) ? L.src_out[pos(k + 3)] : 0;
     TreePair pr;
     Fq d;
-    tree_load<true>(L, j, pr, d);
+    tree_load<true>(L, sc & 0x7fffffffu, sc >> 31, vc[0], vc[1], pr, d);
     G1Affine r;
     if (pr.kind >= 3) {
       const Fq dinv = run * ldg_fq(L.pref + j);
@@ -420,7 +505,18 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_apply(const __grid_con
     }
     st_fq(L.out_x + j, r.x);
     st_fq(L.out_y + j, r.y);
-    if (L.off_next && !(pr.tprime & 1)) L.keys_next[L.off_next[pr.b] + (pr.tprime >> 1)] = pr.b;
+    if (L.off_next) {  // descriptors and keys of the next level: even positions of this level's runs name their pair
+      const uint32_t b = L.keys_out[j];
+      const uint32_t o = L.off_out[b], tp = j - o;
+      if (!(tp & 1)) {
+        const uint32_t m = L.off_out[b + 1] - o, jn = L.off_next[b] + (tp >> 1);
+        L.keys_next[jn] = b;
+        L.src_next[jn] = j | ((tp + 1 < m) ? 0x80000000u : 0u);
+      }
+    }
+    sc = s1; s1 = s2; s2 = s3;
+    vc[0] = v1[0]; vc[1] = v1[1];
+    v1[0] = v2[0]; v1[1] = v2[1];
   }
 }
 
@@ -514,12 +610,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t *__r
 // keys of level 1: every even-position entry of a level-0 run names its bucket at off_1[b] + t/2 (buckets >= split go to the
 // second half's buffer)
 __global__ void __launch_bounds__(256) k_tree_keys1(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off0, const uint32_t *__restrict__ off1,
-                                                    uint32_t nbuckets, uint32_t split, uint32_t *__restrict__ keys1_lo, uint32_t *__restrict__ keys1_hi) {
+                                                    uint32_t nbuckets, uint32_t split, uint32_t *__restrict__ keys1_lo, uint32_t *__restrict__ keys1_hi,
+                                                    uint32_t *__restrict__ src1_lo, uint32_t *__restrict__ src1_hi) {
   const size_t n0 = off0[nbuckets];
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n0; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t b = keys[i];
-    const uint32_t t = (uint32_t)i - off0[b];
-    if (!(t & 1)) (b < split ? keys1_lo : keys1_hi)[off1[b] + (t >> 1)] = b;
+    const uint32_t o = off0[b], t = (uint32_t)i - o;
+    if (!(t & 1)) {
+      const uint32_t m = off0[b + 1] - o, j = off1[b] + (t >> 1);
+      (b < split ? keys1_lo : keys1_hi)[j] = b;
+      (b < split ? src1_lo : src1_hi)[j] = (uint32_t)i | ((t + 1 < m) ? 0x80000000u : 0u);
+    }
   }
 }
 // the second half's final level, copied next to the first half's (positions [off[split], off[nbuckets]) are its own)
@@ -968,7 +1069,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
       L = v <= TREE_MAX_LEVELS ? v : TREE_MAX_LEVELS;
     }
   }
-  Scratch<uint32_t> t_start, t_end, t_off, t_tiles, t_keys[2][2];  // [part][side]
+  Scratch<uint32_t> t_start, t_end, t_off, t_tiles, t_keys[2][2], t_src[2][2];  // [part][side]
   Scratch<Fq> t_x[2][2], t_y[2][2], t_pref[2], t_tot, t_invtot, t_tot2, t_tot3;
   Scratch<uint4> t_xpad;
   const uint4 *xpad = in.xpad;
@@ -976,7 +1077,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   auto bound = [&](uint32_t l) { return (size_t)((M + ((size_t)1 << l) - 1) >> l) + nb; };  // >= entries of level l
   TKM_CUDA(cudaEventRecord(ctx->kev0, ctx->stream));
   if (L > 0) {
-    if (bound(1) + nb >= 0xffffffffull) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM too large for the 32-bit element indices of the pair tree");
+    if (M >= 0x7fffffffull) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM too large for the 31-bit element indices of the pair tree");
     const uint32_t levels = L + 1;
     TKM_TRY(t_start.alloc(ctx, nb));
     TKM_TRY(t_end.alloc(ctx, nb));
@@ -1007,6 +1108,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
         TKM_TRY(t_x[part][side].alloc(ctx, cap));
         TKM_TRY(t_y[part][side].alloc(ctx, cap));
         TKM_TRY(t_keys[part][side].alloc(ctx, cap));
+        TKM_TRY(t_src[part][side].alloc(ctx, cap));
       }
       TKM_TRY(t_pref[part].alloc(ctx, bound(1)));
     }
@@ -1040,7 +1142,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
     }
     auto off = [&](uint32_t l) { return t_off.p + (size_t)l * (nb + 1); };
     k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, parts == 2 ? nb / 2 : nb, t_keys[0][0].p,
-                                                                           t_keys[parts - 1][0].p);
+                                                                           t_keys[parts - 1][0].p, t_src[0][0].p, t_src[parts - 1][0].p);
     TKM_TRY(launch_check(ctx, "k_tree_keys1"));
     if (parts == 2) {
       if (!ctx->tree_stream) {
@@ -1068,6 +1170,8 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
         tl.off_next = l + 2 <= L ? off(l + 2) : nullptr;
         tl.keys_out = t_keys[part][o].p;
         tl.keys_next = t_keys[part][i].p;
+        tl.src_out = t_src[part][o].p;
+        tl.src_next = t_src[part][i].p;
         tl.out_x = t_x[part][o].p;
         tl.out_y = t_y[part][o].p;
         tl.pref = t_pref[part].p;

@@ -766,6 +766,8 @@ class PolyExpr:
 
     def evaluate_fused_with_domain(self, target_x_size, target_y_size, ctx=None):
         ctx = ctx or self._ctx()
+        if ctx is None:
+            raise ValueError("an expression without polynomial leaves needs an explicit context")
         if target_x_size & (target_x_size - 1) or target_y_size & (target_y_size - 1):
             raise ValueError("Fused polynomial expression domains must be powers of two.")
         xd, yd = self.degree_bound()
