@@ -479,12 +479,22 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_apply(const __grid_con
     uint32_t v2[2] = {0, 0};
     if (live(k + 2)) load_vals(s2, v2);
     const uint32_t s3 = live(k + 3) ? L.src_out[pos(k + 3)] : 0;
+    // loads that feed the end of the iteration are issued first: the bucket of this element (for the next level's
+    // descriptors) and its prefix product; the offsets that depend on the bucket follow once the operands have arrived
+    const uint32_t b = L.off_next ? L.keys_out[j] : 0u;
+    const Fq pf = ldg_fq(L.pref + j);
     TreePair pr;
     Fq d;
     tree_load<true>(L, sc & 0x7fffffffu, sc >> 31, vc[0], vc[1], pr, d);
+    uint32_t o_b = 0, o_b1 = 0, o_n = 0;
+    if (L.off_next) {
+      o_b = L.off_out[b];
+      o_b1 = L.off_out[b + 1];
+      o_n = L.off_next[b];
+    }
     G1Affine r;
     if (pr.kind >= 3) {
-      const Fq dinv = run * ldg_fq(L.pref + j);
+      const Fq dinv = run * pf;
       run = run * d;
       Fq num;
       if (pr.kind == 3) {
@@ -506,12 +516,11 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_apply(const __grid_con
     st_fq(L.out_x + j, r.x);
     st_fq(L.out_y + j, r.y);
     if (L.off_next) {  // descriptors and keys of the next level: even positions of this level's runs name their pair
-      const uint32_t b = L.keys_out[j];
-      const uint32_t o = L.off_out[b], tp = j - o;
+      const uint32_t tp = j - o_b;
       if (!(tp & 1)) {
-        const uint32_t m = L.off_out[b + 1] - o, jn = L.off_next[b] + (tp >> 1);
+        const uint32_t jn = o_n + (tp >> 1);
         L.keys_next[jn] = b;
-        L.src_next[jn] = j | ((tp + 1 < m) ? 0x80000000u : 0u);
+        L.src_next[jn] = j | ((tp + 1 < o_b1 - o_b) ? 0x80000000u : 0u);
       }
     }
     sc = s1; s1 = s2; s2 = s3;
