@@ -149,6 +149,18 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
       y = d;
     }
     if (x.v[0] == 0x12345678u && y.v[1] == 1) sink[0] = x.v[1];
+  } else if (KIND == 7) {  // the same butterfly on the round-1 reduction (add-with-carry chains on the ALU pipe), for comparison
+    using FrOld = Fp<FrParamsAddChains>;
+    FrOld x = FrOld::one(), y = FrOld::r2(), w = FrOld::r2();
+    x.v[0] ^= t;
+    w.v[1] ^= t;
+    for (int it = 0; it < iters; it++) {
+      FrOld s = x + y;
+      FrOld d = (x - y) * w;
+      x = s;
+      y = d;
+    }
+    if (x.v[0] == 0x12345678u && y.v[1] == 1) sink[0] = x.v[1];
   } else if (KIND == 2) {
     Fr x = Fr::one(), y = Fr::r2();
     x.v[0] ^= t;
@@ -920,6 +932,7 @@ int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
       case 4: iters = 64; ops_per_iter = 1; k_microbench<4><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 5: iters = 4096; ops_per_iter = 16; k_microbench<5><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 6: iters = 512; ops_per_iter = 1; k_microbench<6><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 7: iters = 512; ops_per_iter = 1; k_microbench<7><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown microbench kind %d", kind);
     }
     TKM_TRY(launch_check(ctx, "k_microbench"));

@@ -57,6 +57,17 @@ inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = ((
 inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + cc_flag()); }
 #endif
 
+// -x mod 2^32 as a product ptxas cannot turn back into a negation (the factor lives in constant memory); see Fp::reduce_row.
+#if defined(__CUDA_ARCH__)
+static __constant__ uint32_t c_all_ones = 0xffffffffu;
+TKM_D uint32_t neg_opaque(uint32_t x) { return x * c_all_ones; }
+#elif defined(__CUDACC__)
+static __constant__ uint32_t c_all_ones = 0xffffffffu;
+inline uint32_t neg_opaque(uint32_t x) { return 0u - x; }
+#else
+inline uint32_t neg_opaque(uint32_t x) { return 0u - x; }
+#endif
+
 // ---------------------------------------------------------------- field parameters
 struct FrParams {
   static constexpr int N = 8;
@@ -64,6 +75,9 @@ struct FrParams {
   // r = ... ffffffff 00000001: the two low limbs are 1 and 2^32-1, so m*(p0 + p1*2^32) = m*2^64 - m*2^32 + m
   // needs no multiplier at all (see Fp::reduce_row).
   static constexpr bool LOW_LIMBS_ONE_MINUS_ONE = true;
+  // 1: reduction rows as fused multiply-add carry chains started by the borrow of 0 - E[0] (see Fp::reduce_row);
+  // 0: the round-1 form (plain 64-bit products folded in with add-with-carry chains on the ALU pipe).
+  static constexpr int REDUCE_FORM = 1;
   // r uses 255 of the 256 container bits: the doubled rows of the dedicated squaring (see Fp::sqr) would overflow the
   // 2^(32(N+1)) accumulator bound, so Fr squares through the general product.
   static constexpr bool DEDICATED_SQR = false;
@@ -80,8 +94,12 @@ struct FrParams {
     return M[i];
   }
 };
+struct FrParamsAddChains : FrParams {
+  static constexpr int REDUCE_FORM = 0;
+};
 struct FqParams {
   static constexpr int N = 12;
+  static constexpr int REDUCE_FORM = 0;
   static constexpr uint32_t INV = 0xfffcfffdu;  // -q^-1 mod 2^32
   static constexpr bool LOW_LIMBS_ONE_MINUS_ONE = false;
   static constexpr bool DEDICATED_SQR = true;  // q < 2^381 leaves three spare bits in the 384-bit container
@@ -195,7 +213,37 @@ struct alignas(16) Fp {
   }
   // Reduction half-row: make column 0 of T vanish.  E aligned at column 0, O at column 1.
   TKM_HD static void reduce_row(uint32_t *E, uint32_t *O) {
+    if (P::LOW_LIMBS_ONE_MINUS_ONE && P::REDUCE_FORM == 1) {
+      // p0 = 1 and -p^-1 = -1 mod 2^32: m = -E[0], and column 0 becomes E[0] + m = 2^32*[E[0] != 0].  That carry is
+      // the carry out of E[0] + 0xffffffff, so that addition (result discarded) leaves it in the carry flag and the odd-limb
+      // chain starts with it: (O[0],O[1]) += m*p1 + carry, (O[2],O[3]) += m*p3, ...  (Not sub.cc 0 - E[0]: the hardware
+      // carry after a subtraction is the inverted borrow and ptxas hands it to a following madc unchanged.)  The p0 product is never formed:
+      // 7 wide IMADs per row instead of 8 (Fr: 64 + 56 = 120 per product) and no separate add-with-carry chains.
+      // m is taken as E[0] * 0xffffffff with the factor read from constant memory: when ptxas sees the negation it
+      // splits every m*p[j] multiply-add into an IMAD.X + IMAD.HI.U32.X pair (6 FMA-pipe cycles instead of 4); a product
+      // it cannot strength-reduce keeps the pairs fused into IMAD.WIDE.U32.X (checked with cuobjdump -sass,
+      // profiles/r02_sass_histograms.txt: 280 instructions per NTT butterfly instead of 408).
+      const uint32_t m = neg_opaque(E[0]);
+      (void)add_cc(E[0], 0xffffffffu);  // carry flag = [E[0] != 0]
+      O[0] = madc_lo_cc(P::mod(1), m, O[0]);
+      O[1] = madc_hi_cc(P::mod(1), m, O[1]);
+#pragma unroll
+      for (int j = 3; j < N; j += 2) {
+        O[j - 1] = madc_lo_cc(P::mod(j), m, O[j - 1]);
+        O[j] = madc_hi_cc(P::mod(j), m, O[j]);
+      }
+      E[2] = mad_lo_cc(P::mod(2), m, E[2]);
+      E[3] = madc_hi_cc(P::mod(2), m, E[3]);
+#pragma unroll
+      for (int j = 4; j < N; j += 2) {
+        E[j] = madc_lo_cc(P::mod(j), m, E[j]);
+        E[j + 1] = madc_hi_cc(P::mod(j), m, E[j + 1]);
+      }
+      O[N - 1] = addc(O[N - 1], 0);
+      return;  // E[0] is now (logically) zero and is never read again; E[1] is untouched
+    }
     if (P::LOW_LIMBS_ONE_MINUS_ONE) {
+      // (round-1 form, kept for the microbenchmark comparison: FrParamsAddChains)
       // p0 = 1, p1 = 2^32 - 1, -p^-1 = -1 mod 2^32:  m = -E[0].  Column 0: E[0] + m = 2^32*[m != 0].
       // Columns (1,2) receive that carry plus m*p1 = m*2^32 - m, i.e. the 64-bit value
       //   V = m ? (m << 32) - (m - 1) : 0   ->  lo = m ? 1 - m : 0,  hi = m - [m > 1]
