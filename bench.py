@@ -27,7 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
 LOG_N = 22
 NTT_X, NTT_Y = 16384, 512
 NTT_BUTTERFLIES = NTT_X * NTT_Y * ((14 - 2) / 2 + (9 - 2) / 2 + 0.5)  # 83.9 M products per transform
-FR_MUL_WIDE_IMADS = 112  # Fr Montgomery product: 64 a*b + 48 reduction wide IMADs (r's two low limbs need no multiplier)
+FR_MUL_WIDE_IMADS = 120  # Fr Montgomery product as issued: 64 a*b + 56 reduction wide IMADs (r's lowest limb needs no product; ff.cuh reduce_row)
+FR_MUL_WIDE_IMADS_R01 = 112  # the count round 1 was judged on (the p1 product taken as add-with-carry chains instead)
 WIDE_PER_MADD = 6 * 288 + 2 * 222 + 432  # XYZZ mixed addition: 6 products + 2 dedicated squarings + the fused two-product Y3
 WIDE_PER_AFFINE_ADD = 5 * 288 + 222      # affine pair-tree addition: 3 products of Montgomery's trick + lambda, lambda^2, lambda*(x1 - x3)
 
@@ -475,10 +476,11 @@ def main():
                     "roofline_int32": {"bound": "int32", "unit": "T(32x32+64 IMAD.WIDE)/s", "achieved": NTT_BUTTERFLIES * FR_MUL_WIDE_IMADS / (kms * 1e-3) / 1e12,
                                        "peak": max(imad_wide, imad_wide_x) / 1e12,
                                        "frac": NTT_BUTTERFLIES * FR_MUL_WIDE_IMADS / (kms * 1e-3) / max(imad_wide, imad_wide_x),
+                                       "frac_at_112_per_product": NTT_BUTTERFLIES * FR_MUL_WIDE_IMADS_R01 / (kms * 1e-3) / max(imad_wide, imad_wide_x),
                                        "butterfly_stream": {"achieved_g_per_s": NTT_BUTTERFLIES / (kms * 1e-3) / 1e9, "measured_stream_g_per_s": bfly / 1e9},
                                        "note": "product-carrying butterflies of a 16384x512 transform: N*((log2 x - 2)/2 + (log2 y - 2)/2 + 1/2) = 83.9 M "
-                                               "(the radix-4 tail of each axis needs one product per four elements) x 112 wide IMADs per Fr product "
-                                               "(64 a*b + 48 reduction; ff.cuh) / the k_ntt_pass launches' event-timed duration; peak = the same measured "
+                                               "(the radix-4 tail of each axis needs one product per four elements) x 120 wide IMADs issued per Fr product "
+                                               "(64 a*b + 56 reduction as fused carry chains; ff.cuh; frac_at_112_per_product restates it on round 1's count) / the k_ntt_pass launches' event-timed duration; peak = the same measured "
                                                "IMAD.WIDE.U32 issue peak the MSM roofline uses"}}
             # e2e biNTT through the host-buffer entry point (pinned buffers)
             h_poly = torch.empty((nn, 4), dtype=torch.int64, pin_memory=True)

@@ -129,6 +129,23 @@ def test_full_snark_verifies_and_rejects_tampering(tiny):
     assert not VF.verify_snark(t["params"], t["sigma"], t["pre"], inst2, t["points"], t["scalars"])
 
 
+def test_verifier_rejects_malformed_inputs(tiny):
+    """What the reference's deserialisation and indexing refuse (verify-rust/src/lib.rs:150-170 indexes a_pub_*[i] and panics;
+    G1serde decoding never yields off-curve or non-canonical coordinates): a short instance, an off-curve proof point,
+    a coordinate >= q, an evaluation >= r raise instead of flowing into the pairing."""
+    t = tiny
+    short = copy.deepcopy(t["inst"])
+    short.a_pub_user = short.a_pub_user[:-1]
+    with pytest.raises(ValueError):
+        VF.verify_snark(t["params"], t["sigma"], t["pre"], short, t["points"], t["scalars"])
+    x, y = t["points"]["U"]
+    for bad_pt in ((x, (y + 1) % fr.Q_MOD), (x + fr.Q_MOD, y)):
+        with pytest.raises(ValueError):
+            VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], dict(t["points"], U=bad_pt), t["scalars"])
+    with pytest.raises(ValueError):
+        VF.verify_snark(t["params"], t["sigma"], t["pre"], t["inst"], t["points"], dict(t["scalars"], R_eval=t["scalars"]["R_eval"] + fr.R_MOD))
+
+
 def test_unsatisfied_witness_is_caught(tiny):
     """A corrupted internal wire breaks the R1CS: the quotient identity check of prove0 (prove/src/lib.rs:1546-1556) fails."""
     t = tiny
@@ -197,6 +214,13 @@ def test_native_loaders_match_the_python_readers(tmp_path):
         assert x.subcircuitId == y.subcircuitId and list(x.variables) == y.variables and x.variables[2] == y.variables[2]
     wt_a, wt_b = qap.WitnessTable(params, npl, infos), qap.WitnessTable(params, pl, infos)
     assert np.array_equal(wt_a.values, wt_b.values) and np.array_equal(wt_a.var_off, wt_b.var_off)
+    # one value moved from the first placement to the second keeps the total but shifts every later value: "Corrupted
+    # placement variables" like the per-placement check of the reference (iotools/mod.rs:505-520), not a silent shift
+    moved = copy.deepcopy(pl)
+    moved[1].variables.insert(0, moved[0].variables.pop())
+    F.write_synthesizer_output(str(tmp_path / "bad"), moved, perm, inst)
+    with pytest.raises(ValueError, match="Corrupted placement variables"):
+        F.read_synthesizer_output(str(tmp_path / "bad"), infos)
     lib = ffi.load()
 
     def parse(txt, cap=8):

@@ -238,6 +238,15 @@ def read_placement_variables_native(path, infos):
 
     data = open(os.path.join(path, "placementVariables.json"), "rb").read()
     ids = [int(m) for m in re.findall(rb'"subcircuitId"\s*:\s*(\d+)', data)]
+    # per-placement counts before the flat stream is split (the reference checks each placement: iotools/mod.rs:505-520):
+    # the hex strings of every "variables" array are counted with C-speed byte scans
+    segs = data.split(b'"variables"')[1:]
+    if len(segs) != len(ids):
+        raise ValueError("Corrupted placement variables.")
+    for i, seg in zip(ids, segs):
+        end = seg.find(b']')
+        if end < 0 or seg.count(b'"0x', 0, end) + seg.count(b'"0X', 0, end) != infos[i].Nwires:
+            raise ValueError("Corrupted placement variables.")
     total = sum(infos[i].Nwires for i in ids)
     vals = np.empty((total, 4), dtype=np.uint64)
     count = ctypes.c_size_t()

@@ -71,13 +71,32 @@ def eval_a_pub(params, instance, chi):
     """a_pub_X.eval(chi, zeta): the interpolant of the l_free public values over the l_free-th roots of unity."""
     from .fr import lagrange_bases_at
 
+    # the reference indexes a_pub_user[i] / a_pub_block[i] and panics on a short instance (verify-rust/src/lib.rs:150-170)
+    if len(instance.a_pub_user) < params.l_user or len(instance.a_pub_block) < params.l_free - params.l_user:
+        raise ValueError("instance has fewer public values than l_user / l_free - l_user")
     vals = list(instance.a_pub_user[:params.l_user]) + list(instance.a_pub_block[:params.l_free - params.l_user])
     lag = lagrange_bases_at(chi, params.l_free)
     return sum(v * b for v, b in zip(vals, lag)) % R_MOD
 
 
+def check_proof_encoding(points, scalars):
+    """Reject what the reference's deserialisation would never produce: coordinates >= q, points off y^2 = x^3 + 4
+    (the identity is None), evaluations >= r.  An off-curve point would otherwise flow into g1_add and the pairing."""
+    for name, p in points.items():
+        if p is None:
+            continue
+        x, y = p
+        if not (0 <= x < Q_MOD and 0 <= y < Q_MOD) or (y * y - x * x * x - 4) % Q_MOD != 0:
+            raise ValueError(f"proof point {name} is not a canonical point of G1's curve")
+    for name, v in scalars.items():
+        if not 0 <= v < R_MOD:
+            raise ValueError(f"proof scalar {name} is not a canonical element of Fr")
+
+
 def verify_snark(params, sigma, preprocess, instance, points, scalars, kappa2=None):
     """Verifier::verify_snark (verify-rust/src/lib.rs:243-289).  sigma needs G, H, x, y, lagrange_KL and sigma2."""
+    check_proof_encoding(points, scalars)
+    check_proof_encoding(preprocess, {})
     P = {k: _G(v) for k, v in points.items()}
     pre = {k: _G(v) for k, v in preprocess.items()}
     thetas, kappa0, chi, zeta, kappa1 = collect_challenges(points, scalars)
