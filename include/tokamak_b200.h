@@ -328,7 +328,8 @@ int32_t tkm_poly_kernel_time_last(tkm_ctx *ctx, float *out_ms);
 int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out);
 /* Micro-benchmarks: integer pipe peak (dependent-free IMAD / IMAD.WIDE streams) and field-mul rate.
  * kind: 0 = IMAD.U32, 1 = IMAD.WIDE.U32 (64-bit addend), 2 = Fr mul, 3 = Fq mul, 4 = XYZZ mixed add,
- * 5 = IMAD.WIDE.U32.X carry chains (the form the field multiplier issues), 6 = Fr NTT butterfly (product + add + sub).
+ * 5 = IMAD.WIDE.U32.X carry chains (the form the field multiplier issues), 6 = Fr NTT butterfly (product + add + sub),
+ * 7 = the same butterfly on the round-1 reduction (add-with-carry chains; kept for comparison).
  * out = ops/s. */
 int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s);
 

@@ -39,7 +39,8 @@ struct MsmGeom {
   uint32_t W;        // bucket windows (= Wd; 1 when precomputed tables fold every window into one bucket set)
   uint32_t B;        // buckets per window = 2^(c-1)
   uint32_t logB;
-  uint32_t nbuckets; // W*B (+1 trash bucket at index nbuckets)
+  uint32_t logWp;    // log2 of W rounded up to a power of two (0 when W == 1): bucket (w, d) lives at index (d << logWp) | w
+  uint32_t nbuckets; // B << logWp (+1 trash bucket at index nbuckets); slots with w >= W stay empty when W is not a power of two
   uint32_t g;        // bucket segment length for the window reduction
   uint32_t logg;
   uint32_t nseg;     // segments per window = B/g
@@ -47,15 +48,31 @@ struct MsmGeom {
 };
 
 static MsmGeom pick_geom(size_t n, uint32_t fixed_c = 0, uint32_t table_stride = 0) {
-  // minimise W*(n + 3*2^(c-1)) -- mixed adds plus ~3 madd-equivalents per bucket of reduction
+  // Cost of a window width in wide-IMAD units.  Without the pair tree: W*(n + 3*2^(c-1)) chained XYZZ mixed additions
+  // (2604 each; ~3 madd-equivalents per bucket of window reduction).  With it (>= 2^24 digit entries, >= 16 per bucket): the
+  // levels take all but 8..16 entries per bucket as affine additions (1662), the rest stays XYZZ, every level has a fixed
+  // cost (one inversion latency), the sort is 2 or 3 passes and the window reduction costs what was measured (2.1 ns per
+  // bucket).  Measured on B200 (profiles/r02_msm_c_level_sweep.log): c = 16 beats the old model's c = 19 by 16 % at 2^23
+  // (38.4 vs 45.8 ms) and 9 % at 2^24 (72.5 vs 79.3 ms) -- deep buckets are what the tree is good at.
   double best = 1e300;
   uint32_t bc = 8;
   // GLV halves cover 128 bits each (|k1|, |k2| < 2^127 plus the carry bit of the signed recoding).
   static const bool glv_off = getenv("TKM_MSM_NO_GLV") != nullptr;  // developer knob: plain 256-bit digits
   const bool use_glv = !fixed_c && !glv_off;
   for (uint32_t c = 4; c <= 20; c++) {
-    uint32_t W = use_glv ? 2 * ((128 + c - 1) / c) : (256 + c - 1) / c;
-    double cost = (double)W * ((double)n + 3.0 * (double)(1u << (c - 1)));
+    const uint32_t W = use_glv ? 2 * ((128 + c - 1) / c) : (256 + c - 1) / c;
+    const double B = (double)(1u << (c - 1)), M = (double)W * (double)n, avg = (double)n / B;
+    uint32_t L = 0;
+    if (avg >= 16.0 && M >= (double)(1u << 24))
+      while ((8u << (L + 1)) <= avg && L < 8) L++;
+    double cost;
+    if (L == 0) {
+      cost = 2604.0 * (double)W * ((double)n + 3.0 * B);
+    } else {
+      const double R = M / (double)(1u << L);
+      const double sort_passes = (c + 7) / 8;  // 8-bit digits over the c key bits that are not pre-sorted
+      cost = (M - R) * 1662.0 + R * 2604.0 + (double)W * B * 18000.0 + sort_passes * M * 75.0 + (double)L * 3.0e9;
+    }
     if (cost < best) {
       best = cost;
       bc = c;
@@ -75,7 +92,13 @@ static MsmGeom pick_geom(size_t n, uint32_t fixed_c = 0, uint32_t table_stride =
   m.W = fixed_c ? 1 : m.Wd;
   m.logB = bc - 1;
   m.B = 1u << m.logB;
-  m.nbuckets = m.W * m.B;
+  // Digit-major bucket numbering, window in the LOW bits of the key.  k_decompose emits the digit list window-major, so
+  // the list is already sorted by the low logWp key bits; a stable LSD radix sort over the remaining bits alone (the digit
+  // and the trash flag: c bits) leaves it sorted by the whole key -- 16 bits = two 8-bit passes at c = 16 instead of the three
+  // a 20-bit key needs.
+  m.logWp = 0;
+  while ((1u << m.logWp) < m.W) m.logWp++;
+  m.nbuckets = m.B << m.logWp;
   uint32_t want_logg = n < ((size_t)1 << 18) ? 3 : 4;  // segment length 8 / 16 (measured: shorter chains win when few buckets)
   if (const char *e = getenv("TKM_MSM_LOGG")) want_logg = (uint32_t)atoi(e);  // developer knob
   m.logg = m.logB < want_logg ? m.logB : want_logg;
@@ -123,7 +146,7 @@ __global__ void __launch_bounds__(256) k_decompose(const Fr *__restrict__ scalar
         signed_digit(limbs, nl, wi, m.c, carry, mag, neg);
         const uint32_t w = h * m.Wh + wi;
         size_t slot = (size_t)w * n + k;
-        keys[slot] = mag ? ((m.W == 1 ? 0u : w * m.B) + mag - 1) : m.nbuckets;
+        keys[slot] = mag ? (((mag - 1) << m.logWp) | (m.W == 1 ? 0u : w)) : m.nbuckets;
         vals[slot] = (base_idx + w * m.val_stride) | ((neg ^ flip) << 31);
       }
     }
@@ -785,17 +808,18 @@ __global__ void __launch_bounds__(SEG_THREADS) k_segreduce(const uint32_t *__res
 }
 
 // ---------------------------------------------------------------- 5. window reduction
-// Segment s of window w covers digits d = s*g+1 .. s*g+g (bucket slots w*B + s*g .. +g-1).
+// Segment s of window w covers digits d = s*g+1 .. s*g+g (bucket slots ((s*g + k) << logWp) | w, k < g).
 // run = sum B_d, acc = sum (d - s*g) B_d.  Then  sum_d d*B_d = sum_s acc_s + g * sum_s s*run_s.
 __global__ void __launch_bounds__(128) k_bucket_seg(const G1Xyzz *__restrict__ buckets, MsmGeom m, G1Xyzz *__restrict__ seg_acc,
                                                    G1Xyzz *__restrict__ seg_run) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t total = (size_t)m.W * m.nseg;
   if (t >= total) return;
-  const G1Xyzz *b = buckets + t * m.g;
+  const uint32_t w = (uint32_t)(t / m.nseg), sgm = (uint32_t)(t % m.nseg);
+  const G1Xyzz *b = buckets + (((size_t)sgm * m.g) << m.logWp) + w;
   G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
   for (int k = (int)m.g - 1; k >= 0; k--) {
-    G1Xyzz p = load_xyzz(b + k);
+    G1Xyzz p = load_xyzz(b + ((size_t)k << m.logWp));
     g1_add(run, p);
     g1_add(acc, run);
   }
@@ -1043,8 +1067,8 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   const size_t n = in.rows * in.cols;
   const size_t M = n * m.Wd;
   const uint32_t invalid = m.nbuckets;
-  uint32_t key_bits = 1;
-  while ((1ull << key_bits) <= invalid) key_bits++;
+  // the list leaves k_decompose sorted by the low logWp key bits (window-major); the stable sort covers the rest: digit + trash flag
+  const int sort_lo = (int)m.logWp, sort_hi = (int)(m.logWp + m.logB + 1);
 
   Scratch<uint32_t> keys, vals, keys_s, vals_s;
   TKM_TRY(keys.alloc(ctx, M));
@@ -1057,11 +1081,11 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   TKM_TRY(launch_check(ctx, "k_decompose"));
 
   size_t temp_bytes = 0;
-  TKM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)M, 0, (int)key_bits,
+  TKM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)M, sort_lo, sort_hi,
                                            ctx->stream));
   Scratch<uint8_t> temp;
   TKM_TRY(temp.alloc(ctx, temp_bytes));
-  TKM_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)M, 0, (int)key_bits,
+  TKM_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)M, sort_lo, sort_hi,
                                            ctx->stream));
   ctx->launches += 4;  // cub's histogram + onesweep passes (approximate; they are library launches)
 
@@ -1069,7 +1093,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   // buckets are deep enough to pay for the per-level fixed cost
   uint32_t L = 0;
   {
-    const double avg = (double)M / (double)m.nbuckets;  // entries per bucket
+    const double avg = (double)M / ((double)m.W * m.B);  // entries per populated bucket slot
     if (avg >= 16.0 && M >= ((size_t)1 << 24)) {  // below ~16 M entries (2^20 points) the levels' fixed cost (one inversion latency each) eats the saving
       while ((8u << (L + 1)) <= avg && L < TREE_MAX_LEVELS) L++;  // leaves runs of 8..16 entries for the XYZZ pass (measured best at 2^22)
     }
