@@ -96,8 +96,13 @@ int32_t tkm_fr_outer_product(tkm_ctx *ctx, const void *dev_col, const void *dev_
 /* out[k] = base^k, k < n, in Montgomery form on the device (the power vectors behind scale_coeffs, the vanishing and
  * permutation tables; resize_monomial_vec / extend_monomial_vec, vector_operations/mod.rs:674-693). */
 int32_t tkm_fr_powers(tkm_ctx *ctx, const uint8_t base32[32], void *dev_out, size_t n);
-/* dst[dst_idx[k]] = table[src_idx[k]] for k < n (u32 indices on the device, range-checked): the sparse overrides of the
+/* tkm_fr_gather: out[k] = table[idx[k]], k < n (u32 indices on the device, range-checked) -- the scalar vector of a
+ * sparse-gather MSM picked out of the device-resident placement variables (encode_statement_common collects
+ * placement_variables[i].variables[j] the same way on the host, group_structures/mod.rs:266-300).
+ * tkm_fr_scatter_from_table:
+ * dst[dst_idx[k]] = table[src_idx[k]] for k < n (u32 indices on the device, range-checked): the sparse overrides of the
  * permutation evaluation tables s0, s1 (Permutation::to_poly, libs/src/iotools/mod.rs:419-455) without a host round trip. */
+int32_t tkm_fr_gather(tkm_ctx *ctx, const void *dev_table, size_t table_len, const void *dev_idx, size_t n, void *dev_out);
 int32_t tkm_fr_scatter_from_table(tkm_ctx *ctx, void *dev_dst, size_t dst_len, const void *dev_dst_idx, const void *dev_table, size_t table_len,
                                   const void *dev_src_idx, size_t n);
 /* VecOps::transpose (vector_operations/mod.rs:139,168): rows x cols -> cols x rows, out != in. */
@@ -278,6 +283,14 @@ int32_t tkm_poly_commit(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, uint8_t o
  * The polynomial may be freed or modified after begin returns.  At most 32 tickets in flight. */
 int32_t tkm_poly_commit_begin(tkm_ctx *ctx, tkm_poly *p, const tkm_crs *crs, int32_t *out_ticket);
 int32_t tkm_commit_end(tkm_ctx *ctx, int32_t ticket, uint8_t out96[96]);
+/* The begin half for the plain and the sparse-gather MSM (tkm_msm_g1, tkm_msm_g1_indexed; tkm_commit_end resolves the
+ * ticket): Prover::init's binding commitments O_pub_free / O_mid / O_prv and their blinding terms (prove/src/lib.rs:1092-1176,
+ * group_structures/mod.rs:145-300) are independent of each other, so their tails overlap.  The device buffers may be
+ * released with tkm_dev_free (stream-ordered) as soon as begin returns. */
+int32_t tkm_msm_g1_begin(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, const void *dev_bases_mont, size_t n,
+                         int32_t *out_ticket);
+int32_t tkm_msm_g1_indexed_begin(tkm_ctx *ctx, const void *dev_scalars, int32_t scalars_mont, const void *dev_bases_mont,
+                                 const void *dev_idx, size_t n, int32_t *out_ticket);
 
 /* ---- multi-GPU (the reference pins device 0, libs/src/utils/mod.rs:90-96, so this is new surface) --------
  * One context per GPU -- one process per GPU, or several contexts in one process.  NCCL (over NVLink/NVSwitch) is the

@@ -93,6 +93,20 @@ __global__ void __launch_bounds__(256) k_scatter_from_table(Fr *__restrict__ dst
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[dst_idx[k]] = table[src_idx[k]];
 }
 
+// out[k] = table[idx[k]] (out-of-range indices are flagged and read nothing): the scalar side of the sparse-gather MSMs.
+__global__ void __launch_bounds__(256) k_fr_gather(Fr *__restrict__ out, const Fr *__restrict__ table, size_t table_len, const uint32_t *__restrict__ idx, size_t n,
+                                                   uint32_t *__restrict__ bad) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t i = idx[k];
+    if (i >= table_len) {
+      *bad = 1;
+      out[k] = Fr::zero();
+    } else {
+      out[k] = table[i];
+    }
+  }
+}
+
 // ---- micro-benchmarks: dependent-free integer streams and field-op rates (ops/s over the whole GPU)
 template <int KIND>
 __global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
@@ -405,6 +419,21 @@ int32_t tkm_fr_scatter_from_table(tkm_ctx *ctx, void *dev_dst, size_t dst_len, c
                                                                                 (const uint32_t *)dev_src_idx, n);
   return launch_check(ctx, "k_scatter_from_table");
 }
+int32_t tkm_fr_gather(tkm_ctx *ctx, const void *dev_table, size_t table_len, const void *dev_idx, size_t n, void *dev_out) {
+  API_BEGIN
+  if (n == 0) return TKM_OK;
+  TKM_REQUIRE(dev_table && dev_idx && dev_out, "null argument");
+  Scratch<uint32_t> bad;
+  TKM_TRY(bad.alloc(ctx, 1));
+  TKM_CUDA(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
+  k_fr_gather<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>((Fr *)dev_out, (const Fr *)dev_table, table_len, (const uint32_t *)dev_idx, n, bad.p);
+  TKM_TRY(launch_check(ctx, "k_fr_gather"));
+  uint32_t h_bad = 0;
+  TKM_CUDA(cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TKM_CUDA(cudaStreamSynchronize(ctx->stream));
+  TKM_REQUIRE(!h_bad, "gather index out of range");
+  return TKM_OK;
+}
 int32_t tkm_fr_outer_product(tkm_ctx *ctx, const void *col, const void *row, void *out, size_t rows, size_t cols) {
   API_BEGIN
   TKM_REQUIRE((col && row && out) || rows * cols == 0, "null argument");
@@ -528,6 +557,31 @@ int32_t tkm_msm_g1_indexed(tkm_ctx *ctx, const void *scalars, int32_t scalars_mo
   in.cols = n;
   in.idx = (const uint32_t *)idx;
   return msm_run(ctx, in, out96);
+}
+static int32_t msm_begin_common(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, const void *bases, const void *idx, size_t n, int32_t *out_ticket) {
+  MsmInput in;
+  in.scalars = (const Fr *)scalars;
+  in.scalars_mont = scalars_mont != 0;
+  in.scalar_row_stride = n;
+  in.bases = (const G1Affine *)bases;
+  in.base_row_stride = n;
+  in.rows = 1;
+  in.cols = n;
+  in.idx = (const uint32_t *)idx;
+  return msm_run_async(ctx, in, out_ticket);
+}
+int32_t tkm_msm_g1_begin(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, const void *bases, size_t n, int32_t *out_ticket) {
+  API_BEGIN
+  TKM_REQUIRE(out_ticket, "null out pointer");
+  TKM_REQUIRE(n == 0 || (scalars && bases), "null argument");
+  return msm_begin_common(ctx, scalars, scalars_mont, bases, nullptr, n, out_ticket);
+}
+int32_t tkm_msm_g1_indexed_begin(tkm_ctx *ctx, const void *scalars, int32_t scalars_mont, const void *bases, const void *idx, size_t n,
+                                 int32_t *out_ticket) {
+  API_BEGIN
+  TKM_REQUIRE(out_ticket, "null out pointer");
+  TKM_REQUIRE(n == 0 || (scalars && bases && idx), "null argument");
+  return msm_begin_common(ctx, scalars, scalars_mont, bases, idx, n, out_ticket);
 }
 int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint8_t out96[96]) {
   API_BEGIN

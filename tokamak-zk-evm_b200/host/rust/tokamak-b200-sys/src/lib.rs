@@ -109,6 +109,10 @@ extern "C" {
                                out_r: *mut *mut tkm_poly) -> i32;
     pub fn tkm_poly_commit_begin(ctx: *mut tkm_ctx, p: *mut tkm_poly, crs: *const tkm_crs, out_ticket: *mut i32) -> i32;
     pub fn tkm_commit_end(ctx: *mut tkm_ctx, ticket: i32, out96: *mut u8) -> i32;
+    pub fn tkm_msm_g1_begin(ctx: *mut tkm_ctx, dev_scalars: *const c_void, scalars_mont: i32, dev_bases_mont: *const c_void, n: usize,
+                            out_ticket: *mut i32) -> i32;
+    pub fn tkm_msm_g1_indexed_begin(ctx: *mut tkm_ctx, dev_scalars: *const c_void, scalars_mont: i32, dev_bases_mont: *const c_void,
+                                    dev_idx: *const c_void, n: usize, out_ticket: *mut i32) -> i32;
     pub fn tkm_r1cs_uvw_polys(ctx: *mut tkm_ctx, s_d: u32, n_rows: *const u32, rp_base: *const u64, row_ptr: *const u32, row_ptr_len: usize,
                               wire: *const u32, coeff32: *const u8, nnz: usize, sub_of_col: *const u32, var_off: *const u64,
                               witness32: *const u8, n_vars: usize, n: usize, s_max: usize, out_u: *mut *mut tkm_poly,
@@ -140,6 +144,7 @@ extern "C" {
     pub fn tkm_bintt_sharded(ctx: *mut tkm_ctx, dev_in: *const c_void, dev_out: *mut c_void, x_size: usize, y_size: usize, dir: i32,
                              coset_x32: *const u8, coset_y32: *const u8) -> i32;
     pub fn tkm_fr_powers(ctx: *mut tkm_ctx, base32: *const u8, dev_out: *mut c_void, n: usize) -> i32;
+    pub fn tkm_fr_gather(ctx: *mut tkm_ctx, dev_table: *const c_void, table_len: usize, dev_idx: *const c_void, n: usize, dev_out: *mut c_void) -> i32;
     pub fn tkm_fr_scatter_from_table(ctx: *mut tkm_ctx, dev_dst: *mut c_void, dst_len: usize, dev_dst_idx: *const c_void, dev_table: *const c_void,
                                      table_len: usize, dev_src_idx: *const c_void, n: usize) -> i32;
 }

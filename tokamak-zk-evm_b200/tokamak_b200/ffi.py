@@ -39,6 +39,7 @@ SIGNATURES = {
     "tkm_fr_vec_reduce": [c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p],
     "tkm_fr_outer_product": [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t],
     "tkm_fr_powers": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "tkm_fr_gather": [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p],
     "tkm_fr_scatter_from_table": [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t],
     "tkm_fr_suffix_product": [c_void_p, c_void_p, c_void_p, c_size_t],
     "tkm_bintt": [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int32, c_void_p, c_void_p],
@@ -95,6 +96,8 @@ SIGNATURES = {
     "tkm_poly_commit": [c_void_p, c_void_p, c_void_p, c_void_p],
     "tkm_poly_commit_begin": [c_void_p, c_void_p, c_void_p, P(c_int32)],
     "tkm_commit_end": [c_void_p, c_int32, c_void_p],
+    "tkm_msm_g1_begin": [c_void_p, c_void_p, c_int32, c_void_p, c_size_t, P(c_int32)],
+    "tkm_msm_g1_indexed_begin": [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, P(c_int32)],
     "tkm_comm_unique_id": [c_void_p],
     "tkm_comm_init": [c_void_p, c_void_p, c_int32, c_int32],
     "tkm_comm_destroy": [c_void_p],

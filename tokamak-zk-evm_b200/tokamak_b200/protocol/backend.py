@@ -180,6 +180,102 @@ class GpuBackend:
         ctx.dev_free(d_i)
         return g1_to_tuple(out)
 
+    def msm_indexed_async(self, table, idx, scalars):
+        """tkm_msm_g1_indexed_begin: the same sparse-gather MSM queued; .get() resolves it (tkm_commit_end)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        s = _as_fr_array(scalars)
+        n = idx.shape[0]
+        if n == 0:
+            return None
+        assert s.shape[0] == n
+        ctx = self.ctx
+        d_s = ctx.upload_fr(s, to_mont=False)
+        d_i = ctx.dev_alloc(n * 4)
+        ctx.h2d(d_i, idx)
+        t = ctypes.c_int32()
+        check(ctx.lib.tkm_msm_g1_indexed_begin(ctx.h, d_s, 0, table.device_ptr(), d_i, n, ctypes.byref(t)))
+        ctx.dev_free(d_s)  # stream-ordered: released after the queued kernels have read them
+        ctx.dev_free(d_i)
+        return _PendingCommit(ctx, t.value)
+
+    # ---- placement variables kept on the device for the duration of Prover.init
+    def witness_device(self, wt):
+        """The witness table (canonical limbs) uploaded once per WitnessTable; released by release_witness."""
+        dev = getattr(wt, "_dev", None)
+        if dev is None:
+            dev = self.ctx.upload_fr(wt.values, to_mont=False)
+            wt._dev = dev
+        return dev
+
+    def release_witness(self, wt):
+        dev = getattr(wt, "_dev", None)
+        if dev is not None:
+            self.ctx.dev_free(dev)
+            wt._dev = None
+
+    def msm_indexed_witness(self, table, idx, wt, rows, defer=False):
+        """sum_k values[rows[k]] * table[idx[k]]: the scalars are gathered on the device (tkm_fr_gather) from the resident
+        witness table, so only the two u32 index vectors cross PCIe."""
+        n = idx.shape[0]
+        if n == 0:
+            return None
+        ctx = self.ctx
+        d_vals = self.witness_device(wt)
+        d_i, d_r, d_s = ctx.dev_alloc(n * 4), ctx.dev_alloc(n * 4), ctx.dev_alloc(n * 32)
+        ctx.h2d(d_i, idx)
+        ctx.h2d(d_r, rows)
+        check(ctx.lib.tkm_fr_gather(ctx.h, d_vals, wt.values.shape[0], d_r, n, d_s))
+        t = ctypes.c_int32()
+        check(ctx.lib.tkm_msm_g1_indexed_begin(ctx.h, d_s, 0, table.device_ptr(), d_i, n, ctypes.byref(t)))
+        for p_ in (d_i, d_r, d_s):
+            ctx.dev_free(p_)  # stream-ordered
+        pend = _PendingCommit(ctx, t.value)
+        return pend if defer else pend.get()
+
+    def interface_poly(self, params, wt):
+        """gen_bXY (polynomial_structures/mod.rs:132-162) on the device: the interface wires' values scattered from the
+        resident witness table into an m_I x s_max evaluation table, then one inverse biNTT.  Nothing of that size is
+        built on the host."""
+        ctx, lib = self.ctx, self.ctx.lib
+        m_i, s_max = params.l_D - params.l, params.s_max
+        n = m_i * s_max
+        idx, rows = wt.gather_indices(params.l, params.l_D, s_max)
+        k = idx.shape[0]
+        d_vals = self.witness_device(wt)
+        d_ev = ctx.dev_alloc(n * 32)
+        from .. import fr_bytes
+
+        check(lib.tkm_fr_vec_fill(ctx.h, fr_bytes(0)[1], d_ev, n))
+        if k:
+            d_i, d_r = ctx.dev_alloc(k * 4), ctx.dev_alloc(k * 4)
+            ctx.h2d(d_i, idx)
+            ctx.h2d(d_r, rows)
+            check(lib.tkm_fr_scatter_from_table(ctx.h, d_ev, n, d_i, d_vals, wt.values.shape[0], d_r, k))
+            ctx.dev_free(d_i)
+            ctx.dev_free(d_r)
+        check(lib.tkm_fr_to_mont(ctx.h, d_ev, d_ev, n))
+        h = ctypes.c_void_p()
+        check(lib.tkm_poly_from_device(ctx.h, d_ev, m_i, s_max, ctypes.byref(h)))
+        ctx.dev_free(d_ev)
+        q = DensePolynomialExt(ctx, h)
+        check(lib.tkm_poly_ntt_inplace(ctx.h, q.h, 1, None, None))
+        return q
+
+    def msm_points_async(self, points, scalars):
+        """msm_points queued (tkm_msm_g1_begin over freshly uploaded points)."""
+        ctx = self.ctx
+        pts = np.ascontiguousarray(np.stack([g1_from_tuple(p) for p in points]), dtype=np.uint64)
+        n = pts.shape[0]
+        d_p = ctx.dev_alloc(n * 96)
+        ctx.h2d(d_p, pts)
+        check(ctx.lib.tkm_g1_bases_to_mont(ctx.h, d_p, d_p, n))
+        d_s = ctx.upload_fr(frs_from_ints([k % R_MOD for k in scalars]), to_mont=False)
+        t = ctypes.c_int32()
+        check(ctx.lib.tkm_msm_g1_begin(ctx.h, d_s, 0, d_p, n, ctypes.byref(t)))
+        ctx.dev_free(d_s)
+        ctx.dev_free(d_p)
+        return _PendingCommit(ctx, t.value)
+
     def msm_points(self, points, scalars):
         """msm_g1_bases over a handful of host points (the blinding terms of the binding)."""
         pts = np.stack([g1_from_tuple(p) for p in points])

@@ -126,7 +126,10 @@ class Prover:
         self.uXY, self.vXY, self.wXY = backend.uvw_polys(p, csr, wt)
         self.t.add("init.build.witness.uvwXY", time.perf_counter() - t1)
         t1 = time.perf_counter()
-        self.bXY = backend.from_rou_evals(qap.interface_evals_from_table(p, wt), m_i, s_max)
+        if hasattr(backend, "interface_poly"):  # scattered on the device from the resident witness table
+            self.bXY = backend.interface_poly(p, wt)
+        else:
+            self.bXY = backend.from_rou_evals(qap.interface_evals_from_table(p, wt), m_i, s_max)
         self.t.add("init.build.witness.bXY", time.perf_counter() - t1)
         self.rXY = None
         t1 = time.perf_counter()
@@ -151,6 +154,8 @@ class Prover:
         self.t.add("init.build", time.perf_counter() - t0)
         t1 = time.perf_counter()
         self.binding = self._binding(placements, infos, wt)
+        if hasattr(backend, "release_witness"):
+            backend.release_witness(wt)
         self.t.add("init.binding", time.perf_counter() - t1)
         self.t.add("init", time.perf_counter() - t0)
 
@@ -213,19 +218,24 @@ class Prover:
     def _binding(self, placements, infos, wt):
         be, p, sg, mx = self.be, self.p, self.sigma, self.mixer
         A_free = self.encode(self.a_free_X, "A_free")
-        O_pub_free = sg.encode_O_pub_free(be, placements, infos, p)
-        O_mid_core = sg.encode_O_mid_no_zk(be, wt, p)
-        O_prv_core = sg.encode_O_prv_no_zk(be, wt, p)
+        # the four encodings and the two blinding sums are independent: a backend that can queue MSMs returns pending handles
+        # and the serial tails overlap (one wait at the end instead of six)
+        O_pub_free = sg.encode_O_pub_free(be, placements, infos, p, defer=True)
+        O_mid_core = sg.encode_O_mid_no_zk(be, wt, p, defer=True)
+        O_prv_core = sg.encode_O_prv_no_zk(be, wt, p, defer=True)
+        msm_points = be.msm_points_async if hasattr(be, "msm_points_async") else be.msm_points
         # zero-knowledge terms (prove/src/lib.rs:1131-1160): the 17 scalar multiples as two small MSMs
-        O_mid = be.g1_add(O_mid_core, be.msm_points([sg.delta], [mx.rO_mid]))
+        zk_mid = msm_points([sg.delta], [mx.rO_mid])
         terms = [(sg.eta, (-mx.rO_mid) % R_MOD), (sg.delta_inv_alphak_xh_tx[0][0], mx.rU_X), (sg.delta_inv_alphak_xh_tx[1][0], mx.rV_X)]
         terms += [(sg.delta_inv_alphak_xh_tx[2][h], mx.rW_X[h]) for h in range(3)]
         terms += [(sg.delta_inv_alpha4_xj_tx[j], mx.rB_X[j]) for j in range(2)]
         terms += [(sg.delta_inv_alphak_yi_ty[0][0], mx.rU_Y), (sg.delta_inv_alphak_yi_ty[1][0], mx.rV_Y)]
         terms += [(sg.delta_inv_alphak_yi_ty[2][i], mx.rW_Y[i]) for i in range(3)]
         terms += [(sg.delta_inv_alphak_yi_ty[3][i], mx.rB_Y[i]) for i in range(2)]
-        O_prv = be.g1_add(O_prv_core, be.msm_points([t[0] for t in terms], [t[1] for t in terms]))
-        return self._resolve({"A_free": A_free, "O_pub_free": O_pub_free, "O_mid": O_mid, "O_prv": O_prv})
+        zk_prv = msm_points([t[0] for t in terms], [t[1] for t in terms])
+        r = self._resolve({"A_free": A_free, "O_pub_free": O_pub_free, "O_mid_core": O_mid_core, "O_prv_core": O_prv_core, "zk_mid": zk_mid, "zk_prv": zk_prv})
+        return {"A_free": r["A_free"], "O_pub_free": r["O_pub_free"], "O_mid": be.g1_add(r["O_mid_core"], r["zk_mid"]),
+                "O_prv": be.g1_add(r["O_prv_core"], r["zk_prv"])}
 
     # ---- prove0 (prove/src/lib.rs:1446-1782)
     def prove0(self):

@@ -121,17 +121,29 @@ class WitnessTable:
         self.values = np.frombuffer(b"".join(chunks), dtype=np.uint64).reshape(-1, 4)
         self.fmap = [np.array(s.flattenMap, dtype=np.int64) for s in infos]
 
-    def gather(self, lo, hi, s_max):
-        """Every (placement, wire) whose global wire index lies in [lo, hi): -> (table index (g - lo) * s_max + col, values)."""
+    def gather_indices(self, lo, hi, s_max):
+        """Every (placement, wire) whose global wire index lies in [lo, hi): -> (table index (g - lo) * s_max + col, row of
+        the value in self.values), both uint32.  The selection depends only on the subcircuit, so it is computed once per
+        subcircuit and shifted per placement."""
+        cache = self.__dict__.setdefault("_sel_cache", {})
         idx, rows = [], []
         for col, pl in enumerate(self.placements):
-            fm = self.fmap[pl.subcircuitId]
-            sel = np.nonzero((fm >= lo) & (fm < hi))[0]
-            idx.append((fm[sel] - lo) * s_max + col)
+            key = (pl.subcircuitId, lo, hi, s_max)
+            if key not in cache:
+                fm = self.fmap[pl.subcircuitId]
+                sel = np.nonzero((fm >= lo) & (fm < hi))[0]
+                cache[key] = ((fm[sel] - lo) * s_max, sel)
+            base_idx, sel = cache[key]
+            idx.append(base_idx + col)
             rows.append(sel + int(self.var_off[col]))
         idx = np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
         rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
-        return idx.astype(np.uint32), np.ascontiguousarray(self.values[rows])
+        return idx.astype(np.uint32), rows.astype(np.uint32)
+
+    def gather(self, lo, hi, s_max):
+        """gather_indices with the values collected on the host: -> (table index, values)."""
+        idx, rows = self.gather_indices(lo, hi, s_max)
+        return idx, np.ascontiguousarray(self.values[rows])
 
 
 def interface_evals_from_table(params, wt: WitnessTable):

@@ -80,7 +80,22 @@ class Sigma:
         """[P(x, y)]_1 over xy_powers (impl_encode_poly!)."""
         return backend.commit(self.xy_powers, poly)
 
-    def encode_O_pub_free(self, backend, placements, infos, params):
+    @staticmethod
+    def _msm_indexed(backend, defer):
+        """The sparse-gather MSM of the backend; with defer=True and a backend that can queue it, a pending handle
+        (.get()) so that independent encodings overlap their serial tails."""
+        return backend.msm_indexed_async if defer and hasattr(backend, "msm_indexed_async") else backend.msm_indexed
+
+    def _encode_statement(self, backend, table, witness_table, lo, hi, s_max, defer):
+        """encode_statement_common (group_structures/mod.rs:266-300).  A backend that keeps the placement variables on the
+        device (msm_indexed_witness) receives only the two index vectors; otherwise the values are collected on the host."""
+        if hasattr(backend, "msm_indexed_witness"):
+            idx, rows = witness_table.gather_indices(lo, hi, s_max)
+            return backend.msm_indexed_witness(table, idx, witness_table, rows, defer)
+        idx, vals = witness_table.gather(lo, hi, s_max)
+        return self._msm_indexed(backend, defer)(table, idx, vals)
+
+    def encode_O_pub_free(self, backend, placements, infos, params, defer=False):
         """encode_o_pub_free_common: the public sides of bufferPubOut (outputs), bufferPubIn and bufferBlockIn (inputs)
         against gamma_inv_o_inst; bufferEVMIn belongs to O_pub_fix."""
         import numpy as np
@@ -99,7 +114,7 @@ class Sigma:
             for j in range(s0, s0 + cnt):
                 idx.append(info.flattenMap[j])
                 sc.append(pl.variables[j])
-        return backend.msm_indexed(self.gamma_inv_o_inst, np.array(idx, dtype=np.uint32), frs_from_ints(sc))
+        return self._msm_indexed(backend, defer)(self.gamma_inv_o_inst, np.array(idx, dtype=np.uint32), frs_from_ints(sc))
 
     def encode_O_pub_fix(self, backend, a_pub_function, params):
         """encode_o_pub_fix_common: the function instance against the last m_function entries of gamma_inv_o_inst."""
@@ -115,15 +130,13 @@ class Sigma:
         start = params.l - m_function
         return backend.msm_indexed(self.gamma_inv_o_inst, np.arange(start, start + m_function, dtype=np.uint32), frs_from_ints(a_pub_function))
 
-    def encode_O_mid_no_zk(self, backend, witness_table, params):
+    def encode_O_mid_no_zk(self, backend, witness_table, params, defer=False):
         """encode_statement_common over the interface wires [l, l_D) against eta_inv_li_o_inter_alpha4_kj[wire][placement]."""
-        idx, vals = witness_table.gather(params.l, params.l_D, params.s_max)
-        return backend.msm_indexed(self.eta_inv_li_o_inter_alpha4_kj, idx, vals)
+        return self._encode_statement(backend, self.eta_inv_li_o_inter_alpha4_kj, witness_table, params.l, params.l_D, params.s_max, defer)
 
-    def encode_O_prv_no_zk(self, backend, witness_table, params):
+    def encode_O_prv_no_zk(self, backend, witness_table, params, defer=False):
         """encode_statement_common over the private wires [l_D, m_D) against delta_inv_li_o_prv[wire][placement]."""
-        idx, vals = witness_table.gather(params.l_D, params.m_D, params.s_max)
-        return backend.msm_indexed(self.delta_inv_li_o_prv, idx, vals)
+        return self._encode_statement(backend, self.delta_inv_li_o_prv, witness_table, params.l_D, params.m_D, params.s_max, defer)
 
 
 def generate(backend, params, infos, r1cs_list, tau: Tau, g1_gen=G1_FIXED, g2_gen=G2_FIXED):
