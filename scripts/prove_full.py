@@ -13,7 +13,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tokamak-zk-evm_b200"))
 
 
-def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: None, log=lambda *a: None, sigma=None, keep_sigma=False, warmup=0, from_files=True, crs_load=False):
+def real_library_inputs(path, n_placements=166, seed=5):
+    """The reference's checked-in circuit library (tests/golden/real_library.json.xz, packed by tests/golden/gen_real_library.py)
+    with a seeded dataflow of `n_placements` placements (the template transaction uses 166) and a seeded, UNSATISFYING witness
+    (the circom witness calculators cannot run here): inputs for a timing-only prove on the real constraint sparsity."""
+    from tokamak_b200.protocol import formats as F
+    from tokamak_b200.protocol import synthetic as S
+
+    params, infos, r1cs = F.read_packed_library(path)
+    pl, perm, inst = S.synthesize(params, infos, r1cs, n_placements=n_placements, seed=seed, solver=S.fill_witness_unchecked(seed + 1))
+    inst.a_pub_block = list(inst.a_pub_block) + [0] * (params.l_free - params.l_user - len(inst.a_pub_block))  # padded to l_free like instance.json
+    return params, infos, r1cs, pl, perm, inst
+
+
+def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: None, log=lambda *a: None, sigma=None, keep_sigma=False, warmup=0, from_files=True, crs_load=False,
+        inputs=None):
     from tokamak_b200.protocol import preprocess as PP
     from tokamak_b200.protocol import prover as PV
     from tokamak_b200.protocol import qap
@@ -22,8 +36,11 @@ def run(be, spec, repeats=3, verify=True, fixed_base_tables=False, sync=lambda: 
     from tokamak_b200.protocol import verifier as VF
 
     t = time.perf_counter()
-    params, infos, r1cs = S.make_library(spec)
-    pl, perm, inst = S.synthesize(params, infos, r1cs, small_value_fraction=0.5)
+    if inputs is not None:
+        params, infos, r1cs, pl, perm, inst = inputs
+    else:
+        params, infos, r1cs = S.make_library(spec)
+        pl, perm, inst = S.synthesize(params, infos, r1cs, small_value_fraction=0.5)
     if be.name == "b200":
         # the in-memory synthesizer output holds every placement's variables as an array of canonical limbs -- exactly what the
         # library's native loader (tkm_host_parse_hex_scalars) returns for placementVariables.json -- not as Python integers

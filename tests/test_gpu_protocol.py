@@ -109,6 +109,34 @@ def test_r1cs_uvw_polys_against_host_products(backends):
     assert rc == T.ffi.TKM_ERR_INVALID_ARGUMENT if hasattr(T.ffi, "TKM_ERR_INVALID_ARGUMENT") else rc != 0
 
 
+def test_r1cs_uvw_polys_on_the_reference_library(backends):
+    """The same kernel on the REAL constraint structure: the reference's 14-subcircuit library (packed fixture
+    tests/golden/real_library.json.xz, made by tests/golden/gen_real_library.py from the in-tree .r1cs binaries; 81 624
+    non-zeros, 470 distinct coefficients, rows of up to 131 terms) with 40 placements and a seeded witness.  The products
+    A w, B w, C w do not depend on satisfiability, so the literal per-placement dot products are the oracle."""
+    import os
+
+    import oracle_ffi as O
+    from tokamak_b200.protocol import formats as F
+    from tokamak_b200.protocol import qap
+
+    gpu, _ = backends
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_library.json.xz")
+    params, infos, r1cs = F.read_packed_library(path)
+    assert (params.m_D, params.s_D, params.l, params.n, params.s_max) == (26591, 14, 728, 4096, 256)
+    pl, _, _ = S.synthesize(params, infos, r1cs, n_placements=40, seed=21, solver=S.fill_witness_unchecked(22))
+    gpu.init_ntt_domain(params.n * params.s_max)
+    csr, wt = qap.LibraryCSR(r1cs), qap.WitnessTable(params, pl, infos)
+    got = gpu.uvw_polys(params, csr, wt)
+    from oracle_backend import uvw_evals
+
+    exp = uvw_evals(params, pl, r1cs)
+    for g, e in zip(got, exp):
+        assert g.shape == (params.n, params.s_max)
+        assert np.array_equal(g.to_rou_evals(), e)
+    assert np.array_equal(got[0].copy_coeffs(), O.bintt(exp[0], params.n, params.s_max, True))
+
+
 def test_random_polynomial_programs_gpu_vs_oracle(backends):
     """Differential fuzz: random sequences of DensePolynomialExt operations (mismatched shapes, zero polynomials, scalar
     forms, monomial shifts, coefficient scalings, divisions, evaluations) on the GPU engine and on its CPU twin; the padded

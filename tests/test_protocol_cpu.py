@@ -85,6 +85,26 @@ def test_r1cs_reader_on_the_reference_library():
         assert getattr(mine, k) == ref[k], k
 
 
+def test_packed_real_library_fixture():
+    """tests/golden/real_library.json.xz (the reference's circuit library packed by tests/golden/gen_real_library.py): shapes
+    of setupParams.json / subcircuitInfo.json, and -- where the reference tree is present -- every constraint equal to the
+    .r1cs binaries; a dataflow with a seeded witness keeps the reference's wire partition (O_pub_free = 109 public wires)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    params, infos, r1cs = F.read_packed_library(os.path.join(here, "golden", "real_library.json.xz"))
+    params.validate()
+    assert (params.l_free, params.l_user_out, params.l_user, params.l, params.l_D, params.m_D, params.n, params.s_D, params.s_max) == (128, 65, 85, 728, 4824, 26591, 4096, 14, 256)
+    assert [s.name for s in infos[:5]] == ["bufferPubOut", "bufferPubIn", "bufferBlockIn", "bufferEVMIn", "bufferPrvIn"]
+    assert sum(len(lc) for r in r1cs for abc in r.constraints for lc in abc) == 81624
+    lib = "/root/reference/packages/frontend/qap-compiler/subcircuits/library"
+    if os.path.isdir(lib):
+        for s, r in zip(infos, r1cs):
+            assert F.read_r1cs(os.path.join(lib, "r1cs", f"subcircuit{s.id}.r1cs")).constraints == r.constraints
+    pl, perm, inst = S.synthesize(params, infos, r1cs, n_placements=12, seed=3, solver=S.fill_witness_unchecked(4))
+    assert len(inst.a_pub_user) == params.l_user and len(inst.a_pub_function) == params.l - params.l_free
+    assert len(inst.a_pub_user) + len(inst.a_pub_block) == 109  # SURVEY.md 8a: O_pub_free has 109 points
+    assert all(0 <= p.row < params.m_i and 0 <= p.X < params.m_i for p in perm)
+
+
 @pytest.fixture(scope="module")
 def tiny():
     from oracle_backend import OracleBackend

@@ -200,6 +200,36 @@ def read_library_meta(qap_path):
     return params, infos
 
 
+def read_packed_library(path):
+    """The circuit library in the packed form tests/golden/gen_real_library.py writes (setupParams, subcircuitInfo, the
+    .r1cs matrices as CSR row lengths / wire indices / indices into one coefficient table; lzma-compressed JSON):
+    -> (SetupParams, [SubcircuitInfo], [R1CS]) like read_library."""
+    import lzma
+
+    with lzma.open(path, "rt") as f:
+        doc = json.load(f)
+    params = SetupParams(**doc["setupParams"])
+    infos = [SubcircuitInfo(**d) for d in doc["subcircuitInfo"]]
+    coeffs = [int(c, 16) for c in doc["coeffs"]]
+    r1cs = []
+    for s, d in zip(infos, doc["r1cs"]):
+        if d["id"] != s.id or d["n_wires"] != s.Nwires or d["n_constraints"] != s.Nconsts or len(d["lens"]) != 3 * s.Nconsts:
+            raise ValueError(f"packed library: shape mismatch for subcircuit {s.id}")
+        cons, pos = [], 0
+        wires, cidx, lens = d["wires"], d["coeff_idx"], d["lens"]
+        for row in range(s.Nconsts):
+            abc = []
+            for m in range(3):
+                k = lens[3 * row + m]
+                abc.append([(wires[pos + t], coeffs[cidx[pos + t]]) for t in range(k)])
+                pos += k
+            cons.append(tuple(abc))
+        if pos != len(wires) or any(w >= s.Nwires for w in wires):
+            raise ValueError(f"packed library: corrupt CSR for subcircuit {s.id}")
+        r1cs.append(R1CS(s.Nwires, s.Nconsts, cons))
+    return params, infos, r1cs
+
+
 def read_library(qap_path):
     params = SetupParams(**json.load(open(os.path.join(qap_path, "setupParams.json"))))
     infos = [SubcircuitInfo(**{k: d[k] for k in ("id", "name", "Nwires", "Nconsts", "Out_idx", "In_idx", "flattenMap")})

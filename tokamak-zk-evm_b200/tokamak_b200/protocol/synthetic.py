@@ -152,13 +152,33 @@ def check_r1cs(r: R1CS, w):
     return True
 
 
-def synthesize(params: SetupParams, infos, r1cs, n_placements=None, seed=2, small_value_fraction=0.0):
-    """A random dataflow over the library: -> (placements, permutation, instance).
+def fill_witness_unchecked(seed=7):
+    """A stand-in for the witness calculators the real library needs (circom wasm, not runnable here): wire 0 = 1, the
+    inputs as given, every other wire a seeded random field element.  The constraints are NOT satisfied -- for timing-only
+    proves and for kernels whose result does not depend on satisfiability (the sparse R1CS x witness products)."""
+    rng = random.Random(seed)
+
+    def solve(r: R1CS, info: SubcircuitInfo, inputs):
+        w = [rng.randrange(R_MOD) for _ in range(r.n_wires)]
+        w[0] = 1
+        i0, n_in = info.In_idx
+        assert len(inputs) == n_in
+        for k, v in enumerate(inputs):
+            w[i0 + k] = v % R_MOD
+        return w
+
+    return solve
+
+
+def synthesize(params: SetupParams, infos, r1cs, n_placements=None, seed=2, small_value_fraction=0.0, solver=None):
+    """A random dataflow over the library: -> (placements, permutation, instance).  `solver` replaces the forward
+    evaluation of a subcircuit (solve_witness) -- fill_witness_unchecked for libraries that are not forward-solvable.
 
     Columns 0..4 are the five buffers; every later column is a compute subcircuit whose inputs are copies of values
     produced earlier (outputs of the input buffers or of earlier subcircuits); bufferPubOut's inputs copy subcircuit
     outputs.  Copy constraints are emitted as cycles over (interface wire, placement) nodes (permutation.json)."""
     rng = random.Random(seed)
+    solve_witness = solver or globals()["solve_witness"]
     s_max, l = params.s_max, params.l
     n_pl = s_max if n_placements is None else n_placements
     assert 6 <= n_pl <= s_max
