@@ -934,6 +934,22 @@ def test_div_by_ruffini_long_axis(ctx, T):
     assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy) and r == O.fr_to_int(er)
 
 
+@pytest.mark.parametrize("x,y", [(8192, 512), (2, 2048), (1 << 17, 2), (1, 1024), (512, 1), (4096, 1024)])
+def test_div_by_ruffini_and_eval_all_paths(ctx, T, x, y):
+    """Every launch path of div_by_ruffini and eval against the C oracle: the prover's largest shape (segmented X chains, the
+    block-scan carries and the block-scan Y chain), a Y axis beyond one block (serial Y chain), an X axis with more than 1024
+    segments (serial carries), degenerate axes, and the widest Y a single block takes."""
+    a = O.random_fr(470 + (x % 97) + y, x * y)
+    p = poly_from(T, ctx, a, x, y)
+    px, py = 0x0F1E2D3C4B5A69788796A5B4C3D2E1F0, (1 << 254) + 0x1234567
+    qx, qy, r = p.div_by_ruffini(px, py)
+    eqx, eqy, er = O.div_by_ruffini(a, x, y, fr1(px), fr1(py))
+    assert np.array_equal(qx.copy_coeffs(), eqx) and np.array_equal(qy.copy_coeffs(), eqy) and r == O.fr_to_int(er)
+    assert p.eval(px, py) == O.fr_to_int(O.eval_xy(a, x, y, fr1(px), fr1(py))) == r
+    assert p.eval(0, py) == O.fr_to_int(O.eval_xy(a, x, y, fr1(0), fr1(py)))
+    assert p.eval(px, 0) == O.fr_to_int(O.eval_xy(a, x, y, fr1(px), fr1(0)))
+
+
 def test_vector_operations_module(ctx, T):
     """libs/src/vector_operations helpers by their reference names (tests.rs:1487-1524,1595-1622)."""
     from tokamak_b200 import vector_operations as V
