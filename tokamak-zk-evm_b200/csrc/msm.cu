@@ -1318,16 +1318,26 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   return TKM_OK;
 }
 
-// Window reduction of a filled bucket set into weighted `parts` and window sums on the context stream, then the
-// recombination kernel (one warp, latency-bound: < 1 ms) on `final_stream`.  When that is a side stream the caller can already queue the next MSM: the
-// serial tail overlaps the next accumulation instead of idling 147 SMs.
+// Window reduction of a filled bucket set into weighted `parts` and window sums, then the recombination kernel (one warp).
+// All of it is latency-bound (a few warps per scheduler, chains of full XYZZ additions: 1.7 ms at c = 16) and runs on
+// `final_stream`.  When that is a side stream the caller can already queue the next MSM on the context stream: the whole
+// reduction overlaps the next decomposition, sort and pair tree instead of leaving most of the device idle.  The scratch
+// buffers are allocated on the context stream and handed to `final_stream` for their stream-ordered release.
 static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *buckets, G1Xyzz *parts, G1Xyzz *wsum, uint32_t *res_dev,
                              cudaStream_t final_stream, cudaEvent_t ready) {
   const size_t nsegs = (size_t)m.W * m.nseg;
-  Scratch<G1Xyzz> seg_acc, seg_run;
+  Scratch<G1Xyzz> seg_acc, seg_run, sliced;
   TKM_TRY(seg_acc.alloc(ctx, nsegs));
   TKM_TRY(seg_run.alloc(ctx, nsegs));
-  k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, ctx->stream>>>(buckets, m, seg_acc.p, seg_run.p);
+  const uint32_t groups_all = m.W * (m.nbits + 1);
+  TKM_TRY(sliced.alloc(ctx, (size_t)groups_all * 64));
+  const cudaStream_t rs = final_stream;
+  if (rs != ctx->stream) {
+    TKM_CUDA(cudaEventRecord(ready, ctx->stream));  // buckets filled, scratch allocated
+    TKM_CUDA(cudaStreamWaitEvent(rs, ready, 0));
+    seg_acc.s = seg_run.s = sliced.s = rs;
+  }
+  k_bucket_seg<<<(unsigned)((nsegs + 127) / 128), 128, 0, rs>>>(buckets, m, seg_acc.p, seg_run.p);
   TKM_TRY(launch_check(ctx, "k_bucket_seg"));
   {
     // Slices per (window, bit).  The blocks are latency-bound tree-sums, so what matters is that the launch is ONE wave:
@@ -1346,24 +1356,18 @@ static int32_t msm_reduce_to(tkm_ctx *ctx, const MsmGeom &m, const G1Xyzz *bucke
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
     if (splits == 1) {
-      k_bucket_bits<<<groups, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, 1, parts);
+      k_bucket_bits<<<groups, BITS_THREADS, 0, rs>>>(seg_acc.p, seg_run.p, m, 1, parts);
       TKM_TRY(launch_check(ctx, "k_bucket_bits"));
     } else {
-      Scratch<G1Xyzz> sliced;
-      TKM_TRY(sliced.alloc(ctx, (size_t)groups * splits));
-      k_bucket_bits<<<groups * splits, BITS_THREADS, 0, ctx->stream>>>(seg_acc.p, seg_run.p, m, splits, sliced.p);
+      k_bucket_bits<<<groups * splits, BITS_THREADS, 0, rs>>>(seg_acc.p, seg_run.p, m, splits, sliced.p);
       TKM_TRY(launch_check(ctx, "k_bucket_bits"));
-      k_sum_groups<<<groups, 32, 0, ctx->stream>>>(sliced.p, splits, m.nbits, m.logg, parts);
+      k_sum_groups<<<groups, 32, 0, rs>>>(sliced.p, splits, m.nbits, m.logg, parts);
       TKM_TRY(launch_check(ctx, "k_sum_groups"));
     }
   }
-  k_window_sums<<<m.W, 32, 0, ctx->stream>>>(parts, m.nbits + 1, wsum);
+  k_window_sums<<<m.W, 32, 0, rs>>>(parts, m.nbits + 1, wsum);
   TKM_TRY(launch_check(ctx, "k_window_sums"));
-  if (final_stream != ctx->stream) {
-    TKM_CUDA(cudaEventRecord(ready, ctx->stream));
-    TKM_CUDA(cudaStreamWaitEvent(final_stream, ready, 0));
-  }
-  k_final<<<1, 32, 0, final_stream>>>(wsum, m, nullptr, res_dev);
+  k_final<<<1, 32, 0, rs>>>(wsum, m, nullptr, res_dev);
   return launch_check(ctx, "k_final");
 }
 
@@ -1432,6 +1436,7 @@ int32_t msm_run_async(tkm_ctx *ctx, const MsmInput &in, int32_t *out_ticket) {
     G1Xyzz *wsum = k.parts + TICKET_PARTS;
     uint32_t *res = reinterpret_cast<uint32_t *>(k.parts + TICKET_PARTS + 64);
     if (st == TKM_OK) st = msm_reduce_to(ctx, m, buckets.p, k.parts, wsum, res, ctx->side_stream, k.ready);
+    if (st == TKM_OK) buckets.s = ctx->side_stream;  // the reduction reads the bucket set there: release it after that
     if (st == TKM_OK) {
       cudaError_t e = cudaMemcpyAsync(k.host, res, 96, cudaMemcpyDeviceToHost, ctx->side_stream);
       if (e == cudaSuccess) e = cudaEventRecord(k.done, ctx->side_stream);
