@@ -87,7 +87,11 @@ struct NttPass {
 
 constexpr uint32_t NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of tile data
 constexpr uint32_t NTT_MAX_LOGL = 10;
-constexpr uint32_t NTT_THREADS = 256;
+constexpr uint32_t NTT_THREADS = 128;
+#ifndef TKM_NTT_MIN_CTAS
+#define TKM_NTT_MIN_CTAS 6
+#endif
+constexpr int NTT_MIN_CTAS = TKM_NTT_MIN_CTAS;
 
 // Shared-memory index of tile element i.  Tiles whose batch lanes walk `outer` (C = 2 columns per 512-point row) are
 // accessed with power-of-two strides in the last butterfly stages and in the bit-reversed store; XOR-ing the folded
@@ -119,7 +123,7 @@ __device__ __forceinline__ Fr ldg_fr(const Fr *p) {
 }
 
 template <bool INVERSE, bool SWZ>
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPass p) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_CTAS) k_ntt_pass(NttPass p) {
   extern __shared__ uint4 smem[];
   const uint32_t L = 1u << p.logL, C = 1u << p.logC, TILE = L * C;
   // the two 128-bit planes sit one 16-byte slot apart modulo the 128-byte bank row (SWZ: lanes alternate between them)
@@ -381,15 +385,22 @@ static int32_t ntt_axis_impl(tkm_ctx *ctx, const Fr *in, Fr *out, size_t outer, 
   p.batch_inner = (inner > 1 || outer == 1) ? 1 : 0;
   if (!p.batch_inner && inner != 1) return fail(TKM_ERR_INTERNAL, "batch-over-outer needs inner == 1");
   const size_t batch_total = p.batch_inner ? inner : outer;
-  // 1024-element tiles (32 KiB + twiddles): three CTAs per SM stay resident (78 registers) and small transforms still
-  // produce enough tiles to fill 148 SMs (4096 x 256: 0.227 ms vs 0.263 ms with 2048-element tiles; equal at 2^23)
-  uint32_t tile_log = 10;
+  // 512-element tiles (16 KiB + twiddles) on CTAs of 128 threads, six resident per SM (80 registers): the finer grain lets the
+  // load/store and barrier phases of one tile hide under the butterflies of five others (16384 x 512 forward: 1.598 ms with
+  // 1024-element tiles on 256-thread CTAs, 1.552 ms with 1024 / 128 threads, 1.538 ms with 512 / 128; 64-thread CTAs: 1.59 ms)
+  uint32_t tile_log = 9;
+  uint32_t tile_log_long = 9;  // tiles of sub-transforms with L >= 512 (one row per tile at 9: the twiddles are not shared)
   if (const char *e = getenv("TKM_NTT_TILE_LOG")) {  // developer knob
     uint32_t v = (uint32_t)atoi(e);
-    if (v >= 8 && v <= NTT_TILE_LOG) tile_log = v;
+    if (v >= 8 && v <= NTT_TILE_LOG) tile_log = tile_log_long = v;
+  }
+  if (const char *e = getenv("TKM_NTT_TILE_LOG_LONG")) {  // developer knob
+    uint32_t v = (uint32_t)atoi(e);
+    if (v >= 8 && v <= NTT_TILE_LOG) tile_log_long = v;
   }
   auto pick_logC = [&](uint32_t logL) {
-    uint32_t lc = tile_log > logL ? tile_log - logL : 0;
+    const uint32_t tl = logL >= 9 ? tile_log_long : tile_log;
+    uint32_t lc = tl > logL ? tl - logL : 0;
     uint32_t lb = log2_exact(batch_total);
     return lc < lb ? lc : lb;
   };
