@@ -41,6 +41,22 @@ def test_fr_vec_ops_edge_and_random(ctx, T):
     assert np.array_equal(got, exp)
 
 
+def test_fr_mul_zero_columns_of_the_reduction(ctx, T):
+    """The Fr reduction feeds the carry of column 0 (E[0] + m = 2^32 [E[0] != 0]) through the flag into the first fused
+    multiply-add of every row (ff.cuh reduce_row): operands whose MONTGOMERY forms are k * 2^(32 j) make whole runs of rows
+    see E[0] = 0 (no carry) next to rows with E[0] = 0xffffffff.. patterns.  All pairs against Python integers."""
+    rinv = pow(1 << 256, -1, P.R_MOD)
+    ks = [1, 2, 0xFFFFFFFF, 0x80000000, 0xFFFFFFFE, 0x73EDA753, (1 << 64) - 1, (1 << 96) + 1]
+    vals = [k * (1 << (32 * j)) * rinv % P.R_MOD for j in range(8) for k in ks]  # Montgomery form = k * 2^(32 j) mod r
+    vals += [0, 1, P.R_MOD - 1, rinv, (P.R_MOD - 1) * rinv % P.R_MOD]
+    a = frs([x for x in vals for _ in vals])
+    b = frs([y for _ in vals for y in vals])
+    got = ctx.vec_op_host(T.OP_MUL, a, b)
+    exp = frs([x * y % P.R_MOD for x in vals for y in vals])
+    assert np.array_equal(got, exp)
+    assert np.array_equal(got, O.fr_vec_op("mul", a, b))
+
+
 def test_fr_vec_inv_batched(ctx):
     a = np.concatenate([frs([0, 1, P.R_MOD - 1, 0, 0, 7]), O.random_fr(13, 1001)])
     d = ctx.upload_fr(a)
@@ -714,6 +730,55 @@ def test_commit_begin_end_tickets(ctx, T):
     for t in held:
         sigma.encode_poly_end(t)
     sigma.close()
+
+
+def test_msm_begin_end_and_device_gather(ctx, T):
+    """tkm_msm_g1_begin / tkm_msm_g1_indexed_begin (resolved by tkm_commit_end, buffers released right after begin) against the
+    synchronous entry points and the oracle, queued out of order with empty inputs in between; tkm_fr_gather against numpy
+    indexing, out-of-range indices rejected."""
+    import ctypes
+
+    G = g1s([P.G1_GEN])[0]
+    n_tab = 3000
+    pts = O.g1_fixed_base_mul_batch(G, O.random_fr(801, n_tab))
+    d_tab = ctx.upload_bases(pts)
+    lib, vp = ctx.lib, ctypes.c_void_p
+    jobs = []
+    for k, n in enumerate((1, 17, 2048, 2999)):
+        ss = O.random_fr(810 + k, n)
+        idx = np.random.default_rng(820 + k).integers(0, n_tab, size=n).astype(np.uint32)
+        d_s, d_i = ctx.upload_fr(ss, to_mont=False), ctx.dev_alloc(n * 4)
+        ctx.h2d(d_i, idx)
+        t1, t2 = ctypes.c_int32(), ctypes.c_int32()
+        T.check(lib.tkm_msm_g1_indexed_begin(ctx.h, vp(d_s), 0, vp(d_tab), vp(d_i), n, ctypes.byref(t1)))
+        T.check(lib.tkm_msm_g1_begin(ctx.h, vp(d_s), 0, vp(d_tab), n, ctypes.byref(t2)))
+        ctx.dev_free(d_s)
+        ctx.dev_free(d_i)
+        jobs.append((t1.value, O.msm_g1(ss, pts[idx]), t2.value, O.msm_g1(ss, pts[:n])))
+    te = ctypes.c_int32()
+    T.check(lib.tkm_msm_g1_begin(ctx.h, None, 0, None, 0, ctypes.byref(te)))  # empty MSM: the identity
+    out = np.zeros(12, dtype=np.uint64)
+    for t1, e1, t2, e2 in reversed(jobs):
+        T.check(lib.tkm_commit_end(ctx.h, t2, out.ctypes.data_as(vp)))
+        assert np.array_equal(out, e2)
+        T.check(lib.tkm_commit_end(ctx.h, t1, out.ctypes.data_as(vp)))
+        assert np.array_equal(out, e1)
+    T.check(lib.tkm_commit_end(ctx.h, te.value, out.ctypes.data_as(vp)))
+    assert not out.any()
+    # device gather
+    tab = O.random_fr(830, 1000)
+    sel = np.random.default_rng(831).integers(0, 1000, size=5000).astype(np.uint32)
+    d_t, d_sel, d_o = ctx.upload_fr(tab, to_mont=False), ctx.dev_alloc(5000 * 4), ctx.dev_alloc(5000 * 32)
+    ctx.h2d(d_sel, sel)
+    T.check(lib.tkm_fr_gather(ctx.h, vp(d_t), 1000, vp(d_sel), 5000, vp(d_o)))
+    got = np.empty((5000, 4), dtype=np.uint64)
+    ctx.d2h(got, d_o)
+    assert np.array_equal(got, tab[sel])
+    sel[77] = 1000
+    ctx.h2d(d_sel, sel)
+    assert lib.tkm_fr_gather(ctx.h, vp(d_t), 1000, vp(d_sel), 5000, vp(d_o)) != 0
+    for p_ in (d_t, d_sel, d_o, d_tab):
+        ctx.dev_free(p_)
 
 
 def test_poly_expr_fused_matches_coefficients(ctx, T):
