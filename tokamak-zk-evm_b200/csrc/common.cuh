@@ -72,7 +72,7 @@ struct tkm_ctx {
   Ticket tickets[TKM_MAX_TICKETS];
   // copy engine side of the pipelined host-buffer MSM (created on first use)
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copy_ev[17] = {};
+  cudaEvent_t copy_ev[34] = {};  // [2k] scalars of piece k arrived, [2k+1] its bases; [32] staging buffers allocated
   // per-device launch state (function attributes and occupancy are properties of the device the context lives on, so they
   // are cached here and not in process-wide statics: a second context on another GPU must get its own shared-memory opt-in)
   bool ntt_attr_set[4] = {false, false, false, false};
@@ -187,6 +187,11 @@ struct MsmInput {
   uint32_t pre_c = 0;       // fixed-base tables: window bits the tables were built for (0 = plain bases)
   uint32_t pre_stride = 0;  // fixed-base tables: points per table (table w starts at bases + w*pre_stride)
   const uint4 *xpad = nullptr;  // optional: 64-byte x slots over the same index space as bases (see tkm_crs::xpad)
+  // Host pipeline: the bases may still be in flight when the pass starts.  Digit decomposition, sort and the tree's offset
+  // tables need only the scalars; the pass waits for this event right before the first kernel that reads a base, then (when
+  // bases_canonical) converts them to Montgomery form in place.
+  cudaEvent_t bases_ready = nullptr;
+  bool bases_canonical = false;
 };
 int32_t msm_build_xpad(tkm_ctx *ctx, const G1Affine *bases, size_t row_stride, size_t rows, size_t cols, uint32_t tables, size_t table_stride, uint4 *xpad);
 int32_t crs_precompute(tkm_ctx *ctx, const G1Affine *base, size_t n, uint32_t c, G1Affine **out_table, uint32_t *out_W);

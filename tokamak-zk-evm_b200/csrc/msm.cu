@@ -1067,6 +1067,11 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
   const size_t n = in.rows * in.cols;
   const size_t M = n * m.Wd;
   const uint32_t invalid = m.nbuckets;
+  auto await_bases = [&]() -> int32_t {  // see MsmInput::bases_ready
+    if (in.bases_ready) TKM_CUDA(cudaStreamWaitEvent(ctx->stream, in.bases_ready, 0));
+    if (in.bases_canonical) TKM_TRY(g1_to_mont_dev(ctx, in.bases, const_cast<G1Affine *>(in.bases), n));
+    return TKM_OK;
+  };
   // the list leaves k_decompose sorted by the low logWp key bits (window-major); the stable sort covers the rest: digit + trash flag
   const int sort_lo = (int)m.logWp, sort_hi = (int)(m.logWp + m.logB + 1);
 
@@ -1170,16 +1175,17 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
     TKM_TRY(t_invtot.alloc(ctx, T1 * parts));
     TKM_TRY(t_tot2.alloc(ctx, n2 * parts));
     TKM_TRY(t_tot3.alloc(ctx, n3 * parts));
+    auto off = [&](uint32_t l) { return t_off.p + (size_t)l * (nb + 1); };
+    k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, parts == 2 ? nb / 2 : nb, t_keys[0][0].p,
+                                                                           t_keys[parts - 1][0].p, t_src[0][0].p, t_src[parts - 1][0].p);
+    TKM_TRY(launch_check(ctx, "k_tree_keys1"));
+    TKM_TRY(await_bases());  // everything above needed only the scalars
     if (!xpad && !in.idx && !in.pre_c) {  // plain bases (dense or a strided rectangle): a per-call x table pays for itself over the windows
       const size_t span = (in.rows - 1) * in.base_row_stride + in.cols;
       TKM_TRY(t_xpad.alloc(ctx, span * 4));
       TKM_TRY(msm_build_xpad(ctx, in.bases, in.base_row_stride, in.rows, in.cols, 1, 0, t_xpad.p));
       xpad = t_xpad.p;
     }
-    auto off = [&](uint32_t l) { return t_off.p + (size_t)l * (nb + 1); };
-    k_tree_keys1<<<grid_for(M, 256, ctx->sm_count), 256, 0, ctx->stream>>>(keys_s.p, off(0), off(1), nb, parts == 2 ? nb / 2 : nb, t_keys[0][0].p,
-                                                                           t_keys[parts - 1][0].p, t_src[0][0].p, t_src[parts - 1][0].p);
-    TKM_TRY(launch_check(ctx, "k_tree_keys1"));
     if (parts == 2) {
       if (!ctx->tree_stream) {
         TKM_CUDA(cudaStreamCreateWithFlags(&ctx->tree_stream, cudaStreamNonBlocking));
@@ -1262,6 +1268,7 @@ static int32_t msm_accumulate_pass(tkm_ctx *ctx, const MsmInput &in, const MsmGe
       TKM_CUDA(cudaMemcpyAsync(ctx->tree_counts + l, off(l) + nb, 4, cudaMemcpyDeviceToHost, ctx->stream));
   } else {
     ctx->tree_levels = 0;
+    TKM_TRY(await_bases());
   }
   const int fin = (L & 1) ? 0 : 1;  // side holding level L (L >= 1)
   const size_t Macc = L ? bound(L) : M;
@@ -1498,12 +1505,13 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   if (pieces > n) pieces = (uint32_t)n;
   if (!ctx->copy_stream) {
     TKM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 17; i++) TKM_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 34; i++) TKM_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
   }
   // Piece boundaries.  The copy engine outruns the accumulation (~2.4 ms vs ~7 ms per 2^20 points), so only the first
   // piece's copy is exposed: cut the range in growing pieces (weights 1, 3, 4, 4, ..) -- a small first piece starts the
   // compute early, few large later pieces keep the per-piece overhead (sort, chunk tails, bucket merge) low.
   size_t bound[17];
+  static const uint32_t first_permille = getenv("TKM_MSM_HOST_FIRST") ? (uint32_t)atoi(getenv("TKM_MSM_HOST_FIRST")) : 0;  // developer knob: size of the first piece
   {
     uint32_t wsum = 0, acc = 0;
     for (uint32_t k = 0; k < pieces; k++) wsum += k == 0 ? 1 : (k == 1 ? 3 : 4);
@@ -1511,6 +1519,7 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
     for (uint32_t k = 0; k < pieces; k++) {
       acc += k == 0 ? 1 : (k == 1 ? 3 : 4);
       bound[k + 1] = k + 1 == pieces ? n : (size_t)((unsigned __int128)n * acc / wsum);
+      if (k == 0 && first_permille) bound[1] = (size_t)((unsigned __int128)n * first_permille / 1000);
       if (bound[k + 1] <= bound[k]) bound[k + 1] = bound[k] + 1;  // n >= pieces keeps every piece non-empty
       if (bound[k + 1] > n) bound[k + 1] = n;
     }
@@ -1524,14 +1533,16 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   const size_t set_stride = (size_t)m.nbuckets + 1;
   TKM_TRY(buckets.alloc(ctx, set_stride * pieces));
   // the staging buffers come from the compute stream's pool: the copy stream may touch them only after this point
-  TKM_CUDA(cudaEventRecord(ctx->copy_ev[16], ctx->stream));
-  TKM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[16], 0));
+  TKM_CUDA(cudaEventRecord(ctx->copy_ev[32], ctx->stream));
+  TKM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[32], 0));
   int32_t st = TKM_OK;
   for (uint32_t k = 0; k < pieces && st == TKM_OK; k++) {
     const size_t off = bound[k], cnt = bound[k + 1] - bound[k];
+    // scalars first: the piece's digit decomposition, sort and tree offsets start while its bases are still in flight
     cudaError_t e = cudaMemcpyAsync(ds.p + off, scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[2 * k], ctx->copy_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(db.p + off, bases + off * 96, cnt * 96, cudaMemcpyHostToDevice, ctx->copy_stream);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[2 * k + 1], ctx->copy_stream);
     if (e != cudaSuccess) st = fail(TKM_ERR_CUDA, "host-to-device copy of MSM piece %u failed: %s", k, cudaGetErrorString(e));
   }
   if (st == TKM_OK) {
@@ -1540,13 +1551,11 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   }
   for (uint32_t k = 0; k < pieces && st == TKM_OK; k++) {
     const size_t off = bound[k], cnt = bound[k + 1] - bound[k];
-    cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0);
+    cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 * k], 0);
     if (e != cudaSuccess) {
       st = fail(TKM_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
       break;
     }
-    st = g1_to_mont_dev(ctx, db.p + off, db.p + off, cnt);
-    if (st != TKM_OK) break;
     MsmInput in;
     in.scalars = ds.p + off;
     in.scalars_mont = false;
@@ -1556,6 +1565,8 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
     in.rows = 1;
     in.cols = cnt;
     in.idx = nullptr;
+    in.bases_ready = ctx->copy_ev[2 * k + 1];  // waited for inside the pass, right before the first kernel that reads a base
+    in.bases_canonical = true;                 // ... and converted to Montgomery form there
     st = msm_accumulate_pass(ctx, in, m, buckets.p + k * set_stride);
   }
   if (st == TKM_OK && pieces > 1) {
