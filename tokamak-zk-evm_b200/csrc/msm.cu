@@ -3,16 +3,20 @@
 // Replaces msm::msm(scalars, bases, MSMConfig::default(), out[1]) as the reference calls it for every
 // commitment (libs/src/iotools/mod.rs:2093-2099; libs/src/group_structures/mod.rs:108-114,135-141).
 //
-// Pipeline (all on the context stream, no host synchronisation until the 96-byte result is read):
+// Pipeline (no host synchronisation until the 96-byte result is read):
 //   1. k_decompose     one thread per scalar: (optional from-Montgomery,) GLV split k = k1 + k2*lambda into
 //                      two signed 127-bit halves (glv.cuh), signed c-bit digits of each half;
 //                      emits (bucket key, base index | sign) pairs, window-major, zero digits keyed
-//                      to a trash bucket that sorts last.
-//   2. cub radix sort  of the pairs by bucket key (only the significant key bits).
-//   3. k_accumulate    one thread per fixed-length chunk of the sorted list, so work is balanced for
-//                      ANY scalar distribution: XYZZ mixed additions of gathered affine bases; runs
-//                      that lie strictly inside a chunk are final and go straight to their bucket,
-//                      the first/last run of every chunk go to a (key, point) partial list.
+//                      to a trash bucket that sorts last.  Bucket (window w, digit d) has key (d << log2 W) | w.
+//   2. radix sort      stable, over the digit bits of the key only: the window bits are already in order in the
+//                      window-major list (two 8-bit cub onesweep passes at c = 16).
+//   3a. pair tree      (>= 2^24 digit entries) levels of run-aligned pairwise AFFINE additions with batched inversion:
+//                      k_run_bounds / k_scan_* (all levels' offsets), then per level k_tree_fwd (denominators, prefix
+//                      products), k_tree_l2_up / k_tree_l3 / k_tree_l2_down (one inversion per level) and
+//                      k_tree_apply; the two halves of the bucket range run on two streams.
+//   3b. k_accumulate   one thread per fixed-length chunk of the (remaining) sorted list, so work is balanced for
+//                      ANY scalar distribution: XYZZ mixed additions; runs that lie strictly inside a chunk are final
+//                      and go straight to their bucket, the first/last run of every chunk go to a (key, point) partial list.
 //   4. k_segreduce     warp-cooperative segmented reduction of the partial list (shuffle tree of
 //                      full XYZZ additions, 32 entries per warp), repeated until one warp remains.
 //   5. k_bucket_seg /  parallel window reduction: running sums over 16-bucket segments, then per
@@ -20,7 +24,9 @@
 //      k_window_sums   part weighted by its 2^k where it is produced, window sums as shuffle tree-sums,
 //   6. k_final         Horner over the windows of each half as two concurrent chains, sum = chain1 + phi(chain2),
 //                      one inversion (binary extended Euclid) to affine.
-// Integer-pipe bound: N*W mixed additions of ~10 Fq products each; no tensor cores.
+//   Queued MSMs (tickets) run 5-6 on a side stream under the next MSM's 1-3.
+// Integer-pipe bound: N*W bucket additions of 5 products + 1 squaring (affine, tree) or ~10 products (XYZZ) in Fq
+// (SURVEY.md 8d); no tensor cores.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdlib>
