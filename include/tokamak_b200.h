@@ -342,7 +342,8 @@ int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out);
 /* Micro-benchmarks: integer pipe peak (dependent-free IMAD / IMAD.WIDE streams) and field-mul rate.
  * kind: 0 = IMAD.U32, 1 = IMAD.WIDE.U32 (64-bit addend), 2 = Fr mul, 3 = Fq mul, 4 = XYZZ mixed add,
  * 5 = IMAD.WIDE.U32.X carry chains (the form the field multiplier issues), 6 = Fr NTT butterfly (product + add + sub),
- * 7 = the same butterfly on the round-1 reduction (add-with-carry chains; kept for comparison).
+ * 7 = the same butterfly on the round-1 reduction (add-with-carry chains; kept for comparison),
+ * 8 / 9 / 10 = ONE thread's chain of Fq inversions (binary Euclid / binary GCD on approximations / Fermat): 1 / latency.
  * out = ops/s. */
 int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s);
 

@@ -10,19 +10,19 @@ template <class F> static void st(uint32_t *p, const F &a) { F r = a.from_mont()
 static G1Affine lda(const uint32_t *p) { G1Affine a; a.x = ld<Fq>(p); a.y = ld<Fq>(p + 12); if (a.x.is_zero() && a.y.is_zero()) return G1Affine::identity(); return a; }
 static void sta(uint32_t *p, const G1Affine &a) { st(p, a.x); st(p + 12, a.y); }
 extern "C" {
-// op: 0 add 1 sub 2 mul 3 inv(a) 4 raw mont mul (no conversion) 5 sqr(a) 6 raw mont sqr 7 inv_bgcd(a)
+// op: 0 add 1 sub 2 mul 3 inv(a) 4 raw mont mul (no conversion) 5 sqr(a) 6 raw mont sqr 7 inv_bgcd(a) 8 inv_fast(a) 9 (Fq) inv_pornin(a) alone, 0 when its own check fails
 void h_fr_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *o) {
   if (op == 4) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr z = x * y; memcpy(o, z.v, 32); return; }
   if (op == 6) { Fr x; memcpy(x.v, a, 32); Fr z = x.sqr(); memcpy(o, z.v, 32); return; }
   Fr x = ld<Fr>(a), y = ld<Fr>(b);
-  Fr z = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : op == 5 ? x.sqr() : op == 7 ? x.inv_bgcd() : x.inv();
+  Fr z = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : op == 5 ? x.sqr() : op == 7 ? x.inv_bgcd() : op == 8 ? x.inv_fast() : x.inv();
   st(o, z);
 }
 void h_fq_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *o) {
   if (op == 4) { Fq x, y; memcpy(x.v, a, 48); memcpy(y.v, b, 48); Fq z = x * y; memcpy(o, z.v, 48); return; }
   if (op == 6) { Fq x; memcpy(x.v, a, 48); Fq z = x.sqr(); memcpy(o, z.v, 48); return; }
   Fq x = ld<Fq>(a), y = ld<Fq>(b);
-  Fq z = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : op == 5 ? x.sqr() : op == 7 ? x.inv_bgcd() : x.inv();
+  Fq z = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : op == 5 ? x.sqr() : op == 7 ? x.inv_bgcd() : op == 8 ? x.inv_fast() : op == 9 ? [&] { bool ok; Fq r = x.inv_pornin(&ok); return ok ? r : Fq::zero(); }() : x.inv();
   st(o, z);
 }
 // acc = sum of n affine points via madd into an XYZZ accumulator (exercises all branches)

@@ -181,6 +181,31 @@ def test_binary_gcd_inverse(L, name):
         assert toint(o) == (pow(a, mod - 2, mod) if a else 0), (name, hex(a))
 
 
+@pytest.mark.parametrize("name", ["fr", "fq"])
+def test_binary_gcd_on_approximations_inverse(L, name):
+    """Fp::inv_fast (Pornin's binary GCD on 64-bit approximations, checked, with the inv_bgcd fallback) equals the Fermat
+    inverse on edge values, powers of two, values around limb boundaries and random elements; for Fq also inv_pornin ALONE
+    (op 9 returns 0 when its own (a, b) = (0, 1) check fails), so the fast path itself is what is tested, not the fallback."""
+    mod, n, fn = (P.R_MOD, 8, L.h_fr_op) if name == "fr" else (P.Q_MOD, 12, L.h_fq_op)
+    rng = random.Random(22)
+    R = 1 << (32 * n)
+    vals = [0, 1, 2, 3, 4, mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1, R % mod, pow(R, -1, mod), (1 << 32) - 1, 1 << 32, 1 << (32 * n - 2)]
+    vals += [rng.randrange(mod) for _ in range(3000)] + [1 << k for k in range(0, 32 * n - 1, 7)]
+    vals += [((1 << k) - 1) % mod for k in range(1, 32 * n, 11)] + [(mod - (1 << k)) % mod for k in range(0, 32 * n - 2, 13)]
+    vals += [rng.randrange(1 << k) for k in (8, 31, 32, 33, 63, 64, 65, 96, 127, 200) for _ in range(30)]
+    rinv = pow(R, -1, mod)
+    vals += [x * rinv % mod for x in (1, 2, 3, (1 << 31), (1 << 32) - 1, (1 << 33) + 1, (1 << 64) - 1, 1 << 95)]  # tiny Montgomery forms: long runs of zero limbs
+    for a in vals:
+        a %= mod
+        exp = pow(a, mod - 2, mod) if a else 0
+        o = np.zeros(n, dtype=np.uint32)
+        fn(8, pp(u32(a, n)), pp(u32(a, n)), pp(o))
+        assert toint(o) == exp, (name, hex(a))
+        if name == "fq" and a:
+            fn(9, pp(u32(a, n)), pp(u32(a, n)), pp(o))
+            assert toint(o) == exp, ("inv_pornin alone", hex(a))
+
+
 def test_fq_dot2(L):
     """Fq::dot2 = a*b + c*d under one interleaved Montgomery reduction (the Y3 of the point formulas), raw limbs."""
     q, n = P.Q_MOD, 12

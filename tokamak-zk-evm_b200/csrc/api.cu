@@ -175,6 +175,15 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t *sink, int iters) {
       y = d;
     }
     if (x.v[0] == 0x12345678u && y.v[1] == 1) sink[0] = x.v[1];
+  } else if (KIND == 8 || KIND == 9 || KIND == 10) {  // latency of ONE thread's Fq inversion chain (what a pair-tree level waits for)
+    if (t != 0) return;
+    Fq x = Fq::r2();
+    x.v[0] ^= (uint32_t)iters;
+    for (int it = 0; it < iters; it++) {
+      Fq y = KIND == 8 ? x.inv_bgcd() : KIND == 9 ? x.inv_fast() : x.inv();
+      x = y + Fq::one();
+    }
+    if (x.v[0] == 0x12345678u) sink[0] = x.v[1];
   } else if (KIND == 2) {
     Fr x = Fr::one(), y = Fr::r2();
     x.v[0] ^= t;
@@ -989,6 +998,9 @@ int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
       case 5: iters = 4096; ops_per_iter = 16; k_microbench<5><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 6: iters = 512; ops_per_iter = 1; k_microbench<6><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
       case 7: iters = 512; ops_per_iter = 1; k_microbench<7><<<blocks, threads, 0, ctx->stream>>>(sink.p, iters); break;
+      case 8: iters = 64; ops_per_iter = 1; k_microbench<8><<<1, 32, 0, ctx->stream>>>(sink.p, iters); break;
+      case 9: iters = 64; ops_per_iter = 1; k_microbench<9><<<1, 32, 0, ctx->stream>>>(sink.p, iters); break;
+      case 10: iters = 16; ops_per_iter = 1; k_microbench<10><<<1, 32, 0, ctx->stream>>>(sink.p, iters); break;
       default: return fail(TKM_ERR_INVALID_ARGUMENT, "unknown microbench kind %d", kind);
     }
     TKM_TRY(launch_check(ctx, "k_microbench"));
@@ -997,7 +1009,7 @@ int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
   }
   float ms = 0;
   TKM_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  *out_ops_per_s = (double)blocks * threads * iters * ops_per_iter / (ms * 1e-3);
+  *out_ops_per_s = (kind >= 8 ? 1.0 : (double)blocks * threads) * iters * ops_per_iter / (ms * 1e-3);
   return TKM_OK;
 }
 

@@ -109,7 +109,7 @@ __device__ __forceinline__ G1Xyzz g1_dbl_coop4(const G1Xyzz &p) {
 // chain of ~570 dependent Montgomery products.  The replicas run the same data-dependent loops: no divergence.
 __device__ __forceinline__ G1Affine g1_to_affine_coop(const G1Xyzz &p) {
   if (p.is_identity()) return G1Affine::identity();
-  Fq t = (p.ZZ * p.ZZZ).inv_bgcd();
+  Fq t = (p.ZZ * p.ZZZ).inv_fast();
   Fq zz_inv = t * p.ZZZ;
   Fq zzz_inv = t * p.ZZ;
   return G1Affine{p.X * zz_inv, p.Y * zzz_inv};
@@ -189,7 +189,7 @@ TKM_HD G1Affine g1_to_affine(const G1Xyzz &p) {
 // counts depend on the value).
 TKM_HD G1Affine g1_to_affine_single(const G1Xyzz &p) {
   if (p.is_identity()) return G1Affine::identity();
-  Fq t = (p.ZZ * p.ZZZ).inv_bgcd();
+  Fq t = (p.ZZ * p.ZZZ).inv_fast();
   Fq zz_inv = t * p.ZZZ;
   Fq zzz_inv = t * p.ZZ;
   return G1Affine{p.X * zz_inv, p.Y * zzz_inv};

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(TREE3_LEAVES) k_tree_l3(Fq *__restrict__ blk, 
   const int tid = threadIdx.x;
   tree[TREE3_LEAVES + tid] = (uint32_t)tid < nblk ? blk[tid] : Fq::one();
   tree_up<TREE3_LEAVES>(tree, tid);
-  if (tid == 0) tree[1] = tree[1].inv_bgcd();
+  if (tid == 0) tree[1] = tree[1].inv_fast();
   tree_down<TREE3_LEAVES>(tree, tid);
   if ((uint32_t)tid < nblk) st_fq(blk + tid, tree[TREE3_LEAVES + tid]);
 }
