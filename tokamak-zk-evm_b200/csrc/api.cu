@@ -600,10 +600,9 @@ int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bas
     return TKM_OK;
   }
   TKM_REQUIRE(scalars && bases, "null argument");
-  // Large inputs: overlap the host->device copies with the bucket accumulation, one point range at a time.
-  // Two pieces (a quarter of the points, then the rest) from 2^19 points up: the second piece's decomposition and sort run
-  // while its bases are still arriving, and two accumulation passes cost less than three (2^22: 25.7 ms against 26.3)
-  uint32_t pieces = n >= ((size_t)1 << 19) ? 2 : 1;
+  // Large inputs: overlap the host->device copies with the bucket accumulation, one point range at a time; the piece layout
+  // (msm_host_pipelined) follows the share of the previous call its copies took.
+  uint32_t pieces = 0;
   if (const char *e = getenv("TKM_MSM_HOST_PIECES")) pieces = (uint32_t)atoi(e);  // developer knob
   return msm_host_pipelined(ctx, scalars, bases, n, pieces, out96);
 }

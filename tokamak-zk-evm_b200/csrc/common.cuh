@@ -72,6 +72,10 @@ struct tkm_ctx {
   Ticket tickets[TKM_MAX_TICKETS];
   // copy engine side of the pipelined host-buffer MSM (created on first use)
   cudaStream_t copy_stream = nullptr;
+  // share of the previous host-buffer MSM's duration its host-to-device copies took (0 = not measured yet): picks the piece layout
+  float h2d_share = 0.f;
+  bool h2d_copy_bound = false;  // with hysteresis: set above 0.55, cleared below 0.40
+  cudaEvent_t copy_t[4] = {};  // timing events: copies begin / end, call begin / end
   cudaEvent_t copy_ev[34] = {};  // [2k] scalars of piece k arrived, [2k+1] its bases; [32] staging buffers allocated
   // per-device launch state (function attributes and occupancy are properties of the device the context lives on, so they
   // are cached here and not in process-wide statics: a second context on another GPU must get its own shared-memory opt-in)

@@ -1506,26 +1506,47 @@ int32_t msm_run(tkm_ctx *ctx, const MsmInput &in, uint8_t out96[96]) {
 // are summed bucket-wise and reduced once at the end.
 int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t pieces, uint8_t out96[96]) {
   if (n > 0x7fffffffull / 32) return fail(TKM_ERR_INVALID_ARGUMENT, "MSM size %zu too large", n);
-  if (pieces < 1) pieces = 1;
-  if (pieces > 16) pieces = 16;
+  if (pieces > 16) pieces = 16;  // 0 = automatic layout
   if (pieces > n) pieces = (uint32_t)n;
+  if (n < 4) pieces = 1;
   if (!ctx->copy_stream) {
     TKM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 34; i++) TKM_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 4; i++) TKM_CUDA(cudaEventCreate(&ctx->copy_t[i]));
   }
-  // Piece boundaries.  The copy engine outruns the accumulation (~2.4 ms vs ~7 ms per 2^20 points), so only the first
-  // piece's copy is exposed: cut the range in growing pieces (weights 1, 3, 4, 4, ..) -- a small first piece starts the
-  // compute early, few large later pieces keep the per-piece overhead (sort, chunk tails, bucket merge) low.
+  // Piece boundaries.  On a box of its own the copy engine outruns the accumulation (512 MiB in 9 ms against 21 ms at 2^22), so
+  // only the first piece's copy is exposed and every further piece costs a less efficient accumulation pass: two pieces, a
+  // quarter of the points first.  When the copies take most of the call (eight ranks sharing the host's memory and PCIe roots:
+  // 23 ms), what is exposed is the work left after the LAST bases have arrived: four pieces ending in a small one
+  // (2 : 3 : 2 : 1).  The layout follows the copy share measured in the previous call on this context.
   size_t bound[17];
   static const uint32_t first_permille = getenv("TKM_MSM_HOST_FIRST") ? (uint32_t)atoi(getenv("TKM_MSM_HOST_FIRST")) : 0;  // developer knob: size of the first piece
+  uint32_t weight[16];
+  if (pieces == 0) {  // automatic
+    if (ctx->h2d_share > 0.55f) ctx->h2d_copy_bound = true;
+    else if (ctx->h2d_share > 0.f && ctx->h2d_share < 0.40f) ctx->h2d_copy_bound = false;
+    const bool copy_bound = ctx->h2d_copy_bound;
+    if (n < ((size_t)1 << 19)) {
+      pieces = 1;
+      weight[0] = 1;
+    } else if (copy_bound && n >= ((size_t)1 << 21)) {
+      pieces = 4;
+      weight[0] = 2; weight[1] = 3; weight[2] = 2; weight[3] = 1;
+    } else {
+      pieces = 2;
+      weight[0] = 1; weight[1] = 3;
+    }
+  } else {
+    for (uint32_t k = 0; k < pieces; k++) weight[k] = k == 0 ? 1 : (k == 1 ? 3 : 4);
+  }
   {
     uint32_t wsum = 0, acc = 0;
-    for (uint32_t k = 0; k < pieces; k++) wsum += k == 0 ? 1 : (k == 1 ? 3 : 4);
+    for (uint32_t k = 0; k < pieces; k++) wsum += weight[k];
     bound[0] = 0;
     for (uint32_t k = 0; k < pieces; k++) {
-      acc += k == 0 ? 1 : (k == 1 ? 3 : 4);
+      acc += weight[k];
       bound[k + 1] = k + 1 == pieces ? n : (size_t)((unsigned __int128)n * acc / wsum);
-      if (k == 0 && first_permille) bound[1] = (size_t)((unsigned __int128)n * first_permille / 1000);
+      if (k == 0 && first_permille && pieces > 1) bound[1] = (size_t)((unsigned __int128)n * first_permille / 1000);
       if (bound[k + 1] <= bound[k]) bound[k + 1] = bound[k] + 1;  // n >= pieces keeps every piece non-empty
       if (bound[k + 1] > n) bound[k + 1] = n;
     }
@@ -1541,6 +1562,8 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   // the staging buffers come from the compute stream's pool: the copy stream may touch them only after this point
   TKM_CUDA(cudaEventRecord(ctx->copy_ev[32], ctx->stream));
   TKM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[32], 0));
+  TKM_CUDA(cudaEventRecord(ctx->copy_t[2], ctx->stream));
+  TKM_CUDA(cudaEventRecord(ctx->copy_t[0], ctx->copy_stream));
   int32_t st = TKM_OK;
   for (uint32_t k = 0; k < pieces && st == TKM_OK; k++) {
     const size_t off = bound[k], cnt = bound[k + 1] - bound[k];
@@ -1551,6 +1574,7 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
     if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[2 * k + 1], ctx->copy_stream);
     if (e != cudaSuccess) st = fail(TKM_ERR_CUDA, "host-to-device copy of MSM piece %u failed: %s", k, cudaGetErrorString(e));
   }
+  if (st == TKM_OK && cudaEventRecord(ctx->copy_t[1], ctx->copy_stream) != cudaSuccess) st = fail(TKM_ERR_CUDA, "cudaEventRecord failed");
   if (st == TKM_OK) {
     k_fill_identity<<<grid_for(set_stride * pieces, 256, ctx->sm_count), 256, 0, ctx->stream>>>(buckets.p, set_stride * pieces);
     st = launch_check(ctx, "k_fill_identity");
@@ -1584,7 +1608,14 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
     cudaStreamSynchronize(ctx->copy_stream);
     return st;
   }
-  return msm_reduce(ctx, m, buckets.p, out96);
+  st = msm_reduce(ctx, m, buckets.p, out96);  // synchronises the compute stream
+  if (st == TKM_OK && cudaEventRecord(ctx->copy_t[3], ctx->stream) == cudaSuccess && cudaEventSynchronize(ctx->copy_t[3]) == cudaSuccess) {
+    float t_copy = 0.f, t_call = 0.f;
+    if (cudaEventElapsedTime(&t_copy, ctx->copy_t[0], ctx->copy_t[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&t_call, ctx->copy_t[2], ctx->copy_t[3]) == cudaSuccess && t_call > 0.f)
+      ctx->h2d_share = t_copy / t_call;
+  }
+  return st;
 }
 
 }  // namespace tkm
