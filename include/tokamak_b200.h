@@ -127,7 +127,10 @@ int32_t tkm_ntt_batch(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t n,
 
 /* ---- G1 MSM: msm::msm with MSMConfig::default() (libs/src/iotools/mod.rs:2093-2099;
  *      group_structures/mod.rs:108-114,135-141) ---------------------------------------------------- */
-/* Host scalars (n x 32 B canonical), host affine bases (n x 96 B canonical) -> one affine point (96 B). */
+/* Host scalars (n x 32 B canonical), host affine bases (n x 96 B canonical) -> one affine point (96 B).
+ * From 2^19 points up the host-to-device copies are pipelined with the accumulation (pinned buffers make them asynchronous):
+ * the point range is cut into pieces, scalars travel before bases, and a piece's digit decomposition and sort run while its
+ * bases are still in flight; the piece layout follows the share of the previous call its copies took. */
 int32_t tkm_msm_g1_host(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *bases, size_t n, uint8_t out96[96]);
 /* Device-resident: scalars n x 8 u32 (Montgomery if scalars_mont != 0, else canonical),
  * bases = device table in Montgomery form (from tkm_g1_bases_to_mont or a tkm_crs). */
