@@ -333,8 +333,12 @@ def test_msm_host_pipelined_pieces(ctx, n, pieces, monkeypatch):
     assert np.array_equal(ctx.msm_g1_host(ss, pts), exp)
 
 
-def test_msm_host_pipelined_large(ctx):
-    """2^21 points through the default 4-piece pipeline; answer from known discrete logs (O(N) field work)."""
+@pytest.mark.parametrize("copy_bound", ["0", "1"])
+def test_msm_host_pipelined_large(ctx, copy_bound, monkeypatch):
+    """2^21 points through both automatic layouts of the host pipeline -- two pieces (a quarter, then the rest) when the call
+    is compute-bound, four ending in a small one (2 : 3 : 2 : 1) when its copies dominate; scalars travel before bases and each
+    pass waits for its bases inside.  Answer from known discrete logs (O(N) field work)."""
+    monkeypatch.setenv("TKM_MSM_HOST_COPY_BOUND", copy_bound)
     n = 1 << 21
     G = g1s([P.G1_GEN])[0]
     ks = O.random_fr(170, n)

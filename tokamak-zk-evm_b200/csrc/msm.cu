@@ -1525,7 +1525,8 @@ int32_t msm_host_pipelined(tkm_ctx *ctx, const uint8_t *scalars, const uint8_t *
   if (pieces == 0) {  // automatic
     if (ctx->h2d_share > 0.55f) ctx->h2d_copy_bound = true;
     else if (ctx->h2d_share > 0.f && ctx->h2d_share < 0.40f) ctx->h2d_copy_bound = false;
-    const bool copy_bound = ctx->h2d_copy_bound;
+    bool copy_bound = ctx->h2d_copy_bound;
+    if (const char *e = getenv("TKM_MSM_HOST_COPY_BOUND")) copy_bound = atoi(e) != 0;  // developer knob: force a layout
     if (n < ((size_t)1 << 19)) {
       pieces = 1;
       weight[0] = 1;
