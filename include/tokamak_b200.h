@@ -246,7 +246,12 @@ enum {
   TKM_PEX_SUB = 3,   /* push a - b                                                  (Sub)                     */
   TKM_PEX_MUL = 4,   /* push a * b                                                  (Mul)                     */
   TKM_PEX_SCALE = 5, /* top *= consts32[operand]                                    (Scale)                   */
-  TKM_PEX_XM1 = 6    /* top *= (omega_x^i - 1), the evaluations of X - 1            (MulXMinusOne, :504-518)  */
+  TKM_PEX_XM1 = 6,   /* top *= (omega_x^i - 1), the evaluations of X - 1            (MulXMinusOne, :504-518)  */
+  /* push the evaluations of leaves[l](X / w_mx, Y / w_my), w_m the primitive m-th root of unity (a power of two dividing the
+   * domain's extent): operand = l | (log2(mx) + 1) << 4 | (log2(my) + 1) << 10, a zero field = that axis is not scaled.  On the
+   * evaluation grid this is leaves[l]'s table rotated by x_size/mx rows and y_size/my columns, so r(X/w, Y) and r(X/w, Y/w)
+   * (prove/src/lib.rs:2110-2146: scale_coeffs_x / _y of r, then PolyExpr::poly of each) cost no transform of their own. */
+  TKM_PEX_LEAF_SHIFT = 7
 };
 int32_t tkm_polyexpr_eval(tkm_ctx *ctx, const tkm_poly *const *leaves, uint32_t n_leaves, const uint32_t *program, uint32_t n_ops,
                           const uint8_t *consts32, uint32_t n_consts, size_t target_x, size_t target_y, tkm_poly **out);

@@ -736,6 +736,43 @@ def test_commit_begin_end_tickets(ctx, T):
     sigma.close()
 
 
+def test_poly_expr_leaf_over_roots(ctx, T):
+    """PolyExpr.poly_over_roots(p, mx, my) = p(X / w_mx, Y / w_my) as a rotated read of p's leaf transform
+    (TKM_PEX_LEAF_SHIFT): equal to the leaf of the explicitly scaled polynomial (scale_coeffs_x / _y by the inverse roots,
+    what prove2 builds for r(X/w, Y) and r(X/w, Y/w)), in a product with another leaf, on several domains; malformed operands
+    are rejected."""
+    import ctypes
+
+    E = T.PolyExpr
+    ctx.init_ntt_domain_for_size(1 << 14)
+    px, py = 16, 8
+    p = poly_from(T, ctx, O.random_fr(840, px * py), px, py)
+    q = poly_from(T, ctx, O.random_fr(841, px * py), px, py)
+    for mx, my, dx, dy in ((16, 0, 64, 16), (16, 8, 64, 16), (0, 8, 32, 32), (4, 2, 32, 16), (64, 16, 64, 16)):
+        s = p.clone()
+        if mx:
+            s = s.scale_coeffs_x(pow(ctx.get_root_of_unity(mx), -1, P.R_MOD))
+        if my:
+            s = s.scale_coeffs_y(pow(ctx.get_root_of_unity(my), -1, P.R_MOD))
+        exp = E.sub(E.mul(E.poly(s), E.poly(q)), E.poly(s)).evaluate_fused_with_domain(dx, dy, ctx)
+        expr = E.sub(E.mul(E.poly_over_roots(p, mx, my), E.poly(q)), E.poly_over_roots(p, mx, my))
+        got = expr.evaluate_fused_with_domain(dx, dy, ctx)
+        assert np.array_equal(got.copy_coeffs(), exp.copy_coeffs()), (mx, my, dx, dy)
+        c = expr.evaluate_coeffs(ctx)
+        c.resize(dx, dy)
+        assert np.array_equal(c.copy_coeffs(), exp.copy_coeffs())
+    with pytest.raises(ValueError):
+        E.poly_over_roots(p, 128, 0).evaluate_fused_with_domain(64, 16, ctx)  # root of order 128 on a 64-point axis
+    with pytest.raises(ValueError):
+        E.poly_over_roots(p, 12, 0)
+    hs = (ctypes.c_void_p * 1)(p.h)
+    cs = frs([0])
+    h = ctypes.c_void_p()
+    for word in (T.PEX_LEAF_SHIFT | (1 | 0 << 4) << 8, T.PEX_LEAF_SHIFT | (0 | 9 << 4) << 8, T.PEX_LEAF_SHIFT | (0 | 1 << 16) << 8):
+        prog = np.array([word], dtype=np.uint32)
+        assert ctx.lib.tkm_polyexpr_eval(ctx.h, hs, 1, prog.ctypes.data_as(ctypes.c_void_p), 1, cs.ctypes.data_as(ctypes.c_void_p), 1, 64, 16, ctypes.byref(h)) != 0
+
+
 def test_msm_begin_end_and_device_gather(ctx, T):
     """tkm_msm_g1_begin / tkm_msm_g1_indexed_begin (resolved by tkm_commit_end, buffers released right after begin) against the
     synchronous entry points and the oracle, queued out of order with empty inputs in between; tkm_fr_gather against numpy

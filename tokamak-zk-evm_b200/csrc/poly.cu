@@ -140,6 +140,18 @@ __global__ void __launch_bounds__(256) k_polyexpr(Fr *__restrict__ out, size_t x
           top.v[4] = hi.x; top.v[5] = hi.y; top.v[6] = hi.z; top.v[7] = hi.w;
           break;
         }
+        case TKM_PEX_LEAF_SHIFT: {  // the leaf's table rotated by x_size/mx rows and y_size/my columns (see the header)
+          st[sp++] = top;
+          const uint32_t lx = (arg >> 4) & 63u, ly = (arg >> 10) & 63u;
+          size_t i = e / y_size, j = e % y_size;
+          if (lx) i = (i + x_size - (x_size >> (lx - 1))) & (x_size - 1);
+          if (ly) j = (j + y_size - (y_size >> (ly - 1))) & (y_size - 1);
+          const uint4 *q = reinterpret_cast<const uint4 *>(pr.leaf[arg & 15u] + i * y_size + j);
+          uint4 lo = __ldg(q), hi = __ldg(q + 1);
+          top.v[0] = lo.x; top.v[1] = lo.y; top.v[2] = lo.z; top.v[3] = lo.w;
+          top.v[4] = hi.x; top.v[5] = hi.y; top.v[6] = hi.z; top.v[7] = hi.w;
+          break;
+        }
         case TKM_PEX_CONST:
           st[sp++] = top;
           top = pr.konst[arg];
@@ -936,6 +948,14 @@ int32_t tkm_polyexpr_eval(tkm_ctx *ctx, const tkm_poly *const *leaves, uint32_t 
       case TKM_PEX_ADD: case TKM_PEX_SUB: case TKM_PEX_MUL: TKM_REQUIRE(depth >= 2, "op %u: stack underflow", pc); depth--; break;
       case TKM_PEX_SCALE: TKM_REQUIRE(arg < n_consts && depth >= 1, "op %u: bad scale", pc); break;
       case TKM_PEX_XM1: TKM_REQUIRE(depth >= 1, "op %u: stack underflow", pc); break;
+      case TKM_PEX_LEAF_SHIFT: {
+        const uint32_t l = arg & 15u, lx = (arg >> 4) & 63u, ly = (arg >> 10) & 63u;
+        TKM_REQUIRE((arg >> 16) == 0 && l < n_leaves && leaves[l], "op %u: leaf %u out of range", pc, l);
+        TKM_REQUIRE((lx == 0 || ((size_t)1 << (lx - 1)) <= target_x) && (ly == 0 || ((size_t)1 << (ly - 1)) <= target_y),
+                    "op %u: the root's order must divide the domain's extent", pc);
+        depth++;
+        break;
+      }
       default: return fail(TKM_ERR_INVALID_ARGUMENT, "op %u: unknown opcode %u", pc, code);
     }
     TKM_REQUIRE(depth <= PEX_STACK, "op %u: expression needs more than %d stack entries", pc, PEX_STACK);

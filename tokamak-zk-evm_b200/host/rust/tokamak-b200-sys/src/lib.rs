@@ -23,6 +23,7 @@ pub const TKM_PEX_SUB: u32 = 3;
 pub const TKM_PEX_MUL: u32 = 4;
 pub const TKM_PEX_SCALE: u32 = 5;
 pub const TKM_PEX_XM1: u32 = 6;
+pub const TKM_PEX_LEAF_SHIFT: u32 = 7;
 
 extern "C" {
     pub fn tkm_last_error() -> *const c_char;

@@ -15,7 +15,7 @@ from .ffi import TkmError, check
 R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 FORWARD, INVERSE = 0, 1
 OP_ADD, OP_SUB, OP_MUL, OP_DIV = 0, 1, 2, 3
-PEX_LEAF, PEX_CONST, PEX_ADD, PEX_SUB, PEX_MUL, PEX_SCALE, PEX_XM1 = range(7)  # tkm_polyexpr_eval opcodes
+PEX_LEAF, PEX_CONST, PEX_ADD, PEX_SUB, PEX_MUL, PEX_SCALE, PEX_XM1, PEX_LEAF_SHIFT = range(8)  # tkm_polyexpr_eval opcodes
 
 
 def _vp(a):
@@ -661,6 +661,17 @@ class PolyExpr:
         return PolyExpr("poly", p)
 
     @staticmethod
+    def poly_over_roots(p, mx=0, my=0):
+        """p(X / w_mx, Y / w_my) with w_m the primitive m-th root of unity (m a power of two, 0 = axis not scaled): what
+        scale_coeffs_x / _y by an inverse root produce (r(X/w, Y), r(X/w, Y/w) in prove2, prove/src/lib.rs:2110-2146), as a leaf
+        that shares p's transform -- on the evaluation grid it is p's table rotated (TKM_PEX_LEAF_SHIFT).  An extension of the
+        reference's PolyExpr::poly; evaluate_coeffs falls back to the scaled polynomial."""
+        for m in (mx, my):
+            if m and m & (m - 1):
+                raise ValueError("the root's order must be a power of two")
+        return PolyExpr("poly_shift", p, int(mx), int(my))
+
+    @staticmethod
     def scalar(s):
         return PolyExpr("scalar", int(s) % R_MOD)
 
@@ -689,7 +700,7 @@ class PolyExpr:
         return PolyExpr("sum", [PolyExpr.scale(s, e) for s, e in terms])
 
     def _ctx(self):
-        if self.kind == "poly":
+        if self.kind in ("poly", "poly_shift"):
             return self.args[0].ctx
         for a in self.args:
             if isinstance(a, PolyExpr):
@@ -709,6 +720,13 @@ class PolyExpr:
         k, a = self.kind, self.args
         if k == "poly":
             return a[0].clone()
+        if k == "poly_shift":
+            q = a[0].clone()
+            if a[1]:
+                q = q.scale_coeffs_x(pow(ctx.get_root_of_unity(a[1]), R_MOD - 2, R_MOD))
+            if a[2]:
+                q = q.scale_coeffs_y(pow(ctx.get_root_of_unity(a[2]), R_MOD - 2, R_MOD))
+            return q
         if k == "scalar":
             return DensePolynomialExt.from_coeffs(ctx, frs_from_ints([a[0]]), 1, 1)
         if k == "add":
@@ -734,7 +752,7 @@ class PolyExpr:
     # -- degree bound (:262-309) ---------------------------------------------------------------------------
     def degree_bound(self):
         k, a = self.kind, self.args
-        if k == "poly":
+        if k in ("poly", "poly_shift"):
             return a[0].find_degree()
         if k == "scalar":
             return (-1, -1) if a[0] == 0 else (0, 0)
@@ -791,6 +809,12 @@ class PolyExpr:
             k, a = e.kind, e.args
             if k == "poly":
                 prog.append(PEX_LEAF | leaf(a[0]) << 8)
+            elif k == "poly_shift":  # p(X / w_mx, Y / w_my): the same leaf transform, read rotated
+                if a[1] > target_x_size or a[2] > target_y_size:
+                    raise ValueError("the root's order must divide the domain's extent")
+                fx = (a[1].bit_length() if a[1] else 0)  # log2(m) + 1 for a power of two, 0 = axis not scaled
+                fy = (a[2].bit_length() if a[2] else 0)
+                prog.append(PEX_LEAF_SHIFT | (leaf(a[0]) | fx << 4 | fy << 10) << 8)
             elif k == "scalar":
                 prog.append(PEX_CONST | const(a[0]) << 8)
             elif k in ("add", "sub", "mul"):

@@ -303,10 +303,14 @@ class GpuBackend:
         (PolyExpr::evaluate_fused_with_domain, prove/src/lib.rs:2110-2146)."""
         from .. import PolyExpr as E
 
+        # r(X/w, Y) and r(X/w, Y/w) are r's evaluation table rotated by x_size/m_I rows (and y_size/s_max columns): they
+        # share r's leaf transform (TKM_PEX_LEAF_SHIFT), five forward biNTTs instead of seven
+        m_i, s_max = x_size // 4, y_size // 2
+        e_wX, e_wXwY = E.poly_over_roots(r, m_i, 0), E.poly_over_roots(r, m_i, s_max)  # == E.poly(r_wX), E.poly(r_wXwY)
         rg = E.mul(E.poly(r), E.poly(g))
         p1 = E.mul(E.sub(E.poly(r), E.scalar(1)), E.poly(KL))
-        p2 = E.mul_x_minus_one(E.sub(rg, E.mul(E.poly(r_wX), E.poly(f))))
-        p3 = E.mul(E.poly(K0), E.sub(rg, E.mul(E.poly(r_wXwY), E.poly(f))))
+        p2 = E.mul_x_minus_one(E.sub(rg, E.mul(e_wX, E.poly(f))))
+        p3 = E.mul(E.poly(K0), E.sub(rg, E.mul(e_wXwY, E.poly(f))))
         expr = E.weighted_sum([(1, p1), (kappa0 % R_MOD, p2), (kappa0 * kappa0 % R_MOD, p3)])
         return expr.evaluate_fused_with_domain(x_size, y_size, self.ctx)
 
