@@ -243,6 +243,20 @@ static int run_gpu_tests() {
     }
     EXPECT(threw);
   });
+  T("PolyExpr::poly_over_roots == the leaf of the scaled polynomial (r(X/w, Y), r(X/w, Y/w) of prove2)", [&] {
+    ctx.init_ntt_domain_for_size(1 << 10);
+    auto p = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(8 * 4), 8, 4);
+    auto q = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(8 * 4), 8, 4);
+    auto scaled = p.scale_coeffs_x(ctx.get_root_of_unity(8).inv()).scale_coeffs_y(ctx.get_root_of_unity(4).inv());
+    auto lhs = PolyExpr::mul(PolyExpr::poly_over_roots(p, 8, 4), PolyExpr::poly(q)).evaluate_fused_with_domain(ctx, 32, 8);
+    auto rhs = PolyExpr::mul(PolyExpr::poly(scaled), PolyExpr::poly(q)).evaluate_fused_with_domain(ctx, 32, 8);
+    auto cf = PolyExpr::mul(PolyExpr::poly_over_roots(p, 8, 4), PolyExpr::poly(q)).evaluate_coeffs(ctx);
+    for (int k = 0; k < 6; k++) {
+      auto pt = rng.generate_random(2);
+      EXPECT(lhs.eval(pt[0], pt[1]) == rhs.eval(pt[0], pt[1]));
+      EXPECT(cf.eval(pt[0], pt[1]) == rhs.eval(pt[0], pt[1]));
+    }
+  });
   T("poly_comb! as one lincomb pass == chained operators (prove/src/lib.rs:30-38,48-124)", [&] {
     auto p = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(8 * 4), 8, 4);
     auto q = DensePolynomialExt::from_coeffs(ctx, rng.generate_random(4 * 16), 4, 16);

@@ -433,10 +433,21 @@ inline DensePolynomialExt operator-(const ScalarField &s, const DensePolynomialE
 // distinct leaf (pointer-keyed, like the reference's leaf cache :459-502), ONE pointwise kernel, one inverse biNTT.
 class PolyExpr {
  public:
-  enum Kind { Poly, Scalar, Add, Sub, Mul, Scale, MulXMinusOne, Sum };
+  enum Kind { Poly, Scalar, Add, Sub, Mul, Scale, MulXMinusOne, Sum, PolyOverRoots };
   static PolyExpr poly(const DensePolynomialExt &p) {
     PolyExpr e(Poly);
     e.n_->p = &p;
+    return e;
+  }
+  // p(X / w_mx, Y / w_my), w_m the primitive m-th root of unity (m a power of two; 0 = axis not scaled): what
+  // scale_coeffs_x / _y by an inverse root produce (r(X/w, Y), r(X/w, Y/w) of prove2, prove/src/lib.rs:2110-2146) as a leaf that
+  // shares p's transform (TKM_PEX_LEAF_SHIFT: p's evaluation table read rotated).  An addition to the reference's constructors.
+  static PolyExpr poly_over_roots(const DensePolynomialExt &p, uint64_t mx, uint64_t my) {
+    if ((mx & (mx - 1)) || (my & (my - 1))) throw std::runtime_error("the root's order must be a power of two");
+    PolyExpr e(PolyOverRoots);
+    e.n_->p = &p;
+    e.n_->mx = mx;
+    e.n_->my = my;
     return e;
   }
   static PolyExpr scalar(const ScalarField &s) {
@@ -501,6 +512,7 @@ class PolyExpr {
     Kind k;
     const DensePolynomialExt *p = nullptr;
     ScalarField s = ScalarField::zero();
+    uint64_t mx = 0, my = 0;  // PolyOverRoots
     std::vector<std::shared_ptr<Node>> kids;
   };
   struct Program {
@@ -529,6 +541,11 @@ class PolyExpr {
   static void emit(const Node &n, Program &pr) {
     switch (n.k) {
       case Poly: pr.ops.push_back(TKM_PEX_LEAF | pr.leaf(n.p) << 8); break;
+      case PolyOverRoots: {
+        auto field = [](uint64_t m) { uint32_t f = 0; while (m) { f++; m >>= 1; } return f; };  // log2(m) + 1, 0 = not scaled
+        pr.ops.push_back(TKM_PEX_LEAF_SHIFT | (pr.leaf(n.p) | field(n.mx) << 4 | field(n.my) << 10) << 8);
+        break;
+      }
       case Scalar: pr.ops.push_back(TKM_PEX_CONST | pr.konst(n.s) << 8); break;
       case Add: case Sub: case Mul:
         emit(*n.kids[0], pr);
@@ -555,6 +572,12 @@ class PolyExpr {
   static DensePolynomialExt coeffs(const Node &n, const Context &c) {
     switch (n.k) {
       case Poly: return DensePolynomialExt(*n.p);
+      case PolyOverRoots: {
+        DensePolynomialExt q(*n.p);
+        if (n.mx) q = q.scale_coeffs_x(c.get_root_of_unity(n.mx).inv());
+        if (n.my) q = q.scale_coeffs_y(c.get_root_of_unity(n.my).inv());
+        return q;
+      }
       case Scalar: return DensePolynomialExt::from_coeffs(c, {n.s}, 1, 1);
       case Add: return coeffs(*n.kids[0], c) + coeffs(*n.kids[1], c);
       case Sub: return coeffs(*n.kids[0], c) - coeffs(*n.kids[1], c);
@@ -575,7 +598,7 @@ class PolyExpr {
   }
   static std::pair<int64_t, int64_t> bound(const Node &n) {
     switch (n.k) {
-      case Poly: return n.p->find_degree();
+      case Poly: case PolyOverRoots: return n.p->find_degree();
       case Scalar: return n.s == ScalarField::zero() ? std::make_pair<int64_t, int64_t>(-1, -1) : std::make_pair<int64_t, int64_t>(0, 0);
       case Add: case Sub: {
         auto l = bound(*n.kids[0]), r = bound(*n.kids[1]);

@@ -33,6 +33,14 @@ pub fn init_ntt_domain_for_size(size: usize) -> Result<(), ()> {
     Ok(())
 }
 
+/// ntt::get_root_of_unity (uses at bivariate_polynomial/mod.rs:505, prove/src/lib.rs:1971-1972): the primitive n-th root
+pub fn get_root_of_unity(n: u64) -> ScalarField {
+    assert!(n.is_power_of_two(), "root order must be a power of two");
+    let mut out = [0u8; 32];
+    check(unsafe { sys::tkm_root_of_unity(n.trailing_zeros(), out.as_mut_ptr()) });
+    ScalarField::from_bytes_le(&out)
+}
+
 impl DensePolynomialExt {
     fn wrap(h: *mut sys::tkm_poly) -> Self {
         let (mut x, mut y) = (0usize, 0usize);
@@ -278,6 +286,10 @@ pub enum PolyExpr<'a> {
     Scale(ScalarField, Box<PolyExpr<'a>>),
     MulXMinusOne(Box<PolyExpr<'a>>),
     Sum(Vec<PolyExpr<'a>>),
+    /// p(X / w_mx, Y / w_my), w_m the primitive m-th root of unity (0 = axis not scaled): an addition to the reference's
+    /// constructors -- the leaf of `p.scale_coeffs_x(w_mx^-1).scale_coeffs_y(w_my^-1)` read rotated out of p's transform
+    /// (TKM_PEX_LEAF_SHIFT), as prove2 needs for r(X/w, Y) and r(X/w, Y/w) (prove/src/lib.rs:2110-2146)
+    PolyOverRoots(&'a DensePolynomialExt, u64, u64),
 }
 
 #[derive(Default)]
@@ -302,6 +314,10 @@ impl Program {
 
 impl<'a> PolyExpr<'a> {
     pub fn poly(poly: &'a DensePolynomialExt) -> Self { Self::Poly(poly) }
+    pub fn poly_over_roots(poly: &'a DensePolynomialExt, mx: u64, my: u64) -> Self {
+        assert!(mx & mx.wrapping_sub(1) == 0 && my & my.wrapping_sub(1) == 0, "the root's order must be a power of two");
+        Self::PolyOverRoots(poly, mx, my)
+    }
     pub fn scalar(scalar: ScalarField) -> Self { Self::Scalar(scalar) }
     pub fn add(lhs: Self, rhs: Self) -> Self { Self::Add(Box::new(lhs), Box::new(rhs)) }
     pub fn sub(lhs: Self, rhs: Self) -> Self { Self::Sub(Box::new(lhs), Box::new(rhs)) }
@@ -316,6 +332,12 @@ impl<'a> PolyExpr<'a> {
     pub fn evaluate_coeffs(&self) -> DensePolynomialExt {
         match self {
             Self::Poly(p) => (*p).clone(),
+            Self::PolyOverRoots(p, mx, my) => {
+                let mut q = (*p).clone();
+                if *mx != 0 { q = q.scale_coeffs_x(&get_root_of_unity(*mx).inv()); }
+                if *my != 0 { q = q.scale_coeffs_y(&get_root_of_unity(*my).inv()); }
+                q
+            }
             Self::Scalar(s) => DensePolynomialExt::from_coeffs(&[*s], 1, 1),
             Self::Add(l, r) => &l.evaluate_coeffs() + &r.evaluate_coeffs(),
             Self::Sub(l, r) => &l.evaluate_coeffs() - &r.evaluate_coeffs(),
@@ -338,7 +360,7 @@ impl<'a> PolyExpr<'a> {
     /// degree bound (:262-309); (-1, -1) = the zero polynomial
     pub fn degree_bound(&self) -> (i64, i64) {
         match self {
-            Self::Poly(p) => p.find_degree(),
+            Self::Poly(p) | Self::PolyOverRoots(p, _, _) => p.find_degree(),
             Self::Scalar(s) => if *s == ScalarField::zero() { (-1, -1) } else { (0, 0) },
             Self::Add(l, r) | Self::Sub(l, r) => {
                 let (a, b) = (l.degree_bound(), r.degree_bound());
@@ -385,6 +407,11 @@ impl<'a> PolyExpr<'a> {
     fn emit(&self, pr: &mut Program) {
         match self {
             Self::Poly(p) => { let i = pr.leaf(p); pr.ops.push(sys::TKM_PEX_LEAF | i << 8); }
+            Self::PolyOverRoots(p, mx, my) => {
+                let field = |m: u64| 64 - m.leading_zeros();  // log2(m) + 1, 0 = axis not scaled
+                let i = pr.leaf(p);
+                pr.ops.push(sys::TKM_PEX_LEAF_SHIFT | (i | field(*mx) << 4 | field(*my) << 10) << 8);
+            }
             Self::Scalar(s) => { let i = pr.konst(*s); pr.ops.push(sys::TKM_PEX_CONST | i << 8); }
             Self::Add(l, r) => { l.emit(pr); r.emit(pr); pr.ops.push(sys::TKM_PEX_ADD); }
             Self::Sub(l, r) => { l.emit(pr); r.emit(pr); pr.ops.push(sys::TKM_PEX_SUB); }
