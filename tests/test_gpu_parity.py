@@ -591,6 +591,34 @@ def test_mul_polynomial(ctx, T):
     assert (pa * z).is_zero()
 
 
+@pytest.mark.parametrize("sa,sb", [((32, 1), (16, 8)), ((16, 8), (32, 1)), ((1, 16), (8, 32)), ((8, 32), (1, 16)), ((64, 1), (1, 32)),
+                                   ((1, 32), (64, 1)), ((16, 1), (32, 1)), ((1, 8), (1, 64)), ((2048, 1), (1024, 4)), ((4096, 1), (4096, 64))])
+def test_mul_with_a_univariate_factor(ctx, T, sa, sb):
+    """_mul when a factor is X- or Y-univariate (K0(X) * d(X, Y), L(X) * L(Y), t(X) * q in prove2/prove4): the one-axis
+    convolution path (transform along that axis only) gives the shape and coefficients of the general product, also when the
+    univariate factor is stored with a padded second axis of zeros and on axes long enough for the two-pass NTT."""
+    a = O.random_fr(343 + sa[0] + sb[1], sa[0] * sa[1])
+    b = O.random_fr(344 + sa[1] + sb[0], sb[0] * sb[1])
+    pa, pb = poly_from(T, ctx, a, *sa), poly_from(T, ctx, b, *sb)
+    ctx.init_ntt_domain_for_size(1 << 20)
+    m = pa * pb
+    exp, nx, ny = P.poly_mul(to_ints(a), sa[0], sa[1], to_ints(b), sb[0], sb[1]) if sa[0] * sb[0] <= 4096 else (None, None, None)
+    if exp is not None:
+        assert m.shape == (nx, ny) and m.coeffs_ints() == exp
+    else:  # large: the product at random points
+        for k in range(4):
+            x, y = 0x1234567 + k, (1 << 200) + 77 * k
+            assert m.eval(x, y) == pa.eval(x, y) * pb.eval(x, y) % P.R_MOD
+    # the same factor stored with a zero-padded second axis (degree 0 along it, size 4)
+    if sa[1] == 1 and exp is not None:
+        wide = np.zeros((sa[0], 4, 4), dtype=np.uint64)
+        wide[:, 0, :] = a
+        pw = poly_from(T, ctx, wide.reshape(-1, 4), sa[0], 4)
+        m2 = pw * pb
+        m2.resize(nx, ny)
+        assert m2.coeffs_ints() == exp
+
+
 @pytest.mark.parametrize("x,y,c,d", [(16, 16, 4, 4), (64, 32, 16, 8), (8192, 512, 4096, 256), (256, 64, 64, 64 // 2)])
 def test_div_by_vanishing_opt(ctx, T, x, y, c, d):
     """test_div_by_vanishing_opt_basic (tests.rs:1224-1237): build P = Qx t_x + Qy t_y, divide, compare with the oracle

@@ -571,6 +571,50 @@ int32_t poly_resize(tkm_ctx *ctx, tkm_poly *p, size_t tx, size_t ty) {
   return TKM_OK;
 }
 
+// p[i][j] *= v[i] (by_row) or v[j]: the pointwise step of a product with a univariate factor.
+__global__ void __launch_bounds__(256) k_axis_scale(Fr *__restrict__ p, const Fr *__restrict__ v, size_t x_size, size_t y_size, int by_row) {
+  const size_t total = x_size * y_size;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const Fr s = v[by_row ? e / y_size : e % y_size];
+    p[e] = p[e] * s;
+  }
+}
+
+// _mul with a univariate factor (K0(X) * d(X, Y), t(X) * q(X, Y), L(X) * L(Y) in prove2/prove4): the product is a
+// convolution along ONE axis, so only that axis is transformed -- the other axis' passes of all three transforms and the whole
+// 2-D transform of the univariate factor are not needed.  uni: the univariate factor (degree 0 along the other axis), its
+// coefficients along `x_axis ? X : Y`; other: any polynomial.  Same result as the general path (exact arithmetic).
+static int32_t poly_mul_univariate(tkm_ctx *ctx, const tkm_poly *uni, int64_t udeg, bool x_axis, const tkm_poly *other, int64_t odx, int64_t ody,
+                                   tkm_poly **out) {
+  const size_t nx = next_pow2((size_t)(odx + (x_axis ? udeg : 0) + 1)), ny = next_pow2((size_t)(ody + (x_axis ? 0 : udeg) + 1));
+  const size_t na = x_axis ? nx : ny;
+  if (ctx->domain_log2 < 0) return fail(TKM_ERR_DOMAIN, "NTT domain is not initialized. Call tkm_ntt_domain_init first.");
+  if (log2_exact(nx) + log2_exact(ny) > (uint32_t)ctx->domain_log2)  // the general path's condition, kept (bivariate_polynomial/mod.rs:1440-1445)
+    return fail(TKM_ERR_DOMAIN, "NTT domain size too small: initialized size 2^%d but input size %zu", ctx->domain_log2, nx * ny);
+  tkm_poly *res = nullptr;
+  TKM_TRY(poly_alloc(ctx, nx, ny, &res));
+  Scratch<Fr> vec;
+  int32_t st = vec.alloc(ctx, na);
+  if (st == TKM_OK) st = poly_reshape_into(ctx, other->d, other->x_size, other->y_size, nx, ny, 0, 0, res->d);
+  // the factor's coefficients: column 0 of uni (x axis) or row 0 (y axis), zero-padded to the axis length
+  if (st == TKM_OK) st = x_axis ? poly_reshape_into(ctx, uni->d, uni->x_size, uni->y_size, na, 1, 0, 0, vec.p)
+                                : poly_reshape_into(ctx, uni->d, uni->x_size, uni->y_size, 1, na, 0, 0, vec.p);
+  const size_t outer = x_axis ? 1 : nx, inner = x_axis ? ny : 1;
+  if (st == TKM_OK) st = ntt_axis(ctx, res->d, res->d, outer, na, inner, TKM_FORWARD, nullptr);
+  if (st == TKM_OK) st = ntt_axis(ctx, vec.p, vec.p, 1, na, 1, TKM_FORWARD, nullptr);
+  if (st == TKM_OK) {
+    k_axis_scale<<<grid_for(nx * ny, 256, ctx->sm_count), 256, 0, ctx->stream>>>(res->d, vec.p, nx, ny, x_axis ? 1 : 0);
+    st = launch_check(ctx, "k_axis_scale");
+  }
+  if (st == TKM_OK) st = ntt_axis(ctx, res->d, res->d, outer, na, inner, TKM_INVERSE, nullptr);
+  if (st != TKM_OK) {
+    poly_release(ctx, res);
+    return st;
+  }
+  *out = res;
+  return TKM_OK;
+}
+
 int32_t poly_mul(tkm_ctx *ctx, const tkm_poly *a, const tkm_poly *b, tkm_poly **out) {
   int64_t adx, ady, bdx, bdy;
   TKM_TRY(poly_find_degree(ctx, a, &adx, &ady));
@@ -596,6 +640,11 @@ int32_t poly_mul(tkm_ctx *ctx, const tkm_poly *a, const tkm_poly *b, tkm_poly **
     size_t cnt = (*out)->x_size * (*out)->y_size;
     return vec_scale(ctx, s, other->d, (*out)->d, cnt);
   }
+  // a univariate factor: one-axis convolution (a or b; X- or Y-univariate)
+  if (ady == 0) return poly_mul_univariate(ctx, a, adx, true, b, bdx, bdy, out);
+  if (bdy == 0) return poly_mul_univariate(ctx, b, bdx, true, a, adx, ady, out);
+  if (adx == 0) return poly_mul_univariate(ctx, a, ady, false, b, bdx, bdy, out);
+  if (bdx == 0) return poly_mul_univariate(ctx, b, bdy, false, a, adx, ady, out);
   const size_t tx = (size_t)(adx + bdx + 1), ty = (size_t)(ady + bdy + 1);
   const size_t nx = next_pow2(tx), ny = next_pow2(ty);
   const size_t total = nx * ny;
