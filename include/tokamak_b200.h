@@ -321,6 +321,9 @@ int32_t tkm_msm_g1_sharded(tkm_ctx *ctx, const void *dev_scalars, int32_t scalar
 int32_t tkm_bintt_sharded(tkm_ctx *ctx, const void *dev_in, void *dev_out, size_t x_size, size_t y_size, int32_t dir,
                           const uint8_t *coset_x32, const uint8_t *coset_y32);
 
+/* Keccak-256 with the original 0x01 padding (tiny_keccak::Keccak::v256): the hash of RollingKeccakTranscript
+ * (prove/src/lib.rs:3211-3519).  Host only, no device needed. */
+int32_t tkm_host_keccak256(const uint8_t *data, size_t len, uint8_t out32[32]);
 /* ---- host-side data loader (no device work) -------------------------------------------------------
  * Every "0x..." string of a JSON text, in file order, as 32-byte canonical little-endian scalars reduced mod r:
  * the HexString -> ScalarField::from_hex parsing of placementVariables.json / instance.json

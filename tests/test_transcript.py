@@ -21,6 +21,18 @@ def _sha3_via_our_permutation(data: bytes) -> bytes:
     return b"".join(a[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
 
 
+def test_native_keccak_matches_the_restatement():
+    """tkm_host_keccak256 (host-side function of the library, no device needed) against the pure-Python restatement on every
+    length around the rate boundaries (135, 136, 137, 271, 272, ...) and on random data; keccak256 uses it when the library loads."""
+    import random
+
+    rng = random.Random(5)
+    for n in list(range(0, 300)) + [1000, 1087, 1088, 1089, 4096]:
+        data = bytes(rng.randrange(256) for _ in range(n))
+        assert TR.keccak256(data) == TR.keccak256_py(data), n
+    assert TR._native is not TR.keccak256_py, "the shared library should be loadable in this test environment"
+
+
 def test_keccak256_known_answers():
     assert TR.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
     assert TR.keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"

@@ -978,6 +978,55 @@ int32_t tkm_launch_count(tkm_ctx *ctx, uint64_t *out) {
   return TKM_OK;
 }
 
+// Keccak-256 with the original 0x01 padding (tiny_keccak::Keccak::v256, the hash of the reference's Fiat-Shamir transcript,
+// prove/src/lib.rs:3211-3519), on the host: a proof takes ~90 hashes of 100 bytes between its stages, and while the host
+// hashes the device has nothing queued.
+static void keccak_f1600(uint64_t a[25]) {
+  static const uint64_t RC[24] = {0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808Aull, 0x8000000080008000ull, 0x000000000000808Bull,
+                                  0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008Aull, 0x0000000000000088ull,
+                                  0x0000000080008009ull, 0x000000008000000Aull, 0x000000008000808Bull, 0x800000000000008Bull, 0x8000000000008089ull,
+                                  0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800Aull, 0x800000008000000Aull,
+                                  0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};  // [x + 5y]
+  auto rol = [](uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; };
+  for (int round = 0; round < 24; round++) {
+    uint64_t c[5], b[25];
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+    for (int x = 0; x < 5; x++) {
+      const uint64_t d = c[(x + 4) % 5] ^ rol(c[(x + 1) % 5], 1);
+      for (int y = 0; y < 5; y++) a[x + 5 * y] ^= d;
+    }
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol(a[x + 5 * y], ROT[x + 5 * y]);
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+    a[0] ^= RC[round];
+  }
+}
+int32_t tkm_host_keccak256(const uint8_t *data, size_t len, uint8_t out32[32]) {
+  if ((!data && len) || !out32) return fail(TKM_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t rate = 136;
+  uint64_t a[25] = {0};
+  auto absorb = [&](const uint8_t *blk) {
+    for (size_t i = 0; i < rate / 8; i++) {
+      uint64_t w = 0;
+      for (int k = 7; k >= 0; k--) w = (w << 8) | blk[8 * i + k];
+      a[i] ^= w;
+    }
+    keccak_f1600(a);
+  };
+  size_t off = 0;
+  for (; off + rate <= len; off += rate) absorb(data + off);
+  uint8_t last[136] = {0};
+  if (len > off) memcpy(last, data + off, len - off);
+  last[len - off] ^= 0x01;
+  last[rate - 1] ^= 0x80;
+  absorb(last);
+  for (int i = 0; i < 4; i++)
+    for (int k = 0; k < 8; k++) out32[8 * i + k] = (uint8_t)(a[i] >> (8 * k));
+  return TKM_OK;
+}
+
 int32_t tkm_microbench(tkm_ctx *ctx, int32_t kind, double *out_ops_per_s) {
   API_BEGIN
   TKM_REQUIRE(out_ops_per_s, "null out pointer");

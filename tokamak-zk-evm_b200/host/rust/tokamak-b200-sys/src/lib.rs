@@ -128,6 +128,7 @@ extern "C" {
     pub fn tkm_event_time_begin(ctx: *mut tkm_ctx) -> i32;
     pub fn tkm_event_time_end(ctx: *mut tkm_ctx, out_ms: *mut f32) -> i32;
     pub fn tkm_launch_count(ctx: *mut tkm_ctx, out: *mut u64) -> i32;
+    pub fn tkm_host_keccak256(data: *const u8, len: usize, out32: *mut u8) -> i32;
     pub fn tkm_microbench(ctx: *mut tkm_ctx, kind: i32, out_ops_per_s: *mut f64) -> i32;
     pub fn tkm_poly_lincomb(ctx: *mut tkm_ctx, k: u32, polys: *const *const tkm_poly, coeffs32: *const u8, shift_x: *const u32,
                             shift_y: *const u32, out: *mut *mut tkm_poly) -> i32;

@@ -41,6 +41,15 @@ def frs_from_ints(vs):
     return np.frombuffer(b"".join(int(v % R_MOD).to_bytes(32, "little") for v in vs), dtype=np.uint64).reshape(-1, 4).copy()
 
 
+def frs_sparse(size, entries):
+    """`size` field elements, zero except entries = {index: int}: the vanishing, monomial and unit-vector tables of the prover
+    without a Python loop over their zeros."""
+    a = np.zeros((size, 4), dtype=np.uint64)
+    for i, v in entries.items():
+        a[i] = np.frombuffer(int(v % R_MOD).to_bytes(32, "little"), dtype=np.uint64)
+    return a
+
+
 def frs_to_ints(a):
     b = np.ascontiguousarray(a, dtype=np.uint64).tobytes()
     return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]

@@ -109,6 +109,7 @@ SIGNATURES = {
     "tkm_event_time_begin": [c_void_p],
     "tkm_event_time_end": [c_void_p, P(ctypes.c_float)],
     "tkm_launch_count": [c_void_p, P(c_uint64)],
+    "tkm_host_keccak256": [ctypes.c_char_p, c_size_t, ctypes.c_char_p],
     "tkm_microbench": [c_void_p, c_int32, P(ctypes.c_double)],
     "tkm_kernel_time_last": [c_void_p, P(ctypes.c_float)],
 }

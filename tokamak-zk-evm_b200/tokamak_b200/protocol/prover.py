@@ -8,7 +8,7 @@ from dataclasses import dataclass
 from typing import List
 
 
-from .. import frs_from_ints
+from .. import frs_from_ints, frs_sparse
 from ..transcript import TranscriptManager
 from . import qap
 from .formats import format_proof
@@ -161,38 +161,33 @@ class Prover:
 
     # ---- small fixed polynomials
     def _vanishing_x(self, k):
-        c = [0] * (2 * k)
-        c[0], c[k] = NEG_ONE, ONE
-        return self.be.from_coeffs(frs_from_ints(c), 2 * k, 1)
+        return self.be.from_coeffs(frs_sparse(2 * k, {0: NEG_ONE, k: ONE}), 2 * k, 1)
 
     def _vanishing_y(self, k):
-        c = [0] * (2 * k)
-        c[0], c[k] = NEG_ONE, ONE
-        return self.be.from_coeffs(frs_from_ints(c), 1, 2 * k)
+        return self.be.from_coeffs(frs_sparse(2 * k, {0: NEG_ONE, k: ONE}), 1, 2 * k)
 
     def _low_degree_x_times_vanishing(self, coeffs, exponent):
         size = _pow2(exponent + len(coeffs))
-        out = [0] * size
+        out = {}
         for i, c in enumerate(coeffs):
-            out[i] = (out[i] - c) % R_MOD
-            out[i + exponent] = (out[i + exponent] + c) % R_MOD
-        return out, size
+            out[i] = (out.get(i, 0) - c) % R_MOD
+            out[i + exponent] = (out.get(i + exponent, 0) + c) % R_MOD
+        return frs_sparse(size, out), size
 
     def low_degree_x_times_vanishing(self, coeffs, exponent):
         out, size = self._low_degree_x_times_vanishing(coeffs, exponent)
-        return self.be.from_coeffs(frs_from_ints(out), size, 1)
+        return self.be.from_coeffs(out, size, 1)
 
     def low_degree_y_times_vanishing(self, coeffs, exponent):
         out, size = self._low_degree_x_times_vanishing(coeffs, exponent)
-        return self.be.from_coeffs(frs_from_ints(out), 1, size)
+        return self.be.from_coeffs(out, 1, size)
 
     def _mono(self, x):
         return self.be.from_coeffs(frs_from_ints([0, 1]), 2, 1) if x else self.be.from_coeffs(frs_from_ints([0, 1]), 1, 2)
 
     def _lagrange(self, size, idx, along_x):
-        ev = [0] * size
-        ev[idx] = 1
-        return self.be.from_rou_evals(frs_from_ints(ev), size, 1) if along_x else self.be.from_rou_evals(frs_from_ints(ev), 1, size)
+        ev = frs_sparse(size, {idx: 1})
+        return self.be.from_rou_evals(ev, size, 1) if along_x else self.be.from_rou_evals(ev, 1, size)
 
     def encode(self, poly, name):
         """Sigma1::encode_poly.  With a backend that can queue commitments (commit_async) this returns a pending handle:

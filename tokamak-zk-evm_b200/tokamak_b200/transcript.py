@@ -1,7 +1,9 @@
 """Fiat-Shamir transcript of the Tokamak prover/verifier, host side (the reference computes it on the host with
 tiny_keccak): RollingKeccakTranscript and the TranscriptManager absorb/squeeze schedule
 (packages/backend/prove/src/lib.rs:3211-3730).  Hash = Keccak-256 with the original 0x01 padding (not SHA3-256).
-Pure Python: a proof needs a few dozen 100-byte hashes."""
+A proof needs ~90 hashes of 100 bytes between its stages, while the device has nothing queued: keccak256 goes through the
+library's host-side tkm_host_keccak256 (40 ms of pure Python per proof otherwise); keccak256_py is the same function in pure
+Python (the KAT-pinned restatement, and what runs when the shared library is not built)."""
 
 R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 
@@ -32,7 +34,7 @@ def _keccak_f(a):
     return a
 
 
-def keccak256(data: bytes) -> bytes:
+def keccak256_py(data: bytes) -> bytes:
     """Keccak-256 (rate 136, original padding 0x01 .. 0x80), as tiny_keccak::Keccak::new_keccak256."""
     rate = 136
     msg = bytearray(data)
@@ -47,6 +49,33 @@ def keccak256(data: bytes) -> bytes:
         a = _keccak_f(a)
     out = b"".join(a[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
     return out
+
+
+_native = None
+
+
+def keccak256(data: bytes) -> bytes:
+    """keccak256_py through the library's host function when the shared library is there (no device needed)."""
+    global _native
+    if _native is None:
+        try:
+            import ctypes
+
+            from . import ffi
+
+            lib = ffi.load()
+            buf = ctypes.create_string_buffer(32)
+
+            def _native(d, _lib=lib, _buf=buf):
+                if _lib.tkm_host_keccak256(d, len(d), _buf) != 0:
+                    raise RuntimeError("tkm_host_keccak256 failed")
+                return _buf.raw
+
+            if _native(b"") != keccak256_py(b""):  # paranoia: never trade a wrong transcript for speed
+                raise RuntimeError("native Keccak disagrees with the restatement")
+        except Exception:
+            _native = keccak256_py
+    return _native(bytes(data))
 
 
 class RollingKeccakTranscript:
