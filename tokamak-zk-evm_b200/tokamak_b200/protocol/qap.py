@@ -117,8 +117,9 @@ class WitnessTable:
             self.var_off[col] = off
             off += len(pl.variables)
             limbs = getattr(pl.variables, "limbs", None)  # ScalarArray from the native loader: already in device layout
-            chunks.append(limbs.tobytes() if limbs is not None else b"".join([v.to_bytes(32, "little") for v in pl.variables]))
-        self.values = np.frombuffer(b"".join(chunks), dtype=np.uint64).reshape(-1, 4)
+            chunks.append(limbs if limbs is not None
+                          else np.frombuffer(b"".join([v.to_bytes(32, "little") for v in pl.variables]), dtype=np.uint64).reshape(-1, 4))
+        self.values = np.concatenate(chunks) if chunks else np.zeros((0, 4), dtype=np.uint64)  # one copy of the ~19 MB table
         self.fmap = [np.array(s.flattenMap, dtype=np.int64) for s in infos]
 
     def gather_indices(self, lo, hi, s_max):
