@@ -289,6 +289,8 @@ int32_t tkm_ctx_destroy(tkm_ctx *ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     for (cudaEvent_t e : ctx->copy_ev)
       if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->copy_t)
+      if (e) cudaEventDestroy(e);
   }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;

@@ -64,12 +64,12 @@ def keccak256(data: bytes) -> bytes:
             from . import ffi
 
             lib = ffi.load()
-            buf = ctypes.create_string_buffer(32)
 
-            def _native(d, _lib=lib, _buf=buf):
-                if _lib.tkm_host_keccak256(d, len(d), _buf) != 0:
+            def _native(d, _lib=lib, _mk=ctypes.create_string_buffer):
+                buf = _mk(32)  # per call: the transcript may be driven from more than one thread
+                if _lib.tkm_host_keccak256(d, len(d), buf) != 0:
                     raise RuntimeError("tkm_host_keccak256 failed")
-                return _buf.raw
+                return buf.raw
 
             if _native(b"") != keccak256_py(b""):  # paranoia: never trade a wrong transcript for speed
                 raise RuntimeError("native Keccak disagrees with the restatement")
