@@ -75,4 +75,34 @@ impl G1Table {
         }
         out
     }
+    /// The same MSM queued (tkm_msm_g1_indexed_begin): returns at once with a ticket; `PendingG1::get` resolves it
+    /// (tkm_commit_end).  Prover::init's O_pub_free / O_mid / O_prv and their blinding sums (prove/src/lib.rs:1092-1176) are
+    /// independent, so a caller queues them all and collects them together: their serial tails overlap.
+    pub fn msm_indexed_begin(&self, scalars: &[ScalarField], idx: &[u32]) -> PendingG1 {
+        if scalars.len() != idx.len() { panic!("Mismatch between the numbers of bases and scalars"); }
+        let mut ticket: i32 = -1;
+        unsafe {
+            let (mut ds, mut di, mut dt) = (std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut());
+            check(sys::tkm_crs_device_ptr(self.h, &mut dt, std::ptr::null_mut(), std::ptr::null_mut()));
+            check(sys::tkm_dev_alloc(ctx(), scalars.len().max(1) * 32, &mut ds));
+            check(sys::tkm_dev_alloc(ctx(), idx.len().max(1) * 4, &mut di));
+            check(sys::tkm_memcpy_h2d(ctx(), ds, scalars.as_ptr() as *const _, scalars.len() * 32));
+            check(sys::tkm_memcpy_h2d(ctx(), di, idx.as_ptr() as *const _, idx.len() * 4));
+            let st = sys::tkm_msm_g1_indexed_begin(ctx(), ds, 0, dt, di, scalars.len(), &mut ticket);
+            sys::tkm_dev_free(ctx(), ds);  // stream-ordered: released after the queued kernels have read them
+            sys::tkm_dev_free(ctx(), di);
+            check(st);
+        }
+        PendingG1 { ticket }
+    }
+}
+
+/// A queued commitment or MSM (tkm_poly_commit_begin, tkm_msm_g1_begin, tkm_msm_g1_indexed_begin).
+pub struct PendingG1 { ticket: i32 }
+impl PendingG1 {
+    pub fn get(self) -> G1serde {
+        let mut out = G1serde::zero();
+        check(unsafe { sys::tkm_commit_end(ctx(), self.ticket, out.0.as_mut_ptr()) });
+        out
+    }
 }
