@@ -543,10 +543,10 @@ def main():
                      note="one operand read (twice, second time from L2), result 16384x512", muls_per_elem=2, elems=npts)
             timed_op("k_axpby (p + q)", lambda: pa + pb, 3 * npts * 32)
             timed_op("k_scale_coeffs (scale_coeffs_x)", lambda: pa.scale_coeffs_x(sc[0]), 2 * npts * 32, muls_per_elem=1, elems=npts)
-            timed_op("k_row_dot/k_col_dot (eval at a point)", lambda: pa.eval(sc[0], sc[1]), npts * 32)
+            timed_op("k_eval_partial + k_sum_partials (eval at a point)", lambda: pa.eval(sc[0], sc[1]), npts * 32)
             timed_op("k_vanish_qy/_qx (div_by_vanishing_opt c=4096 d=256)", lambda: pa.clone().div_by_vanishing_opt(4096, 256), (1 + 2 + 1 + 1) * npts * 32,
                      note="includes the clone (the reference's &mut self): read+write clone, read, write Q_X, Q_Y/B traffic ~ N")
-            timed_op("k_ruffini_x/_y (div_by_ruffini)", lambda: pa.div_by_ruffini(sc[0], sc[1]), 2 * npts * 32)
+            timed_op("k_ruffini_seg_* + k_ruffini_y_scan (div_by_ruffini)", lambda: pa.div_by_ruffini(sc[0], sc[1]), 2 * npts * 32)
             d_t0, d_t1 = ctx.dev_alloc(npts * 32), ctx.dev_alloc(npts * 32)
             T.check(lib.tkm_fr_vec_fill(h, T.fr_bytes(5)[1], d_t0, npts))
             timed_op("k_transpose (4096 x 1024)", lambda: ctx.transpose_dev(d_t0, d_t1, 4096, 1024), 2 * npts * 32)
