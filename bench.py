@@ -57,9 +57,19 @@ def bench_config(log_n, world):
             "l2": "inputs (0.5 GiB) larger than the 126 MB L2"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-# (profiles/r01_ncu_k_accumulate_summary.csv: 2^22-point MSM; profiles/r01_ncu_k_ntt_pass_summary.csv: 16384 x 512 forward)
-NCU_TRAFFIC = {"k_accumulate": 11.913, "k_ntt_pass_x3": 1.464}
+# dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full captures of a 2^22-point MSM and a 16384 x 512
+# forward transform (profiles/r02_ncu_k_tree_apply_summary.csv, r02_ncu_k_tree_fwd_summary.csv, r02_ncu_k_accumulate_summary.csv,
+# r02_ncu_k_ntt_pass_summary.csv).  tree_level0: both halves of k_tree_fwd (4.489 + 4.049 GB) and k_tree_apply (8.713 + 7.866 GB) at
+# level 0, 67.1 M digit entries; the deeper levels were not captured and are scaled by their entry counts.
+NCU_TRAFFIC = {"tree_level0": 25.117, "tree_level0_entries": 67.1e6, "k_accumulate_tail": 0.552, "k_ntt_pass_x3": 1.464}
+
+
+def accumulation_traffic_gb(detail):
+    """DRAM traffic of one accumulation phase from the level-0 capture: a level's passes move bytes in proportion to its entries."""
+    e = detail.get("entries_per_level") or []
+    if len(e) < 2:
+        return None  # no pair tree in this MSM: nothing captured for the chained form this round
+    return NCU_TRAFFIC["tree_level0"] * sum(e[:-1]) / NCU_TRAFFIC["tree_level0_entries"] + NCU_TRAFFIC["k_accumulate_tail"]
 
 
 def msm_windows(n):
@@ -447,7 +457,8 @@ def main():
                 ach = work / (acc_ms * 1e-3)
                 peak = max(imad_wide, imad_wide_x)
                 line["roofline"] = {"bound": "int32", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T(32x32+64 IMAD.WIDE)/s", "frac": ach / peak,
-                                    "traffic": NCU_TRAFFIC["k_accumulate"], "traffic_unit": "GB per launch (dram read+write, ncu --set full capture in profiles/)",
+                                    "traffic": accumulation_traffic_gb(detail), "traffic_unit": "GB per accumulation phase (dram read+write: level-0 tree launches and the XYZZ pass from the ncu --set full "
+                                    "captures in profiles/, deeper levels scaled by their entry counts); the pair tree trades bytes for multiplications: ~400 B per addition against 104 B for the chained form",
                                     "algorithmic_gb": adds * 104 / 1e9, "kernel": "accumulation phase: k_tree_fwd/k_tree_apply per level + k_accumulate", "kernel_ms": acc_ms,
                                     "kernel_share_of_step": acc_ms / ms_res, "work": detail,
                                     "note": "MSM is integer-pipe bound (SURVEY.md 8d; the schema's hbm/tensor bounds do not describe it): issued wide IMADs of the "
