@@ -85,6 +85,19 @@ def test_r1cs_reader_on_the_reference_library():
         assert getattr(mine, k) == ref[k], k
 
 
+def test_sparse_scalar_tables():
+    """frs_sparse (the prover's vanishing / unit-vector / blinding tables without a Python loop over their zeros) against
+    frs_from_ints on the dense list, values reduced mod r, later entries overriding nothing else."""
+    import numpy as np
+
+    from tokamak_b200 import frs_from_ints, frs_sparse
+
+    dense = [0] * 64
+    dense[0], dense[7], dense[63] = fr.R_MOD - 1, 5, (1 << 255) % fr.R_MOD
+    assert np.array_equal(frs_sparse(64, {0: -1, 7: 5, 63: 1 << 255}), frs_from_ints(dense))
+    assert not frs_sparse(8, {}).any()
+
+
 def test_packed_real_library_fixture():
     """tests/golden/real_library.json.xz (the reference's circuit library packed by tests/golden/gen_real_library.py): shapes
     of setupParams.json / subcircuitInfo.json, and -- where the reference tree is present -- every constraint equal to the
